@@ -1,0 +1,168 @@
+/*
+ * mcmcgpu.h -- C ABI of libmcmcgpu.so, the B200 (sm_100a) many-chain engine for the MCMC.jl hot path.
+ *
+ * The reference (dingliumath/MCMC.jl) has no FFI layer: its extension surface is Julia multiple
+ * dispatch.  Each entry point below states the reference interface (file:line under the reference
+ * tree) it stands in for; the Julia-side `ccall` binding a maintainer would add is in
+ * INTEGRATION.md and mcmc.jl_b200/julia/GPUMC.jl.
+ *
+ * Conventions
+ *  - every function returns int32 status: 0 ok, <0 error (MCMCGPU_E_*); mcmcgpu_last_error() gives
+ *    the message (library-owned, valid until the next call on the same thread).
+ *  - the host owns every input and output buffer; the library copies inputs at *_create time and
+ *    fills caller-allocated outputs.  Only opaque handles cross the boundary.
+ *  - arrays are dense, column-major Float64 (Julia native); sizes int64; flags uint8.
+ *  - calls are blocking; one host thread per context.  One context == one GPU (one process per GPU).
+ *  - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    MCMCGPU_E_CUDA.
+ */
+#ifndef MCMCGPU_H
+#define MCMCGPU_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCMCGPU_ABI_VERSION 1
+
+/* status codes */
+#define MCMCGPU_OK 0
+#define MCMCGPU_E_ARG (-1)       /* bad argument (maps the reference's ctor assertions)              */
+#define MCMCGPU_E_SUPPORT (-2)   /* "Initial values out of model support" RWM.jl:55 MALA.jl:85 HMC.jl:121 HMCDA.jl:88 likmodel.jl:54 */
+#define MCMCGPU_E_NOGRAD (-3)    /* gradient sampler on a gradient-less model MALA.jl:72 HMC.jl:111 HMCDA.jl:79 */
+#define MCMCGPU_E_CUDA (-4)      /* CUDA / device failure, or no device                               */
+#define MCMCGPU_E_COMM (-5)      /* NCCL failure / not initialised                                    */
+#define MCMCGPU_E_STATE (-6)     /* call out of order (e.g. fetch before execute)                     */
+
+/* likelihood families: the GPU registry behind model() (src/modellers/mcmcmodels.jl:27-33,
+ * src/modellers/likmodel.jl:100-143); formulas from README.md:60-72 and examples/ */
+#define MCMCGPU_FAM_NORMAL_FN 0  /* README.md:60,63  v -> -dot(v,v), grad -2v                          */
+#define MCMCGPU_FAM_NORMAL_DSL 1 /* README.md:67-72  v ~ Normal(mu, sigma)     hyper = {mu, sigma}     */
+#define MCMCGPU_FAM_LINEAR 2     /* examples/linear_regression.jl:14-18        hyper = {prior_sd, noise_sd} */
+#define MCMCGPU_FAM_LOGISTIC 3   /* examples/logistic_regression.jl:16-20      hyper = {prior_sd, sign}  (sign -1: exp(-X*b); +1: test/test_syntax.jl:18) */
+#define MCMCGPU_FAM_PROBIT 4     /* examples/probit_regression.jl:18-41        hyper = {prior_sd}        */
+#define MCMCGPU_FAM_OU 5         /* examples/ornstein.jl:19-27                 hyper = {tau_hi, sigma_hi, mu_hi}; y = series, d = 3 */
+
+/* samplers: src/samplers/RWM.jl:24-36, MALA.jl:50-62, HMC.jl:53-74, HMCDA.jl:24-43 */
+#define MCMCGPU_RWM 0
+#define MCMCGPU_MALA 1
+#define MCMCGPU_HMC 2
+#define MCMCGPU_HMCDA 3
+
+/* engines */
+#define MCMCGPU_ENGINE_AUTO 0
+#define MCMCGPU_ENGINE_FUSED 1   /* whole chain in one per-chain kernel (closed-form families)       */
+#define MCMCGPU_ENGINE_WAVE 2    /* one gradient evaluation for every chain per wave (K1 + transition) */
+
+/* variance estimators src/stats/var.jl:137-166 */
+#define MCMCGPU_VAR_IID 0
+#define MCMCGPU_VAR_BM 1
+#define MCMCGPU_VAR_IMSE 2
+#define MCMCGPU_VAR_IPSE 3
+
+typedef struct mcmcgpu_ctx mcmcgpu_ctx;
+typedef struct mcmcgpu_model mcmcgpu_model;
+typedef struct mcmcgpu_run mcmcgpu_run;
+
+/* sampler parameters; mirrors the reference constructors' fields */
+typedef struct {
+  int32_t kind;        /* MCMCGPU_RWM | MALA | HMC | HMCDA                                           */
+  int32_t nleaps;      /* HMC.nLeaps   (HMC.jl:54)                                                   */
+  double scale;        /* RWM.scale (RWM.jl:25) | MALA.driftStep (MALA.jl:51) | HMC.leapStep (HMC.jl:55) */
+  double rate, len, shrinkage, t0, step; /* HMCDA fields HMCDA.jl:25-29                              */
+  int64_t max_leaps;   /* cap on HMCDA nLeaps = max(1, round(len/leapStep)) (HMCDA.jl:104); 0 = library default 1<<20 */
+  int32_t tuner_on;    /* EmpMCTuner attached (samplers.jl:32-50); MALA/HMC only                     */
+  int32_t adapt_step, max_step;
+  double target_path, target_rate;
+} mcmcgpu_sampler_cfg;
+
+/* runner parameters: SerialMC's range (src/runners/SerialMC.jl:12-35) + the many-chain additions */
+typedef struct {
+  int64_t first, step, last; /* kept steps first:step:last; burnin = first-1, len = last            */
+  int64_t nchains;           /* chains run by THIS context                                           */
+  int64_t chain_offset;      /* global id of this context's first chain (Philox key; chain sharding) */
+  uint64_t seed;
+  int32_t init_per_chain;    /* 0: init is d (shared); 1: init is d x nchains                         */
+  int32_t store_grad;        /* keep pgrads (SerialMC.jl:51-53)                                       */
+  int32_t store_logtarget;   /* keep plogtarget of every kept sample                                   */
+  int32_t engine;            /* MCMCGPU_ENGINE_*                                                       */
+} mcmcgpu_runner_cfg;
+
+typedef struct {
+  double gpu_ms;          /* device time of the sampling loop (CUDA events on the library stream)   */
+  int64_t n_grad_evals;   /* log-target(+gradient) evaluations summed over chains                   */
+  int64_t n_waves;        /* wave-engine iterations (0 for the fused engine)                        */
+  int64_t n_launches;     /* kernels launched by the library during execute                         */
+  double eval_ms;         /* device time spent in the likelihood kernel (wave engine)               */
+} mcmcgpu_run_info;
+
+/* ---- context ---- */
+int32_t mcmcgpu_abi_version(void);
+const char* mcmcgpu_last_error(void);
+/* one context per GPU / process. device_id < 0: current device. */
+int32_t mcmcgpu_init(int32_t device_id, mcmcgpu_ctx** out);
+int32_t mcmcgpu_destroy(mcmcgpu_ctx* ctx);
+/* use a caller-owned CUDA stream (cudaStream_t as void*) for all launches and copies; NULL = library stream */
+int32_t mcmcgpu_set_stream(mcmcgpu_ctx* ctx, void* cuda_stream);
+/* engine options: "time_eval" (1: time every likelihood launch with CUDA events -> run_info.eval_ms),
+ * "poll_every" (waves between completion polls for HMCDA / tuned HMC), "force_splits" (K1 row splits) */
+int32_t mcmcgpu_set_option(mcmcgpu_ctx* ctx, const char* key, int64_t value);
+/* row-sharded tall data: NCCL communicator over the ranks holding the row shards.
+ * unique_id is the 128-byte ncclUniqueId produced by mcmcgpu_comm_unique_id on rank 0. */
+int32_t mcmcgpu_comm_unique_id(void* out128);
+int32_t mcmcgpu_comm_init(mcmcgpu_ctx* ctx, int32_t rank, int32_t nranks, const void* unique_id128);
+
+/* ---- model: stands in for model(...) -> MCMCLikelihoodModel (likmodel.jl:20-58,100-143) ----
+ * X: N x d column-major (NULL for Normal/OU), y: N (NULL for Normal).  With a communicator and
+ * row_sharded != 0, X/y are THIS rank's rows and the prior is added once after the all-reduce. */
+int32_t mcmcgpu_model_create(mcmcgpu_ctx* ctx, int32_t family, int64_t N, int64_t d, const double* X,
+                             const double* y, const double* hyper, int32_t nhyper, int32_t row_sharded,
+                             mcmcgpu_model** out);
+int32_t mcmcgpu_model_destroy(mcmcgpu_model* m);
+
+/* model.eval / model.evalallg for C parameter vectors at once (likmodel.jl:21,25).
+ * B: d x C; out_lt: C; out_grad: d x C or NULL (eval only). */
+int32_t mcmcgpu_logtarget_grad(mcmcgpu_model* m, const double* B, int64_t C, double* out_lt, double* out_grad);
+
+/* ---- run: stands in for run(model * sampler * runner) (runners.jl:7-32, SerialMC.jl:37-85) ----
+ * init: d or d x nchains; scale: d (model.scale, likmodel.jl:30) or NULL = ones;
+ * inj_normals: NULL (Philox) or d x (last+1) x nchains [column 0 = pre-loop draw, HMCDA.jl:90];
+ * inj_uniforms: NULL or (last+1) x nchains.
+ * outputs (NULL = not wanted): samples d x S x nchains, grads d x S x nchains (NaN for RWM,
+ * SerialMC.jl:42), accept S x nchains, logtarget S x nchains, S = length(first:step:last). */
+int32_t mcmcgpu_run_chains(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r,
+                           const double* init, const double* scale, const double* inj_normals,
+                           const double* inj_uniforms, double* out_samples, double* out_grads,
+                           uint8_t* out_accept, double* out_logtarget, mcmcgpu_run_info* info);
+
+/* split form: inputs resident in HBM after create; execute may be timed alone; results stay on the device */
+int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r,
+                           const double* init, const double* scale, const double* inj_normals,
+                           const double* inj_uniforms, mcmcgpu_run** out);
+int32_t mcmcgpu_run_execute(mcmcgpu_run* run, mcmcgpu_run_info* info);
+int32_t mcmcgpu_run_fetch(mcmcgpu_run* run, double* out_samples, double* out_grads, uint8_t* out_accept,
+                          double* out_logtarget);
+/* per-chain diagnostics: final leap step (HMCDA/tuned), kept-step leap steps (S x nchains) and leap counts */
+int32_t mcmcgpu_run_fetch_diag(mcmcgpu_run* run, double* out_eps, int64_t* out_nleaps);
+/* src/stats on the device-resident draws: outputs d x nchains each (NULL = skip).
+ * mean (mean.jl:6), var_iid (var.jl:7-8), var (vtype: var.jl:137-166), ess / actime (ess.jl:6-19),
+ * accept_rate nchains in percent (summary.jl:6-15).  maxlag < 0: S-1; batchlen <= 0: 100. */
+int32_t mcmcgpu_run_stats(mcmcgpu_run* run, int32_t vtype, int64_t maxlag, int64_t batchlen, double* out_mean,
+                          double* out_var_iid, double* out_var, double* out_ess, double* out_actime,
+                          double* out_accept_rate);
+int32_t mcmcgpu_run_destroy(mcmcgpu_run* run);
+
+/* src/stats from host draws: samples d x S x C (the layout mcmcgpu_run_chains fills) */
+int32_t mcmcgpu_stats(mcmcgpu_ctx* ctx, const double* samples, int64_t S, int64_t d, int64_t C, int32_t vtype,
+                      int64_t maxlag, int64_t batchlen, double* out_mean, double* out_var_iid, double* out_var,
+                      double* out_ess, double* out_actime);
+
+/* the engine's own draws, for draw-matched replay through another implementation:
+ * normals d x (last+1) x nchains and uniforms (last+1) x nchains exactly as the samplers consume them */
+int32_t mcmcgpu_philox_draws(mcmcgpu_ctx* ctx, uint64_t seed, int64_t chain_offset, int64_t nchains, int64_t d,
+                             int64_t last, double* out_normals, double* out_uniforms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,113 @@
+// common.cuh -- shared device helpers of libmcmcgpu: Philox4x32-10 draws, family formulas, layouts.
+// All sampler arithmetic is FP64 and written in the reference's operation order; the
+// translation units that include the sampler code are compiled with -fmad=false so that no
+// multiply-add is contracted (bit-level agreement with the CPU restatement on closed-form targets).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "../../include/mcmcgpu.h"
+
+#define MG_LOG2PI 1.8378770664093453
+#define MG_LN_SQRT_2PI 0.91893853320467274178
+#define MG_TWO_PI 6.283185307179586
+#define MG_SQRT1_2 0.70710678118654752440
+
+namespace mg {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11).  Engine convention: key = (seed lo, seed hi);
+// counter = (chain lo, chain hi, step, block).  Normal block b gives normals 2b and 2b+1
+// (Box-Muller); block 0xFFFFFFFF gives the uniform of the Metropolis test.  Step 0 is the
+// pre-loop draw of HMCDA (HMCDA.jl:90).
+// ---------------------------------------------------------------------------------------------
+struct u4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ u4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                     uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+#ifdef __CUDA_ARCH__
+    uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0, hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+#else
+    uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+#endif
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  u4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+  return o;
+}
+
+// 53-bit uniform in (0,1), exact in binary64
+__host__ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
+  uint64_t b = (((uint64_t)hi << 21) ^ ((uint64_t)lo >> 11)) & ((1ull << 53) - 1);
+  return ((double)b + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t chain, uint32_t step, uint32_t block,
+                                                   double& z0, double& z1) {
+  u4 o = philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), step, block, (uint32_t)seed, (uint32_t)(seed >> 32));
+  double u1 = u01(o.x, o.y), u2 = u01(o.z, o.w);
+  double r = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  z0 = r * c; z1 = r * s;
+}
+__device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t chain, uint32_t step) {
+  u4 o = philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), step, 0xFFFFFFFFu, (uint32_t)seed, (uint32_t)(seed >> 32));
+  return u01(o.x, o.y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar log-densities (Distributions.jl 2013 == Rmath dnorm4 / dunif / pnorm log scale)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double logpdf_normal(double x, double mu, double sigma) {
+  double z = (x - mu) / sigma;
+  return -(MG_LN_SQRT_2PI + 0.5 * z * z + log(sigma));
+}
+__device__ __forceinline__ double logpdf_uniform(double x, double a, double b) {
+  return (a <= x && x <= b) ? -log(b - a) : -CUDART_INF;
+}
+// log Phi(x): logcdf(Normal(), x) of examples/probit_regression.jl:29
+__device__ __forceinline__ double log_ndtr(double x) {
+  if (x > 0.0) return log1p(-0.5 * erfc(x * MG_SQRT1_2));
+  if (x > -37.0) return log(0.5 * erfc(-x * MG_SQRT1_2));
+  double x2 = x * x, r = 1.0 / x2;
+  double s = 1.0 - r * (1.0 - 3.0 * r * (1.0 - 5.0 * r * (1.0 - 7.0 * r * (1.0 - 9.0 * r))));
+  return -0.5 * x2 - MG_LN_SQRT_2PI - log(-x) + log(s);
+}
+
+// in(i, first:step:last)  (SerialMC.jl:49) and the kept index
+__host__ __device__ __forceinline__ bool in_range(int64_t i, int64_t first, int64_t step, int64_t last) {
+  return i >= first && i <= last && ((i - first) % step) == 0;
+}
+
+// model description as the kernels see it
+struct ModelDev {
+  int32_t family;
+  int64_t N, d;
+  double hyper[4];
+  const double* series;  // OU: x[0..N-1] on the device
+};
+
+// sampler + runner description as the kernels see it
+struct SamplerDev {
+  int32_t kind, nleaps;
+  double scale, rate, len, shrinkage, t0, step;
+  int64_t max_leaps;
+  int32_t tuner_on, adapt_step, max_step;
+  double target_path, target_rate;
+};
+struct RunnerDev {
+  int64_t first, step, last, S;
+  int64_t C, Cp;          // chains, padded chain count (array pitch)
+  int64_t chain_offset;
+  uint64_t seed;
+  int32_t init_per_chain, store_grad, store_lt;
+};
+
+}  // namespace mg

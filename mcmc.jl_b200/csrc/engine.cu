@@ -1,0 +1,749 @@
+// engine.cu -- host side of libmcmcgpu.so: the C ABI of include/mcmcgpu.h (contexts, models, runs).
+// No CPU fallback exists: every compute entry point needs a CUDA device and fails with
+// MCMCGPU_E_CUDA otherwise.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "fused_chain.h"
+#include "k1_regress.h"
+#include "nccl_dyn.h"
+#include "stats.h"
+#include "transition.h"
+
+using namespace mg;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(x)                                                                                      \
+  do {                                                                                             \
+    cudaError_t e__ = (x);                                                                         \
+    if (e__ != cudaSuccess)                                                                        \
+      return fail(MCMCGPU_E_CUDA, std::string("CUDA: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+struct mcmcgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  NcclComm comm = nullptr;
+  int rank = 0, nranks = 1;
+  int64_t time_eval = 0;      // option: time every likelihood launch with events
+  int64_t poll_every = 8;     // option: waves between completion polls (HMCDA / tuned HMC)
+  int64_t force_splits = 0;   // option: override K1 row splits
+  int32_t* h_remaining = nullptr;  // pinned
+};
+
+struct mcmcgpu_model {
+  mcmcgpu_ctx* ctx = nullptr;
+  int family = 0;
+  int64_t N = 0, d = 0;
+  double hyper[4] = {0, 0, 0, 0};
+  double k1_hyper[4] = {0, 0, 0, 0};
+  double* d_series = nullptr;
+  K1Pack pack;
+  bool is_regression = false;
+  bool row_sharded = false;
+  ModelDev dev() const {
+    ModelDev M; M.family = family; M.N = N; M.d = d;
+    for (int i = 0; i < 4; i++) M.hyper[i] = hyper[i];
+    M.series = d_series;
+    return M;
+  }
+};
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)); }
+
+struct mcmcgpu_run {
+  mcmcgpu_model* m = nullptr;
+  mcmcgpu_sampler_cfg s;
+  mcmcgpu_runner_cfg r;
+  int engine = 0;
+  int64_t C = 0, Cp = 0, S = 0, d = 0;
+  bool executed = false;
+  bool has_diag = false;
+  // inputs
+  double *init = nullptr, *scale = nullptr, *inj_normals = nullptr, *inj_uniforms = nullptr;
+  // outputs
+  double *samples = nullptr, *grads = nullptr, *logtarget = nullptr, *eps = nullptr, *final_eps = nullptr;
+  uint8_t* accept = nullptr;
+  int32_t *nleaps = nullptr, *status = nullptr;
+  unsigned long long* n_evals = nullptr;
+  // wave state
+  double *q = nullptr, *part = nullptr, *red = nullptr, *cur_pars = nullptr, *cur_grad = nullptr, *cur_lt = nullptr,
+         *mom = nullptr, *H0 = nullptr, *eps_cur = nullptr, *da_leapstep = nullptr, *da_dual = nullptr, *da_dualH = nullptr,
+         *tn_step = nullptr;
+  int32_t *phase = nullptr, *leap = nullptr, *nleaps_cur = nullptr, *remaining = nullptr;
+  int64_t *istep = nullptr, *kept = nullptr, *tn_nleaps = nullptr, *tn_acc = nullptr, *tn_prop = nullptr;
+  uint8_t* need_ll = nullptr;
+  int nsplit = 1;
+  std::vector<void*> owned;
+  template <typename T>
+  cudaError_t alloc(T** p, size_t n, bool zero = true) {
+    cudaError_t e = dalloc(p, n);
+    if (e != cudaSuccess) return e;
+    owned.push_back((void*)*p);
+    if (zero) return cudaMemsetAsync(*p, 0, sizeof(T) * (n ? n : 1), m->ctx->stream);
+    return cudaSuccess;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int32_t mcmcgpu_abi_version(void) { return MCMCGPU_ABI_VERSION; }
+const char* mcmcgpu_last_error(void) { return g_err.c_str(); }
+
+int32_t mcmcgpu_init(int32_t device_id, mcmcgpu_ctx** out) {
+  if (!out) return fail(MCMCGPU_E_ARG, "out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(MCMCGPU_E_CUDA, std::string("no CUDA device available (libmcmcgpu has no CPU fallback): ") +
+                                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device_id < 0) CU(cudaGetDevice(&device_id));
+  if (device_id >= n) return fail(MCMCGPU_E_ARG, "device_id out of range");
+  CU(cudaSetDevice(device_id));
+  mcmcgpu_ctx* c = new mcmcgpu_ctx();
+  c->device = device_id;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CU(cudaMallocHost((void**)&c->h_remaining, sizeof(int32_t)));
+  *out = c;
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_destroy(mcmcgpu_ctx* c) {
+  if (!c) return MCMCGPU_OK;
+  cudaSetDevice(c->device);
+  if (c->comm) { const NcclApi* api = nccl_api(nullptr); if (api) api->CommDestroy(c->comm); }
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->h_remaining) cudaFreeHost(c->h_remaining);
+  delete c;
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_set_stream(mcmcgpu_ctx* c, void* cuda_stream) {
+  if (!c) return fail(MCMCGPU_E_ARG, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+  else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_set_option(mcmcgpu_ctx* c, const char* key, int64_t value) {
+  if (!c || !key) return fail(MCMCGPU_E_ARG, "ctx/key is NULL");
+  std::string k(key);
+  if (k == "time_eval") c->time_eval = value;
+  else if (k == "poll_every") c->poll_every = value < 1 ? 1 : value;
+  else if (k == "force_splits") c->force_splits = value;
+  else return fail(MCMCGPU_E_ARG, "unknown option " + k);
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_comm_unique_id(void* out128) {
+  const char* err = nullptr;
+  const NcclApi* api = nccl_api(&err);
+  if (!api) return fail(MCMCGPU_E_COMM, err ? err : "NCCL unavailable");
+  NcclUniqueId id;
+  int rc = api->GetUniqueId(&id);
+  if (rc != 0) return fail(MCMCGPU_E_COMM, std::string("ncclGetUniqueId: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+  memcpy(out128, &id, sizeof(id));
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_comm_init(mcmcgpu_ctx* c, int32_t rank, int32_t nranks, const void* unique_id128) {
+  if (!c || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(MCMCGPU_E_ARG, "bad comm arguments");
+  const char* err = nullptr;
+  const NcclApi* api = nccl_api(&err);
+  if (!api) return fail(MCMCGPU_E_COMM, err ? err : "NCCL unavailable");
+  CU(cudaSetDevice(c->device));
+  NcclUniqueId id;
+  memcpy(&id, unique_id128, sizeof(id));
+  int rc = api->CommInitRank(&c->comm, nranks, id, rank);
+  if (rc != 0) return fail(MCMCGPU_E_COMM, std::string("ncclCommInitRank: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+  c->rank = rank; c->nranks = nranks;
+  return MCMCGPU_OK;
+}
+
+// ---- model ---------------------------------------------------------------------------------------
+int32_t mcmcgpu_model_create(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t d, const double* X, const double* y,
+                             const double* hyper, int32_t nhyper, int32_t row_sharded, mcmcgpu_model** out) {
+  if (!c || !out) return fail(MCMCGPU_E_ARG, "ctx/out is NULL");
+  if (d < 1) return fail(MCMCGPU_E_ARG, "d must be >= 1");
+  if (nhyper < 0 || nhyper > 4 || (nhyper > 0 && !hyper)) return fail(MCMCGPU_E_ARG, "bad hyper");
+  CU(cudaSetDevice(c->device));
+  mcmcgpu_model* m = new mcmcgpu_model();
+  m->ctx = c; m->family = family; m->N = N; m->d = d;
+  for (int i = 0; i < nhyper; i++) m->hyper[i] = hyper[i];
+  switch (family) {
+    case MCMCGPU_FAM_NORMAL_FN: m->N = 0; break;
+    case MCMCGPU_FAM_NORMAL_DSL:
+      m->N = 0;
+      if (nhyper < 2) { m->hyper[0] = 0.0; m->hyper[1] = 1.0; }
+      if (!(m->hyper[1] > 0)) { delete m; return fail(MCMCGPU_E_ARG, "Normal sigma must be > 0"); }
+      break;
+    case MCMCGPU_FAM_LINEAR:
+      if (nhyper < 1) m->hyper[0] = 1.0;
+      if (nhyper < 2) m->hyper[1] = 1.0;
+      m->is_regression = true; break;
+    case MCMCGPU_FAM_LOGISTIC:
+      if (nhyper < 1) m->hyper[0] = 1.0;
+      if (nhyper < 2) m->hyper[1] = -1.0;
+      m->is_regression = true; break;
+    case MCMCGPU_FAM_PROBIT:
+      if (nhyper < 1) m->hyper[0] = 10.0;
+      m->is_regression = true; break;
+    case MCMCGPU_FAM_OU:
+      if (d != 3) { delete m; return fail(MCMCGPU_E_ARG, "Ornstein-Uhlenbeck has 3 parameters (tau, sigma, mu)"); }
+      if (nhyper < 3) { m->hyper[0] = 100.0; m->hyper[1] = 2.0; m->hyper[2] = 20.0; }
+      if (!y || N < 2) { delete m; return fail(MCMCGPU_E_ARG, "OU needs a series of length >= 2 in y"); }
+      break;
+    default: delete m; return fail(MCMCGPU_E_ARG, "unknown family");
+  }
+  if (m->is_regression) {
+    if (!X || !y || N < 1) { delete m; return fail(MCMCGPU_E_ARG, "regression families need X (N x d) and y (N)"); }
+    if (!(m->hyper[0] > 0)) { delete m; return fail(MCMCGPU_E_ARG, "prior sd must be > 0"); }
+    if (!k1_supported(d)) { delete m; return fail(MCMCGPU_E_ARG, "regression families support 1 <= d <= 104 in this build"); }
+    if (row_sharded && !c->comm) { delete m; return fail(MCMCGPU_E_COMM, "row_sharded model needs mcmcgpu_comm_init first"); }
+    m->row_sharded = row_sharded != 0;
+    double *dX = nullptr, *dy = nullptr;
+    CU(dalloc(&dX, (size_t)(N * d)));
+    CU(dalloc(&dy, (size_t)N));
+    CU(cudaMemcpyAsync(dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(dy, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
+    CU(k1_pack(m->pack, dX, dy, N, d, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dX); cudaFree(dy);
+    for (int i = 0; i < 4; i++) m->k1_hyper[i] = m->hyper[i];
+    if (family == MCMCGPU_FAM_LINEAR) m->k1_hyper[3] = std::log(m->hyper[1]);
+  }
+  if (family == MCMCGPU_FAM_OU) {
+    CU(dalloc(&m->d_series, (size_t)N));
+    CU(cudaMemcpyAsync(m->d_series, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  *out = m;
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_model_destroy(mcmcgpu_model* m) {
+  if (!m) return MCMCGPU_OK;
+  cudaSetDevice(m->ctx->device);
+  k1_free(m->pack);
+  if (m->d_series) cudaFree(m->d_series);
+  delete m;
+  return MCMCGPU_OK;
+}
+
+}  // extern "C"
+
+// one evaluation of every chain at q -> part (and the all-reduce for row-sharded models)
+static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* red, int nsplit, int64_t C, int64_t Cp,
+                     bool need_grad, const uint8_t* need_ll, const int32_t* phase, const int32_t* remaining,
+                     const double** part_out, int* nsplit_out) {
+  cudaStream_t st = m->ctx->stream;
+  *part_out = part; *nsplit_out = nsplit;
+  if (m->is_regression) {
+    K1Args a;
+    a.P = m->pack; a.family = m->family;
+    for (int i = 0; i < 4; i++) a.hyper[i] = m->k1_hyper[i];
+    a.q = q; a.part = part; a.Cp = Cp; a.nsplit = nsplit; a.need_grad = need_grad ? 1 : 0;
+    a.need_ll = need_ll; a.phase = phase; a.remaining = remaining;
+    CU(k1_launch(a, st));
+    if (m->row_sharded) {
+      const NcclApi* api = nccl_api(nullptr);
+      if (!api || !m->ctx->comm) return fail(MCMCGPU_E_COMM, "communicator not initialised");
+      CU(launch_reduce_splits(part, nsplit, m->d + 2, Cp, red, st));
+      int rc = api->AllReduce(red, red, (size_t)((m->d + 2) * Cp), NCCL_FLOAT64, NCCL_SUM, m->ctx->comm, st);
+      if (rc != 0) return fail(MCMCGPU_E_COMM, std::string("ncclAllReduce: ") + (api->GetErrorString ? api->GetErrorString(rc) : "error"));
+      *part_out = red; *nsplit_out = 1;
+    }
+  } else {
+    CU(launch_eval_closed(m->dev(), q, part, C, Cp, phase, remaining, st));
+    *nsplit_out = 1;
+  }
+  return MCMCGPU_OK;
+}
+
+static int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+extern "C" {
+
+int32_t mcmcgpu_logtarget_grad(mcmcgpu_model* m, const double* B, int64_t C, double* out_lt, double* out_grad) {
+  if (!m || !B || !out_lt || C < 1) return fail(MCMCGPU_E_ARG, "bad arguments");
+  mcmcgpu_ctx* c = m->ctx;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int64_t d = m->d, Cp = round_up(C, K1_CHAINS);
+  int nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp)) : 1;
+  double *hB = nullptr, *q = nullptr, *part = nullptr, *red = nullptr, *lt = nullptr, *grad = nullptr, *gout = nullptr;
+  CU(dalloc(&hB, (size_t)(C * d)));
+  CU(dalloc(&q, (size_t)(d * Cp)));
+  CU(dalloc(&part, (size_t)(nsplit * (d + 2) * Cp)));
+  CU(dalloc(&red, (size_t)((d + 2) * Cp)));
+  CU(dalloc(&lt, (size_t)Cp));
+  CU(dalloc(&grad, (size_t)(d * Cp)));
+  CU(dalloc(&gout, (size_t)(C * d)));
+  CU(cudaMemsetAsync(q, 0, sizeof(double) * (size_t)(d * Cp), st));
+  CU(cudaMemcpyAsync(hB, B, sizeof(double) * (size_t)(C * d), cudaMemcpyHostToDevice, st));
+  CU(transpose_to_chain_minor(hB, q, C, d, Cp, st));
+  const double* pp; int ns;
+  int rc = eval_wave(m, q, part, red, nsplit, C, Cp, out_grad != nullptr, nullptr, nullptr, nullptr, &pp, &ns);
+  if (rc != MCMCGPU_OK) return rc;
+  CU(launch_finalize(m->dev(), q, pp, ns, C, Cp, lt, out_grad ? grad : nullptr, st));
+  CU(cudaMemcpyAsync(out_lt, lt, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
+  if (out_grad) {
+    CU(transpose_to_chain_major(grad, gout, 0, C, d, Cp, st));
+    CU(cudaMemcpyAsync(out_grad, gout, sizeof(double) * (size_t)(C * d), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  cudaFree(hB); cudaFree(q); cudaFree(part); cudaFree(red); cudaFree(lt); cudaFree(grad); cudaFree(gout);
+  return MCMCGPU_OK;
+}
+
+// ---- run -----------------------------------------------------------------------------------------
+static int check_cfg(const mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r) {
+  // SerialMC.jl:25-27
+  if (r->first - 1 < 0) return fail(MCMCGPU_E_ARG, "Burnin rounds should be >= 0");
+  if (r->last <= r->first - 1) return fail(MCMCGPU_E_ARG, "Total MCMC length should be > to burnin");
+  if (r->step < 1) return fail(MCMCGPU_E_ARG, "Thinning should be >= 1");
+  if (r->nchains < 1) return fail(MCMCGPU_E_ARG, "nchains must be >= 1");
+  if (r->last >= (1LL << 32) - 1) return fail(MCMCGPU_E_ARG, "at most 2^32-2 steps");
+  switch (s->kind) {
+    case MCMCGPU_RWM: if (!(s->scale > 0)) return fail(MCMCGPU_E_ARG, "scale should be > 0"); break;             // RWM.jl:29
+    case MCMCGPU_MALA: if (!(s->scale > 0)) return fail(MCMCGPU_E_ARG, "MALA drift step should be > 0"); break;   // MALA.jl:55
+    case MCMCGPU_HMC:
+      if (s->nleaps <= 0) return fail(MCMCGPU_E_ARG, "inner steps should be > 0");                                // HMC.jl:60
+      if (!(s->scale > 0)) return fail(MCMCGPU_E_ARG, "inner steps scaling should be > 0");                       // HMC.jl:61
+      break;
+    case MCMCGPU_HMCDA:                                                                                           // HMCDA.jl:33-36
+      if (!(s->rate > 0 && s->rate < 1)) return fail(MCMCGPU_E_ARG, "Target acceptance rate should be between 0 and 1");
+      if (!(s->len > 0)) return fail(MCMCGPU_E_ARG, "len parameter of HMCDA sampler must be non-negative");
+      if (!(s->shrinkage > 0)) return fail(MCMCGPU_E_ARG, "shrinkage parameter of HMCDA sampler must be positive");
+      if (!(s->t0 >= 0)) return fail(MCMCGPU_E_ARG, "t0 parameter of HMCDA sampler must be non-negative");
+      break;
+    default: return fail(MCMCGPU_E_ARG, "unknown sampler kind");
+  }
+  if (s->tuner_on) {
+    if (s->kind != MCMCGPU_MALA && s->kind != MCMCGPU_HMC) return fail(MCMCGPU_E_ARG, "EmpMCTuner applies to MALA and HMC");
+    if (s->adapt_step <= 0 || s->max_step <= 0 || !(s->target_rate > 0 && s->target_rate < 1))   // samplers.jl:40-43
+      return fail(MCMCGPU_E_ARG, "bad EmpMCTuner parameters");
+  }
+  (void)m;
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_destroy(mcmcgpu_run* run) {
+  if (!run) return MCMCGPU_OK;
+  cudaSetDevice(run->m->ctx->device);
+  cudaStreamSynchronize(run->m->ctx->stream);
+  for (void* p : run->owned) cudaFree(p);
+  delete run;
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r, const double* init,
+                           const double* scale, const double* inj_normals, const double* inj_uniforms, mcmcgpu_run** out) {
+  if (!m || !s || !r || !init || !out) return fail(MCMCGPU_E_ARG, "NULL argument");
+  int rc = check_cfg(m, s, r);
+  if (rc != MCMCGPU_OK) return rc;
+  if ((inj_normals == nullptr) != (inj_uniforms == nullptr)) return fail(MCMCGPU_E_ARG, "inject both normals and uniforms or neither");
+  mcmcgpu_ctx* c = m->ctx;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  mcmcgpu_run* R = new mcmcgpu_run();
+  R->m = m; R->s = *s; R->r = *r;
+  if (R->s.max_leaps <= 0) R->s.max_leaps = 1LL << 20;
+  const int64_t d = m->d, C = r->nchains, Cp = round_up(C, K1_CHAINS);
+  const int64_t S = (r->last - r->first) / r->step + 1;
+  R->C = C; R->Cp = Cp; R->S = S; R->d = d;
+  int engine = r->engine;
+  const bool can_fuse = fused_supported(m->family, d, m->N);
+  if (engine == MCMCGPU_ENGINE_AUTO) engine = can_fuse ? MCMCGPU_ENGINE_FUSED : MCMCGPU_ENGINE_WAVE;
+  if (engine == MCMCGPU_ENGINE_FUSED && !can_fuse) { delete R; return fail(MCMCGPU_E_ARG, "engine FUSED supports the closed-form families with d <= 8"); }
+  if (engine != MCMCGPU_ENGINE_FUSED && engine != MCMCGPU_ENGINE_WAVE) { delete R; return fail(MCMCGPU_E_ARG, "unknown engine"); }
+  R->engine = engine;
+  R->has_diag = (s->kind == MCMCGPU_HMCDA) || s->tuner_on;
+#define RCU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { std::string msg = std::string("CUDA: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__); mcmcgpu_run_destroy(R); return fail(MCMCGPU_E_CUDA, msg); } } while (0)
+  // inputs
+  if (r->init_per_chain) {
+    double* tmp = nullptr;
+    RCU(dalloc(&tmp, (size_t)(C * d)));
+    RCU(cudaMemcpyAsync(tmp, init, sizeof(double) * (size_t)(C * d), cudaMemcpyHostToDevice, st));
+    RCU(R->alloc(&R->init, (size_t)(d * Cp)));
+    RCU(transpose_to_chain_minor(tmp, R->init, C, d, Cp, st));
+    RCU(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  } else {
+    RCU(R->alloc(&R->init, (size_t)d));
+    RCU(cudaMemcpyAsync(R->init, init, sizeof(double) * (size_t)d, cudaMemcpyHostToDevice, st));
+  }
+  {
+    std::vector<double> sc((size_t)d, 1.0);
+    if (scale) for (int64_t j = 0; j < d; j++) sc[(size_t)j] = scale[j];
+    RCU(R->alloc(&R->scale, (size_t)d));
+    RCU(cudaMemcpyAsync(R->scale, sc.data(), sizeof(double) * (size_t)d, cudaMemcpyHostToDevice, st));
+    RCU(cudaStreamSynchronize(st));
+  }
+  if (inj_normals) {
+    const int64_t K = (r->last + 1) * d, Ku = r->last + 1;
+    double* tmp = nullptr;
+    RCU(dalloc(&tmp, (size_t)(C * K)));
+    RCU(cudaMemcpyAsync(tmp, inj_normals, sizeof(double) * (size_t)(C * K), cudaMemcpyHostToDevice, st));
+    RCU(R->alloc(&R->inj_normals, (size_t)(K * Cp)));
+    RCU(transpose_to_chain_minor(tmp, R->inj_normals, C, K, Cp, st));
+    RCU(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+    RCU(dalloc(&tmp, (size_t)(C * Ku)));
+    RCU(cudaMemcpyAsync(tmp, inj_uniforms, sizeof(double) * (size_t)(C * Ku), cudaMemcpyHostToDevice, st));
+    RCU(R->alloc(&R->inj_uniforms, (size_t)(Ku * Cp)));
+    RCU(transpose_to_chain_minor(tmp, R->inj_uniforms, C, Ku, Cp, st));
+    RCU(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  }
+  // outputs
+  RCU(R->alloc(&R->samples, (size_t)(S * d * Cp), false));
+  if (r->store_grad) RCU(R->alloc(&R->grads, (size_t)(S * d * Cp), false));
+  RCU(R->alloc(&R->accept, (size_t)(S * Cp)));
+  if (r->store_logtarget) RCU(R->alloc(&R->logtarget, (size_t)(S * Cp), false));
+  if (R->has_diag) {
+    RCU(R->alloc(&R->eps, (size_t)(S * Cp)));
+    RCU(R->alloc(&R->nleaps, (size_t)(S * Cp)));
+  }
+  RCU(R->alloc(&R->final_eps, (size_t)Cp));
+  RCU(R->alloc(&R->status, (size_t)Cp));
+  RCU(R->alloc(&R->n_evals, 1));
+  if (engine == MCMCGPU_ENGINE_WAVE) {
+    R->nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp)) : 1;
+    RCU(R->alloc(&R->q, (size_t)(d * Cp)));
+    RCU(R->alloc(&R->part, (size_t)(R->nsplit * (d + 2) * Cp)));
+    if (m->row_sharded) RCU(R->alloc(&R->red, (size_t)((d + 2) * Cp)));
+    RCU(R->alloc(&R->cur_pars, (size_t)(d * Cp)));
+    RCU(R->alloc(&R->cur_grad, (size_t)(d * Cp)));
+    RCU(R->alloc(&R->cur_lt, (size_t)Cp));
+    RCU(R->alloc(&R->mom, (size_t)(d * Cp)));
+    RCU(R->alloc(&R->H0, (size_t)Cp));
+    RCU(R->alloc(&R->eps_cur, (size_t)Cp));
+    RCU(R->alloc(&R->da_leapstep, (size_t)Cp));
+    RCU(R->alloc(&R->da_dual, (size_t)Cp));
+    RCU(R->alloc(&R->da_dualH, (size_t)Cp));
+    RCU(R->alloc(&R->tn_step, (size_t)Cp));
+    RCU(R->alloc(&R->phase, (size_t)Cp));
+    RCU(R->alloc(&R->leap, (size_t)Cp));
+    RCU(R->alloc(&R->nleaps_cur, (size_t)Cp));
+    RCU(R->alloc(&R->remaining, 1));
+    RCU(R->alloc(&R->istep, (size_t)Cp));
+    RCU(R->alloc(&R->kept, (size_t)Cp));
+    RCU(R->alloc(&R->tn_nleaps, (size_t)Cp));
+    RCU(R->alloc(&R->tn_acc, (size_t)Cp));
+    RCU(R->alloc(&R->tn_prop, (size_t)Cp));
+    RCU(R->alloc(&R->need_ll, (size_t)Cp));
+  }
+  RCU(cudaStreamSynchronize(st));
+  *out = R;
+  return MCMCGPU_OK;
+}
+
+static RunnerDev runner_dev(const mcmcgpu_run* R) {
+  RunnerDev D;
+  D.first = R->r.first; D.step = R->r.step; D.last = R->r.last; D.S = R->S; D.C = R->C; D.Cp = R->Cp;
+  D.chain_offset = R->r.chain_offset; D.seed = R->r.seed; D.init_per_chain = R->r.init_per_chain;
+  D.store_grad = R->r.store_grad; D.store_lt = R->r.store_logtarget;
+  return D;
+}
+static SamplerDev sampler_dev(const mcmcgpu_run* R) {
+  SamplerDev D;
+  const mcmcgpu_sampler_cfg& s = R->s;
+  D.kind = s.kind; D.nleaps = s.nleaps; D.scale = s.scale; D.rate = s.rate; D.len = s.len; D.shrinkage = s.shrinkage;
+  D.t0 = s.t0; D.step = s.step; D.max_leaps = s.max_leaps; D.tuner_on = s.tuner_on; D.adapt_step = s.adapt_step;
+  D.max_step = s.max_step; D.target_path = s.target_path; D.target_rate = s.target_rate;
+  return D;
+}
+
+__global__ void wave_init_kernel(int32_t* phase, int32_t* remaining, double* q, const double* init, int init_per_chain,
+                                 int64_t C, int64_t Cp, int64_t d) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) *remaining = (int32_t)C;
+  if (c >= Cp) return;
+  phase[c] = (c < C) ? PH_INIT : PH_DONE;
+  for (int64_t j = 0; j < d; j++) q[j * Cp + c] = (c < C) ? (init_per_chain ? init[j * Cp + c] : init[j]) : 0.0;
+}
+
+int32_t mcmcgpu_run_execute(mcmcgpu_run* R, mcmcgpu_run_info* info) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  mcmcgpu_model* m = R->m;
+  mcmcgpu_ctx* c = m->ctx;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  int64_t launches = 0, waves = 0;
+  double eval_ms = 0.0;
+  CU(cudaMemsetAsync(R->n_evals, 0, sizeof(unsigned long long), st));
+  CU(cudaEventRecord(e0, st));
+  if (R->engine == MCMCGPU_ENGINE_FUSED) {
+    FusedArgs A;
+    A.M = m->dev(); A.S = sampler_dev(R); A.R = runner_dev(R);
+    A.init = R->init; A.scale = R->scale; A.inj_normals = R->inj_normals; A.inj_uniforms = R->inj_uniforms;
+    A.samples = R->samples; A.grads = R->grads; A.accept = R->accept; A.logtarget = R->logtarget;
+    A.eps = R->eps; A.nleaps = R->nleaps; A.final_eps = R->final_eps; A.final_pars = nullptr;
+    A.status = R->status; A.n_evals = R->n_evals;
+    CU(launch_fused(A, st));
+    launches = 1;
+  } else {
+    WaveArgs W;
+    W.M = m->dev(); W.S = sampler_dev(R); W.R = runner_dev(R);
+    W.nsplit = R->nsplit; W.row_sharded_prior = 0;
+    W.q = R->q; W.part = R->part;
+    W.cur_pars = R->cur_pars; W.cur_grad = R->cur_grad; W.cur_lt = R->cur_lt; W.mom = R->mom; W.H0 = R->H0;
+    W.phase = R->phase; W.leap = R->leap; W.nleaps_cur = R->nleaps_cur; W.istep = R->istep; W.kept = R->kept;
+    W.eps_cur = R->eps_cur; W.da_leapstep = R->da_leapstep; W.da_dual = R->da_dual; W.da_dualH = R->da_dualH;
+    W.tn_step = R->tn_step; W.tn_nleaps = R->tn_nleaps; W.tn_acc = R->tn_acc; W.tn_prop = R->tn_prop;
+    W.need_ll = R->need_ll; W.status = R->status; W.remaining = R->remaining; W.n_evals = R->n_evals;
+    W.init = R->init; W.scale = R->scale; W.inj_normals = R->inj_normals; W.inj_uniforms = R->inj_uniforms;
+    W.samples = R->samples; W.grads = R->grads; W.accept = R->accept; W.logtarget = R->logtarget;
+    W.eps = R->eps; W.nleaps = R->nleaps; W.final_eps = R->final_eps;
+    CU(cudaMemsetAsync(R->kept, 0, sizeof(int64_t) * (size_t)R->Cp, st));
+    wave_init_kernel<<<(unsigned)((R->Cp + 127) / 128), 128, 0, st>>>(R->phase, R->remaining, R->q, R->init,
+                                                                       R->r.init_per_chain, R->C, R->Cp, R->d);
+    CU(cudaGetLastError());
+    launches++;
+    const int kind = R->s.kind;
+    const bool need_grad = (kind != MCMCGPU_RWM);
+    // number of waves when it is known in advance; otherwise poll the device counter
+    int64_t known = -1;
+    if (kind == MCMCGPU_RWM || kind == MCMCGPU_MALA) known = R->r.last + 1;
+    else if (kind == MCMCGPU_HMC && !R->s.tuner_on) known = 1 + R->r.last * (int64_t)R->s.nleaps;
+    std::vector<cudaEvent_t> evs;
+    bool first = true;
+    for (;;) {
+      const double* pp; int ns;
+      cudaEvent_t a0 = nullptr, a1 = nullptr;
+      if (c->time_eval) { CU(cudaEventCreate(&a0)); CU(cudaEventCreate(&a1)); CU(cudaEventRecord(a0, st)); }
+      int rc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad || first,
+                         first ? nullptr : R->need_ll, R->phase, R->remaining, &pp, &ns);
+      if (rc != MCMCGPU_OK) return rc;
+      if (c->time_eval) { CU(cudaEventRecord(a1, st)); evs.push_back(a0); evs.push_back(a1); }
+      W.part = pp; W.nsplit = ns;
+      CU(launch_transition(W, st));
+      launches += 2 + (m->row_sharded ? 1 : 0);
+      waves++;
+      first = false;
+      if (known >= 0) { if (waves >= known) break; }
+      else if (waves % c->poll_every == 0) {
+        CU(cudaMemcpyAsync(c->h_remaining, R->remaining, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (*c->h_remaining == 0) break;
+      }
+    }
+    if (c->time_eval) {
+      CU(cudaStreamSynchronize(st));
+      for (size_t k = 0; k + 1 < evs.size(); k += 2) {
+        float ms = 0; cudaEventElapsedTime(&ms, evs[k], evs[k + 1]); eval_ms += ms;
+        cudaEventDestroy(evs[k]); cudaEventDestroy(evs[k + 1]);
+      }
+    }
+  }
+  CU(cudaEventRecord(e1, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  R->executed = true;
+  unsigned long long nev = 0;
+  CU(cudaMemcpy(&nev, R->n_evals, sizeof(nev), cudaMemcpyDeviceToHost));
+  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = waves; info->n_launches = launches; info->eval_ms = eval_ms; }
+  // initial-support check (RWM.jl:55, MALA.jl:85, HMC.jl:121, HMCDA.jl:88)
+  std::vector<int32_t> stt((size_t)R->C);
+  CU(cudaMemcpy(stt.data(), R->status, sizeof(int32_t) * (size_t)R->C, cudaMemcpyDeviceToHost));
+  int64_t nbad = 0;
+  for (int32_t v : stt) nbad += (v != 0);
+  if (nbad) return fail(MCMCGPU_E_SUPPORT, "Initial values out of model support, try other values (" + std::to_string(nbad) + " chain(s))");
+  return MCMCGPU_OK;
+}
+
+static int fetch_chunked(mcmcgpu_run* R, const double* dev, int64_t K, double* host) {
+  // device [K][Cp] chain-minor -> host [C][K], in chain chunks through two staging buffers
+  cudaStream_t st = R->m->ctx->stream;
+  const int64_t C = R->C, Cp = R->Cp;
+  int64_t chunk = (int64_t)(256.0 * 1024 * 1024 / (8.0 * (double)K));
+  if (chunk < 64) chunk = 64;
+  if (chunk > C) chunk = C;
+  double* stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2];
+  CU(dalloc(&stage[0], (size_t)(chunk * K)));
+  CU(dalloc(&stage[1], (size_t)(chunk * K)));
+  CU(cudaEventCreate(&done[0])); CU(cudaEventCreate(&done[1]));
+  int b = 0; bool used[2] = {false, false};
+  for (int64_t c0 = 0; c0 < C; c0 += chunk, b ^= 1) {
+    int64_t nc = (C - c0 < chunk) ? C - c0 : chunk;
+    if (used[b]) CU(cudaEventSynchronize(done[b]));
+    CU(transpose_to_chain_major(dev, stage[b], c0, nc, K, Cp, st));
+    CU(cudaMemcpyAsync(host + c0 * K, stage[b], sizeof(double) * (size_t)(nc * K), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(done[b], st));
+    used[b] = true;
+  }
+  CU(cudaStreamSynchronize(st));
+  cudaFree(stage[0]); cudaFree(stage[1]);
+  cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_fetch(mcmcgpu_run* R, double* out_samples, double* out_grads, uint8_t* out_accept, double* out_logtarget) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
+  CU(cudaSetDevice(R->m->ctx->device));
+  cudaStream_t st = R->m->ctx->stream;
+  int rc;
+  if (out_samples) { rc = fetch_chunked(R, R->samples, R->S * R->d, out_samples); if (rc) return rc; }
+  if (out_grads) {
+    if (!R->grads) return fail(MCMCGPU_E_STATE, "gradients were not stored (store_grad = 0)");
+    rc = fetch_chunked(R, R->grads, R->S * R->d, out_grads); if (rc) return rc;
+  }
+  if (out_logtarget) {
+    if (!R->logtarget) return fail(MCMCGPU_E_STATE, "log-targets were not stored (store_logtarget = 0)");
+    rc = fetch_chunked(R, R->logtarget, R->S, out_logtarget); if (rc) return rc;
+  }
+  if (out_accept) {
+    uint8_t* tmp = nullptr;
+    CU(dalloc(&tmp, (size_t)(R->C * R->S)));
+    CU(transpose_to_chain_major_u8(R->accept, tmp, 0, R->C, R->S, R->Cp, st));
+    CU(cudaMemcpyAsync(out_accept, tmp, (size_t)(R->C * R->S), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  }
+  return MCMCGPU_OK;
+}
+
+__global__ void i32_to_i64_kernel(const int32_t* in, int64_t* out, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+int32_t mcmcgpu_run_fetch_diag(mcmcgpu_run* R, double* out_eps, int64_t* out_nleaps) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
+  if (!R->has_diag) return fail(MCMCGPU_E_STATE, "sampler has no step-size diagnostics");
+  CU(cudaSetDevice(R->m->ctx->device));
+  cudaStream_t st = R->m->ctx->stream;
+  if (out_eps) { int rc = fetch_chunked(R, R->eps, R->S, out_eps); if (rc) return rc; }
+  if (out_nleaps) {
+    // widen to double-sized lanes so the same transposer can be used
+    int64_t n = R->S * R->Cp;
+    int64_t* wide = nullptr;
+    CU(dalloc(&wide, (size_t)n));
+    i32_to_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->nleaps, wide, n);
+    CU(cudaGetLastError());
+    int rc = fetch_chunked(R, reinterpret_cast<const double*>(wide), R->S, reinterpret_cast<double*>(out_nleaps));
+    cudaFree(wide);
+    if (rc) return rc;
+  }
+  return MCMCGPU_OK;
+}
+
+static int stats_common(mcmcgpu_ctx* c, const double* samples, const uint8_t* accept, int64_t S, int64_t d, int64_t C, int64_t Cp,
+                        int32_t vtype, int64_t maxlag, int64_t batchlen, double* out_mean, double* out_var_iid, double* out_var,
+                        double* out_ess, double* out_actime, double* out_accept_rate) {
+  cudaStream_t st = c->stream;
+  if (vtype < MCMCGPU_VAR_IID || vtype > MCMCGPU_VAR_IPSE) return fail(MCMCGPU_E_ARG, "Unknown variance type");   // var.jl:138
+  if ((out_ess || out_actime) && vtype == MCMCGPU_VAR_IID) return fail(MCMCGPU_E_ARG, "Unknown ESS type iid");      // ess.jl:4,7
+  if (S < 2) return fail(MCMCGPU_E_ARG, "need at least 2 kept draws");
+  if (maxlag < 0) maxlag = S - 1;
+  if (maxlag > S - 1) maxlag = S - 1;
+  if (batchlen <= 0) batchlen = 100;
+  if (vtype == MCMCGPU_VAR_BM && S / batchlen <= 1)
+    return fail(MCMCGPU_E_ARG, "Choose batch size such that the number of batches is greather than one");           // var.jl:22
+  double* outs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double* hosts[5] = {out_mean, out_var_iid, out_var, out_ess, out_actime};
+  for (int k = 0; k < 5; k++) if (hosts[k]) CU(dalloc(&outs[k], (size_t)(d * Cp)));
+  CU(launch_stats(samples, S, d, C, Cp, vtype, maxlag, batchlen, outs[0], outs[1], outs[2], outs[3], outs[4], st));
+  double* tmp = nullptr;
+  CU(dalloc(&tmp, (size_t)(C * d)));
+  for (int k = 0; k < 5; k++) if (hosts[k]) {
+    CU(transpose_to_chain_major(outs[k], tmp, 0, C, d, Cp, st));
+    CU(cudaMemcpyAsync(hosts[k], tmp, sizeof(double) * (size_t)(C * d), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  if (out_accept_rate && accept) {
+    double* rate = nullptr;
+    CU(dalloc(&rate, (size_t)Cp));
+    CU(launch_accept_rate(accept, S, C, Cp, rate, st));
+    CU(cudaMemcpyAsync(out_accept_rate, rate, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(rate);
+  }
+  CU(cudaStreamSynchronize(st));
+  cudaFree(tmp);
+  for (int k = 0; k < 5; k++) if (outs[k]) cudaFree(outs[k]);
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_stats(mcmcgpu_run* R, int32_t vtype, int64_t maxlag, int64_t batchlen, double* out_mean, double* out_var_iid,
+                          double* out_var, double* out_ess, double* out_actime, double* out_accept_rate) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
+  CU(cudaSetDevice(R->m->ctx->device));
+  return stats_common(R->m->ctx, R->samples, R->accept, R->S, R->d, R->C, R->Cp, vtype, maxlag, batchlen, out_mean, out_var_iid,
+                      out_var, out_ess, out_actime, out_accept_rate);
+}
+
+int32_t mcmcgpu_stats(mcmcgpu_ctx* c, const double* samples, int64_t S, int64_t d, int64_t C, int32_t vtype, int64_t maxlag,
+                      int64_t batchlen, double* out_mean, double* out_var_iid, double* out_var, double* out_ess, double* out_actime) {
+  if (!c || !samples || S < 1 || d < 1 || C < 1) return fail(MCMCGPU_E_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int64_t Cp = round_up(C, K1_CHAINS), K = S * d;
+  double *tmp = nullptr, *dev = nullptr;
+  CU(dalloc(&tmp, (size_t)(C * K)));
+  CU(dalloc(&dev, (size_t)(K * Cp)));
+  CU(cudaMemcpyAsync(tmp, samples, sizeof(double) * (size_t)(C * K), cudaMemcpyHostToDevice, st));
+  CU(transpose_to_chain_minor(tmp, dev, C, K, Cp, st));
+  int rc = stats_common(c, dev, nullptr, S, d, C, Cp, vtype, maxlag, batchlen, out_mean, out_var_iid, out_var, out_ess, out_actime, nullptr);
+  cudaStreamSynchronize(st);
+  cudaFree(tmp); cudaFree(dev);
+  return rc;
+}
+
+int32_t mcmcgpu_run_chains(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r, const double* init,
+                           const double* scale, const double* inj_normals, const double* inj_uniforms, double* out_samples,
+                           double* out_grads, uint8_t* out_accept, double* out_logtarget, mcmcgpu_run_info* info) {
+  if (!r) return fail(MCMCGPU_E_ARG, "NULL argument");
+  mcmcgpu_runner_cfg rr = *r;
+  rr.store_grad = out_grads ? 1 : 0;
+  rr.store_logtarget = out_logtarget ? 1 : 0;
+  mcmcgpu_run* R = nullptr;
+  int rc = mcmcgpu_run_create(m, s, &rr, init, scale, inj_normals, inj_uniforms, &R);
+  if (rc != MCMCGPU_OK) return rc;
+  rc = mcmcgpu_run_execute(R, info);
+  if (rc == MCMCGPU_OK || rc == MCMCGPU_E_SUPPORT) {
+    std::string keep = g_err;
+    int rc2 = mcmcgpu_run_fetch(R, out_samples, out_grads, out_accept, out_logtarget);
+    if (rc2 != MCMCGPU_OK) rc = rc2; else g_err = keep;
+  }
+  mcmcgpu_run_destroy(R);
+  return rc;
+}
+
+int32_t mcmcgpu_philox_draws(mcmcgpu_ctx* c, uint64_t seed, int64_t chain_offset, int64_t nchains, int64_t d, int64_t last,
+                             double* out_normals, double* out_uniforms) {
+  if (!c || !out_normals || !out_uniforms || nchains < 1 || d < 1 || last < 0) return fail(MCMCGPU_E_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  double *zn = nullptr, *un = nullptr;
+  const int64_t n = nchains * (last + 1);
+  CU(dalloc(&zn, (size_t)(n * d)));
+  CU(dalloc(&un, (size_t)n));
+  CU(launch_philox_dump(seed, chain_offset, nchains, d, last, zn, un, st));
+  CU(cudaMemcpyAsync(out_normals, zn, sizeof(double) * (size_t)(n * d), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_uniforms, un, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  cudaFree(zn); cudaFree(un);
+  return MCMCGPU_OK;
+}
+
+}  // extern "C"

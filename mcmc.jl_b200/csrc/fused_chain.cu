@@ -1,0 +1,274 @@
+// fused_chain.cu -- engine "FUSED": one thread runs one whole chain (all MCMC steps) for the
+// closed-form likelihood families (Normal via function, Normal via DSL, Ornstein-Uhlenbeck).
+// Proposal generation (Philox4x32-10 + Box-Muller, or host-injected draws), the leapfrog / Langevin /
+// random-walk move, the Metropolis test, EmpMCTuner / dual-averaging adaptation and the SerialMC
+// keep/thin logic all stay in registers; the only global traffic is the kept draws, written
+// chain-minor ([kept][param][chain]) so every store instruction is fully coalesced.
+//
+// Reference loop bodies restated here: src/samplers/RWM.jl:43-72, MALA.jl:65-126, HMC.jl:81-175,
+// HMCDA.jl:51-143; keep/thin logic src/runners/SerialMC.jl:37-85.  Compiled with -fmad=false.
+#include "common.cuh"
+#include "fused_chain.h"
+#include "families.cuh"
+
+namespace mg {
+
+template <int D>
+__device__ __forceinline__ double dotd(const double (&a)[D], int d) {
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; j++) if (j < d) s += a[j] * a[j];
+  return s;
+}
+
+template <int FAM, int D>
+__global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedArgs A) {
+  extern __shared__ double sh_series[];
+  const ModelDev& M = A.M;
+  const SamplerDev& S = A.S;
+  const RunnerDev& R = A.R;
+  const int d = (int)M.d;
+  if (FAM == MCMCGPU_FAM_OU) {
+    for (int64_t t = threadIdx.x; t < M.N; t += blockDim.x) sh_series[t] = M.series[t];
+    __syncthreads();
+  }
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= R.C) return;
+  const int64_t Cp = R.Cp;
+  const uint64_t gchain = (uint64_t)(R.chain_offset + c);
+  const int64_t burnin = R.first - 1;
+
+  auto draw_normals = [&](int64_t i, double (&z)[D]) {
+    if (A.inj_normals) {
+#pragma unroll
+      for (int j = 0; j < D; j++) z[j] = (j < d) ? A.inj_normals[(i * d + j) * Cp + c] : 0.0;
+    } else {
+#pragma unroll
+      for (int b = 0; 2 * b < D; b++) {
+        double z0 = 0.0, z1 = 0.0;
+        if (2 * b < d) philox_normal_pair(R.seed, gchain, (uint32_t)i, (uint32_t)b, z0, z1);
+        z[2 * b] = z0;
+        if (2 * b + 1 < D) z[2 * b + 1] = (2 * b + 1 < d) ? z1 : 0.0;
+      }
+    }
+  };
+  auto draw_uniform = [&](int64_t i) -> double {
+    return A.inj_uniforms ? A.inj_uniforms[i * Cp + c] : philox_uniform(R.seed, gchain, (uint32_t)i);
+  };
+  int64_t kept = 0;
+  auto store = [&](int64_t i, const double (&pp)[D], double plt, const double (&pg)[D], bool has_grad, bool acc,
+                   double eps, int nl) {
+    if (!in_range(i, R.first, R.step, R.last)) return;
+#pragma unroll
+    for (int j = 0; j < D; j++) if (j < d) A.samples[(kept * d + j) * Cp + c] = pp[j];
+    if (A.grads) {
+#pragma unroll
+      for (int j = 0; j < D; j++) if (j < d) A.grads[(kept * d + j) * Cp + c] = has_grad ? pg[j] : CUDART_NAN;
+    }
+    A.accept[kept * Cp + c] = acc ? 1 : 0;
+    if (A.logtarget) A.logtarget[kept * Cp + c] = plt;
+    if (A.eps) A.eps[kept * Cp + c] = eps;
+    if (A.nleaps) A.nleaps[kept * Cp + c] = nl;
+    kept++;
+  };
+
+  double pars[D], grad[D];
+#pragma unroll
+  for (int j = 0; j < D; j++) pars[j] = (j < d) ? (R.init_per_chain ? A.init[j * Cp + c] : A.init[j]) : 0.0;
+  long long nev = 0;
+  double lt = Family<FAM, D>::evalallg(M, sh_series, d, pars, grad);
+  nev++;
+  if (!isfinite(lt)) {  // "Initial values out of model support" RWM.jl:55 MALA.jl:85 HMC.jl:121 HMCDA.jl:88
+    A.status[c] = 1;
+    return;
+  }
+  A.status[c] = 0;
+
+  if (S.kind == MCMCGPU_RWM) {
+    // RWM.jl:43-72
+    double sc[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) sc[j] = (j < d) ? A.scale[j] * S.scale : 0.0;  // :52
+    for (int64_t i = 1; i <= R.last; i++) {
+      double z[D], prop[D], pg[D];
+      draw_normals(i, z);
+#pragma unroll
+      for (int j = 0; j < D; j++) prop[j] = pars[j] + z[j] * sc[j];            // :59
+      double plt = Family<FAM, D>::evalallg(M, sh_series, d, prop, pg);         // :60 (eval; gradient unused)
+      nev++;
+      double ratio = plt - lt;                                                  // :62
+      bool acc = ratio > 0 || ratio > log(draw_uniform(i));                     // :63
+      if (acc) {
+        store(i, prop, plt, pg, false, true, CUDART_NAN, 0);
+#pragma unroll
+        for (int j = 0; j < D; j++) pars[j] = prop[j];
+        lt = plt;
+      } else {
+        store(i, pars, lt, pg, false, false, CUDART_NAN, 0);
+      }
+    }
+  } else if (S.kind == MCMCGPU_MALA) {
+    // MALA.jl:65-126
+    double tune_step = S.scale;
+    long long accepted = 0, proposed = 0;
+    for (int64_t i = 1; i <= R.last; i++) {
+      double h;
+      if (S.tuner_on) { proposed += 1; h = tune_step; } else h = S.scale;       // :91-96
+      double z[D], mean[D], prop[D], pg[D];
+      draw_normals(i, z);
+      const double sq = sqrt(h);
+#pragma unroll
+      for (int j = 0; j < D; j++) mean[j] = pars[j] + (h / 2.0) * grad[j];      // :98
+#pragma unroll
+      for (int j = 0; j < D; j++) prop[j] = mean[j] + sq * z[j];                // :100
+      double plt = Family<FAM, D>::evalallg(M, sh_series, d, prop, pg);         // :101
+      nev++;
+      const double lc = log(MG_TWO_PI * h) / 2.0;
+      double qno = 0.0;                                                         // :103
+#pragma unroll
+      for (int j = 0; j < D; j++) if (j < d) { double t = mean[j] - prop[j]; qno += -(t * t) / (2.0 * h) - lc; }
+#pragma unroll
+      for (int j = 0; j < D; j++) mean[j] = prop[j] + (h / 2.0) * pg[j];        // :104
+      double qon = 0.0;                                                         // :105
+#pragma unroll
+      for (int j = 0; j < D; j++) if (j < d) { double t = mean[j] - pars[j]; qon += -(t * t) / (2.0 * h) - lc; }
+      double ratio = plt + qon - lt - qno;                                      // :107
+      bool acc = ratio > 0 || ratio > log(draw_uniform(i));                     // :108
+      if (acc) {
+        store(i, prop, plt, pg, true, true, h, 0);
+#pragma unroll
+        for (int j = 0; j < D; j++) { pars[j] = prop[j]; grad[j] = pg[j]; }
+        lt = plt;
+        if (S.tuner_on) accepted += 1;
+      } else {
+        store(i, pars, lt, grad, true, false, h, 0);
+      }
+      if (S.tuner_on && i <= burnin && (i % S.adapt_step) == 0) {               // :116-118, adapt! :36-39
+        double rate = (double)accepted / (double)proposed;
+        tune_step *= (1.0 / (1.0 + exp(-11.0 * (rate - S.target_rate))) + 0.5);
+        accepted = 0; proposed = 0;
+      }
+    }
+    if (A.final_eps) A.final_eps[c] = S.tuner_on ? tune_step : S.scale;
+  } else {
+    // HMC.jl:106-175 and HMCDA.jl:72-143 share HMCSample / leapfrog (HMC.jl:81-102)
+    const bool da = (S.kind == MCMCGPU_HMCDA);
+    long long t_nleaps = S.nleaps; double t_step = S.scale; long long accepted = 0, proposed = 0;
+    double leapStepDA = 1.0, mu = 0.0, dualLeapStep = 1.0, dualH = 0.0;
+    if (da) {
+      // HMCDA.jl:90-94.  The pre-loop randn (step-0 draw) and the leapfrog inside initializeHMCDAStep
+      // (HMCDA.jl:51-69) have no observable effect: state0.H is NaN there (HMC.jl:88), so p = NaN,
+      // a = -1, the while test is false and the function always returns 1.0.
+      leapStepDA = 1.0;
+      mu = log(10.0 * leapStepDA);
+    }
+    for (int64_t i = 1; i <= R.last; i++) {
+      long long nLeaps; double eps;
+      if (da) {
+        eps = leapStepDA;
+        double nl = round(S.len / eps);                                         // HMCDA.jl:104
+        if (!(nl >= 1.0)) nl = 1.0;
+        if (nl > (double)S.max_leaps) nl = (double)S.max_leaps;
+        nLeaps = (long long)nl;
+      } else if (S.tuner_on) { proposed += 1; nLeaps = t_nleaps; eps = t_step; } // HMC.jl:129-134
+      else { nLeaps = S.nleaps; eps = S.scale; }
+      double m[D], p[D], g[D];
+      draw_normals(i, m);                                                       // HMC.jl:136 / HMCDA.jl:100
+      const double H0 = -lt + 0.5 * dotd<D>(m, d);                              // update! HMC.jl:91
+      double plt = lt;
+#pragma unroll
+      for (int j = 0; j < D; j++) { p[j] = pars[j]; g[j] = grad[j]; }
+      for (long long l = 0; l < nLeaps; l++) {                                  // leapfrog HMC.jl:93-102
+#pragma unroll
+        for (int j = 0; j < D; j++) m[j] += (0.5 * g[j]) * eps;
+#pragma unroll
+        for (int j = 0; j < D; j++) p[j] += eps * m[j];
+        plt = Family<FAM, D>::evalallg(M, sh_series, d, p, g);
+        nev++;
+#pragma unroll
+        for (int j = 0; j < D; j++) m[j] += (0.5 * g[j]) * eps;
+      }
+      const double H = -plt + 0.5 * dotd<D>(m, d);
+      const double e = exp(H0 - H);
+      const double u = draw_uniform(i);
+      bool acc; double pacc = 0.0;
+      if (da) { pacc = isnan(e) ? 0.0 : (e < 1.0 ? e : 1.0); acc = u < pacc; }  // HMCDA.jl:120-121 (NaN => 0: documented)
+      else acc = u < e;                                                          // HMC.jl:154
+      if (acc) {
+        store(i, p, plt, g, true, true, eps, (int)nLeaps);
+#pragma unroll
+        for (int j = 0; j < D; j++) { pars[j] = p[j]; grad[j] = g[j]; }
+        lt = plt;
+        if (S.tuner_on) accepted += 1;
+      } else {
+        store(i, pars, lt, grad, true, false, eps, (int)nLeaps);
+      }
+      if (da) {
+        if (i < burnin) {                                                       // HMCDA.jl:133-138
+          double fi = (double)i;
+          double eta = 1.0 / (fi + S.t0);
+          dualH = (1.0 - eta) * dualH + eta * (S.rate - pacc);
+          leapStepDA = exp(mu - sqrt(fi) * dualH / S.shrinkage);
+          eta = pow(fi, -S.step);
+          dualLeapStep = exp((1.0 - eta) * log(dualLeapStep) + eta * log(leapStepDA));
+        } else {
+          leapStepDA = dualLeapStep;                                            // :140
+        }
+      } else if (S.tuner_on && i <= burnin && (i % S.adapt_step) == 0) {        // HMC.jl:167-169, adapt! :39-43
+        double rate = (double)accepted / (double)proposed;
+        t_step *= (1.0 / (1.0 + exp(-11.0 * (rate - S.target_rate))) + 0.5);
+        double cl = ceil(S.target_path / t_step);
+        t_nleaps = (cl < (double)S.max_step) ? (long long)cl : (long long)S.max_step;
+        accepted = 0; proposed = 0;
+      }
+    }
+    if (A.final_eps) A.final_eps[c] = da ? leapStepDA : (S.tuner_on ? t_step : S.scale);
+  }
+  // final state (resume) + evaluation count
+  if (A.final_pars) {
+#pragma unroll
+    for (int j = 0; j < D; j++) if (j < d) A.final_pars[j * Cp + c] = pars[j];
+  }
+  atomicAdd(A.n_evals, (unsigned long long)nev);
+}
+
+template <int FAM, int D>
+static cudaError_t launch_one(const FusedArgs& A, cudaStream_t st) {
+  size_t smem = (FAM == MCMCGPU_FAM_OU) ? sizeof(double) * (size_t)A.M.N : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(fused_chain_kernel<FAM, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  int blocks = (int)((A.R.C + FUSED_THREADS - 1) / FUSED_THREADS);
+  fused_chain_kernel<FAM, D><<<blocks, FUSED_THREADS, smem, st>>>(A);
+  return cudaGetLastError();
+}
+
+template <int FAM>
+static cudaError_t launch_d(const FusedArgs& A, cudaStream_t st) {
+  int d = (int)A.M.d;
+  if (d <= 1) return launch_one<FAM, 1>(A, st);
+  if (d <= 2) return launch_one<FAM, 2>(A, st);
+  if (d <= 3) return launch_one<FAM, 3>(A, st);
+  if (d <= 4) return launch_one<FAM, 4>(A, st);
+  if (d <= 6) return launch_one<FAM, 6>(A, st);
+  if (d <= 8) return launch_one<FAM, 8>(A, st);
+  return cudaErrorInvalidValue;
+}
+
+bool fused_supported(int family, int64_t d, int64_t N) {
+  if (family == MCMCGPU_FAM_NORMAL_FN || family == MCMCGPU_FAM_NORMAL_DSL) return d >= 1 && d <= FUSED_MAX_D;
+  if (family == MCMCGPU_FAM_OU) return d == 3 && N >= 2 && N * 8 <= 200 * 1024;
+  return false;
+}
+
+cudaError_t launch_fused(const FusedArgs& A, cudaStream_t st) {
+  switch (A.M.family) {
+    case MCMCGPU_FAM_NORMAL_FN: return launch_d<MCMCGPU_FAM_NORMAL_FN>(A, st);
+    case MCMCGPU_FAM_NORMAL_DSL: return launch_d<MCMCGPU_FAM_NORMAL_DSL>(A, st);
+    case MCMCGPU_FAM_OU: return launch_one<MCMCGPU_FAM_OU, 3>(A, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace mg

@@ -1,0 +1,27 @@
+#pragma once
+#include "common.cuh"
+namespace mg {
+constexpr int FUSED_THREADS = 128;
+constexpr int FUSED_MAX_D = 8;
+struct FusedArgs {
+  ModelDev M;
+  SamplerDev S;
+  RunnerDev R;
+  const double* init;          // [d] or [d][Cp]
+  const double* scale;         // [d]
+  const double* inj_normals;   // [(last+1)][d][Cp] or null
+  const double* inj_uniforms;  // [(last+1)][Cp] or null
+  double* samples;             // [S][d][Cp]
+  double* grads;               // [S][d][Cp] or null
+  uint8_t* accept;             // [S][Cp]
+  double* logtarget;           // [S][Cp] or null
+  double* eps;                 // [S][Cp] or null
+  int32_t* nleaps;             // [S][Cp] or null
+  double* final_eps;           // [Cp] or null
+  double* final_pars;          // [d][Cp] or null
+  int32_t* status;             // [Cp]
+  unsigned long long* n_evals; // scalar
+};
+bool fused_supported(int family, int64_t d, int64_t N);
+cudaError_t launch_fused(const FusedArgs& A, cudaStream_t st);
+}  // namespace mg

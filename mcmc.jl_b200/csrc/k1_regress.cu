@@ -1,0 +1,352 @@
+// k1_regress.cu -- K1: fused log-likelihood + gradient of the regression families for a tile of
+// 64 chains x a range of rows, on the FP64 tensor cores (DMMA m8n8k4), X tiles staged by bulk
+// async copies (TMA, cp.async.bulk + mbarrier) through a 4-deep shared-memory ring.
+//
+// What it replaces: per chain and per evaluation the reference runs `X * vars`
+// (dgemv, examples/logistic_regression.jl:18), an elementwise logpdf/logcdf pass with an LLAcc sum
+// (DistributionsExtensions.jl:51-58, AccumulatorDerivRules.jl:19-20) and the reverse sweep X' * r
+// (MCMCDerivRules.jl:111, probit_regression.jl:39).  Here all chains share each X tile:
+//
+//   phase 1   eta^T[chain][row] = sum_j beta[chain][j] * X[row][j]        (DMMA, A = beta frags in registers)
+//   epilogue  link function in registers: loglik term, r = d loglik / d eta
+//   phase 2   G^T[chain][j]    += sum_row r[chain][row] * X[row][j]       (DMMA, A = the phase-1 accumulators)
+//
+// The phase-1 accumulator registers ARE the phase-2 A fragments: an m8n8k4 C fragment holds columns
+// (2t, 2t+1) of row g (g = lane/4, t = lane%4) and an A fragment needs column t, so phase 2 simply
+// sums over the rows in the order the registers already hold them (k is a summation index) and loads
+// the matching rows of X for the B fragment.  eta and r never leave registers.
+//
+// Algorithmic work per (row, chain): 4*d flop (2d for eta, 2d for X'r); bound: FP64 tensor pipe.
+#include "k1_regress.h"
+#include <cstdio>
+
+namespace mg {
+
+constexpr int K1_STAGES = 4;
+constexpr int K1_THREADS = K1_WARPS * 32;
+constexpr int PH_DONE_K1 = 99;  // must equal PH_DONE in transition.h
+
+// row permutation inside an 8-row group: column n of the phase-1 B fragment reads row PI[n]
+// (bank-conflict-free for both phases when the row stride is 4 mod 8 doubles)
+__device__ __forceinline__ int pi8(int n) { return (n < 4) ? n : (n ^ 1); }
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// ---- link functions: (eta, y) -> loglik term(s) and r = d loglik / d eta ----------------------
+struct LinkOut { double ll1, ll2, r; bool bad; };
+
+template <int FAM>
+__device__ __forceinline__ LinkOut link(double eta, double y, const double* hy, bool need_ll) {
+  LinkOut o; o.ll2 = 0.0; o.bad = false;
+  if (FAM == MCMCGPU_FAM_LINEAR) {
+    // examples/linear_regression.jl:16-17: resid = Y - X*vars; resid ~ Normal(0, sd)
+    const double nsd = hy[1];
+    double resid = y - eta;
+    double z = (resid - 0.0) / nsd;
+    o.ll1 = -(MG_LN_SQRT_2PI + 0.5 * z * z + hy[3]);  // hy[3] = log(noise_sd), precomputed
+    o.bad = !isfinite(o.ll1);
+    o.r = -((0.0 - resid) / (nsd * nsd));             // MCMCDerivRules.jl:57 through resid = Y - X*vars
+  } else if (FAM == MCMCGPU_FAM_LOGISTIC) {
+    // examples/logistic_regression.jl:18-19: prob = 1/(1+exp(sgn*eta)); Y ~ Bernoulli(prob)
+    const double sgn = hy[1];
+    double e = exp(sgn * eta);
+    double den = 1.0 + e;
+    double p = 1.0 / den;
+    double omp = 1.0 - p;               // Bernoulli stores p0 = 1 - p1
+    bool y1 = (y != 0.0);
+    double arg = y1 ? p : omp;
+    if (need_ll) { o.ll1 = log(arg); o.bad = !isfinite(o.ll1); }
+    else { o.ll1 = 0.0; o.bad = !(arg > 0.0); }   // log(arg) finite <=> arg > 0 (arg <= 1 always; NaN => bad)
+    // d/d eta of the term.  The reference's AD chain (MCMCDerivRules.jl:111 through /, +, exp, -)
+    // is e*(-(1/(p-1+y))/(den*den))*sgn; algebraically -sgn*e*p (y=1) or sgn*p (y=0); the closed form
+    // differs from the chain only by the chain's own rounding (<= eps/(1-p)).
+    o.r = y1 ? (-sgn) * (e * p) : sgn * p;
+  } else {  // PROBIT, examples/probit_regression.jl:26-41
+    const double base = -(eta * eta + MG_LOG2PI) / 2.0;
+    if ((y == 1.0 || y == 0.0) && fabs(eta) < 1e100) {
+      // binary response, finite tails: the other term is an exact zero
+      bool y1 = (y == 1.0);
+      double l = log_ndtr(y1 ? eta : -eta);
+      o.ll1 = y1 ? l : 0.0;
+      o.ll2 = y1 ? 0.0 : l;
+      double w = exp(base - l);
+      o.r = y1 ? w : -w;
+    } else {
+      double lp = log_ndtr(eta), lm = log_ndtr(-eta);
+      o.ll1 = lp * y;
+      o.ll2 = lm * (1.0 - y);
+      o.r = y * exp(base - lp) - (1.0 - y) * exp(base - lm);
+    }
+  }
+  return o;
+}
+
+// ---- the kernel -----------------------------------------------------------------------------
+template <int FAM, int DK>
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_kernel(const K1Args a) {
+  constexpr int S = 8 * DK + 4;
+  constexpr int KS = 2 * DK;                  // k-steps of 4 features in phase 1
+  constexpr int TILE_D = K1_ROWS * S + K1_ROWS;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* tiles = reinterpret_cast<double*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)K1_STAGES * TILE_D);
+  uint64_t* empty = full + K1_STAGES;
+
+  if (a.remaining && *a.remaining == 0) return;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t chain0 = (int64_t)blockIdx.x * K1_CHAINS;
+  const int64_t mychain = chain0 + warp * 8 + g;   // the chain this thread's fragments belong to
+  const int split = blockIdx.y;
+  const int64_t Cp = a.Cp;
+  const int d = (int)a.P.d;
+
+  // skip chain tiles whose chains have all finished (asynchronous HMCDA trajectories)
+  int alive = 1;
+  if (a.phase) alive = (a.phase[chain0 + (tid & (K1_CHAINS - 1))] != PH_DONE_K1);
+  if (!__syncthreads_or(alive)) return;
+
+  // tile range of this split
+  const int64_t per = (a.P.ntiles + a.nsplit - 1) / a.nsplit;
+  const int64_t t0 = (int64_t)split * per;
+  int64_t t1 = t0 + per; if (t1 > a.P.ntiles) t1 = a.P.ntiles;
+  const int64_t nt = (t1 > t0) ? (t1 - t0) : 0;
+  const uint32_t tile_bytes = (uint32_t)(TILE_D * sizeof(double));
+
+  if (tid == 0) {
+    for (int s = 0; s < K1_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K1_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < K1_STAGES && s < nt; s++) {
+      mbar_expect_tx(&full[s], tile_bytes);
+      bulk_g2s(tiles + (size_t)s * TILE_D, a.P.tiles + (t0 + s) * a.P.tile_doubles, tile_bytes, &full[s]);
+    }
+  }
+
+  // beta fragments: A operand of phase 1, a[ks] = beta[chain g][feature 4ks + t]
+  double bf[KS];
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) {
+    int j = 4 * ks + t;
+    bf[ks] = (j < d) ? a.q[(int64_t)j * Cp + mychain] : 0.0;
+  }
+  // per-warp flag: does any of this warp's chains need the log-likelihood value this wave?
+  bool need_ll = true;
+  if (a.need_ll) need_ll = __any_sync(0xffffffffu, a.need_ll[mychain] != 0);
+
+  double G[DK][2];
+#pragma unroll
+  for (int jb = 0; jb < DK; jb++) { G[jb][0] = 0.0; G[jb][1] = 0.0; }
+  double ll1 = 0.0, ll2 = 0.0;
+  int nbad = 0;
+  const double hy[4] = {a.hyper[0], a.hyper[1], a.hyper[2], a.hyper[3]};
+  const int64_t N = a.P.N;
+
+  // shared-memory offsets of this lane's fragment elements inside a tile (doubles)
+  //   phase 1 B fragment: X[8n + pi(g)][4ks + t]
+  //   phase 2 B fragment: X[8n + pi(2t+s)][8jb + g]
+  const int off1 = pi8(g) * S + t;
+  const int row2a = pi8(2 * t), row2b = pi8(2 * t + 1);
+  const int off2a = row2a * S + g, off2b = row2b * S + g;
+
+  for (int64_t it = 0; it < nt; it++) {
+    const int slot = (int)(it % K1_STAGES);
+    const uint32_t par = (uint32_t)((it / K1_STAGES) & 1);
+    mbar_wait(&full[slot], par);
+    const double* X = tiles + (size_t)slot * TILE_D;
+    const double* ys = X + K1_ROWS * S;
+    const int64_t rowbase = (t0 + it) * K1_ROWS;
+
+    // ---- phase 1: eta for 32 rows x 8 chains ----
+    double acc[4][2];
+#pragma unroll
+    for (int n = 0; n < 4; n++) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) {
+#pragma unroll
+      for (int n = 0; n < 4; n++) {
+        double b = X[off1 + n * 8 * S + 4 * ks];
+        dmma(acc[n][0], acc[n][1], bf[ks], b);
+      }
+    }
+    // ---- epilogue: link function on this lane's 8 (row, chain) elements ----
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const int lr = 8 * n + (s ? row2b : row2a);      // local row of accumulator column 2t+s
+        const double y = ys[lr];
+        LinkOut o = link<FAM>(acc[n][s], y, hy, need_ll);
+        const bool valid = (rowbase + lr) < N;
+        if (valid) { ll1 += o.ll1; ll2 += o.ll2; nbad += o.bad ? 1 : 0; }
+        acc[n][s] = o.r;    // rows >= N have X == 0, so their r never reaches G
+      }
+    }
+    // ---- phase 2: G += r^T X ----
+    if (a.need_grad) {
+#pragma unroll
+      for (int n = 0; n < 4; n++) {
+#pragma unroll
+        for (int jb = 0; jb < DK; jb++) {
+          double b0 = X[off2a + n * 8 * S + 8 * jb];
+          dmma(G[jb][0], G[jb][1], acc[n][0], b0);
+          double b1 = X[off2b + n * 8 * S + 8 * jb];
+          dmma(G[jb][0], G[jb][1], acc[n][1], b1);
+        }
+      }
+    }
+    // release the slot; thread 0 refills it with tile it + STAGES once every warp has released
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[slot]);
+    if (tid == 0 && it + K1_STAGES < nt) {
+      mbar_wait(&empty[slot], par);
+      mbar_expect_tx(&full[slot], tile_bytes);
+      bulk_g2s(tiles + (size_t)slot * TILE_D, a.P.tiles + (t0 + it + K1_STAGES) * a.P.tile_doubles, tile_bytes,
+               &full[slot]);
+    }
+  }
+
+  // ---- write this split's partial sums ----
+  // quad reduction of the scalar sums (the 4 lanes of a quad hold different rows of the same chain)
+  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 1); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 2);
+  ll2 += __shfl_xor_sync(0xffffffffu, ll2, 1); ll2 += __shfl_xor_sync(0xffffffffu, ll2, 2);
+  nbad += __shfl_xor_sync(0xffffffffu, nbad, 1); nbad += __shfl_xor_sync(0xffffffffu, nbad, 2);
+  double* part = a.part + (int64_t)split * (d + 2) * Cp;
+  if (t == 0) {
+    part[(int64_t)d * Cp + mychain] = ll1 + ll2;
+    part[(int64_t)(d + 1) * Cp + mychain] = (double)nbad;
+  }
+  if (a.need_grad) {
+#pragma unroll
+    for (int jb = 0; jb < DK; jb++) {
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        int j = 8 * jb + 2 * t + i;   // C fragment: row g (chain), column 2t+i (feature)
+        if (j < d) part[(int64_t)j * Cp + mychain] = G[jb][i];
+      }
+    }
+  }
+}
+
+// ---- packing kernel: column-major X -> tile images -------------------------------------------
+__global__ void k1_pack_kernel(double* tiles, const double* X, const double* y, int64_t N, int64_t d, int S,
+                               int64_t tile_doubles, int64_t ntiles) {
+  // one block per tile; threads stride over (row, col)
+  const int64_t tl = blockIdx.x;
+  double* T = tiles + tl * tile_doubles;
+  const int64_t row0 = tl * K1_ROWS;
+  for (int idx = threadIdx.x; idx < K1_ROWS * S; idx += blockDim.x) {
+    int j = idx / K1_ROWS, r = idx % K1_ROWS;    // r fastest: coalesced reads along a column of X
+    int64_t row = row0 + r;
+    double v = (j < d && row < N) ? X[(int64_t)j * N + row] : 0.0;
+    T[r * S + j] = v;
+  }
+  for (int r = threadIdx.x; r < K1_ROWS; r += blockDim.x) {
+    int64_t row = row0 + r;
+    T[K1_ROWS * S + r] = (row < N) ? y[row] : 0.0;
+  }
+}
+
+bool k1_supported(int64_t d) { return d >= 1 && d <= 8 * K1_MAX_DK; }
+
+cudaError_t k1_pack(K1Pack& P, const double* dX, const double* dy, int64_t N, int64_t d, cudaStream_t st) {
+  P.N = N; P.d = d;
+  P.DK = (int)((d + 7) / 8);
+  P.S = 8 * P.DK + 4;
+  P.ntiles = (N + K1_ROWS - 1) / K1_ROWS;
+  P.tile_doubles = (int64_t)K1_ROWS * P.S + K1_ROWS;
+  cudaError_t e = cudaMalloc(&P.tiles, sizeof(double) * (size_t)(P.ntiles * P.tile_doubles));
+  if (e != cudaSuccess) return e;
+  k1_pack_kernel<<<(unsigned)P.ntiles, 256, 0, st>>>(P.tiles, dX, dy, N, d, P.S, P.tile_doubles, P.ntiles);
+  return cudaGetLastError();
+}
+void k1_free(K1Pack& P) { if (P.tiles) cudaFree(P.tiles); P.tiles = nullptr; }
+
+int k1_choose_splits(const K1Pack& P, int64_t Cp) {
+  int64_t ctiles = Cp / K1_CHAINS;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  int64_t want = (8LL * sms + ctiles - 1) / ctiles;      // aim for >= 8 CTAs per SM in total
+  int64_t maxs = P.ntiles / (2 * K1_STAGES);             // keep >= 8 tiles per CTA
+  if (maxs < 1) maxs = 1;
+  if (want > maxs) want = maxs;
+  if (want > 64) want = 64;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+template <int FAM, int DK>
+static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
+  constexpr int S = 8 * DK + 4;
+  constexpr size_t smem = sizeof(double) * (size_t)K1_STAGES * (K1_ROWS * S + K1_ROWS) + 2 * K1_STAGES * sizeof(uint64_t);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(k1_kernel<FAM, DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid((unsigned)(a.Cp / K1_CHAINS), (unsigned)a.nsplit);
+  k1_kernel<FAM, DK><<<grid, K1_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+template <int FAM>
+static cudaError_t launch_f(const K1Args& a, cudaStream_t st) {
+  switch (a.P.DK) {
+    case 1: return launch_fd<FAM, 1>(a, st);
+    case 2: return launch_fd<FAM, 2>(a, st);
+    case 3: return launch_fd<FAM, 3>(a, st);
+    case 4: return launch_fd<FAM, 4>(a, st);
+    case 5: return launch_fd<FAM, 5>(a, st);
+    case 6: return launch_fd<FAM, 6>(a, st);
+    case 7: return launch_fd<FAM, 7>(a, st);
+    case 8: return launch_fd<FAM, 8>(a, st);
+    case 9: return launch_fd<FAM, 9>(a, st);
+    case 10: return launch_fd<FAM, 10>(a, st);
+    case 11: return launch_fd<FAM, 11>(a, st);
+    case 12: return launch_fd<FAM, 12>(a, st);
+    case 13: return launch_fd<FAM, 13>(a, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t k1_launch(const K1Args& a, cudaStream_t st) {
+  switch (a.family) {
+    case MCMCGPU_FAM_LINEAR: return launch_f<MCMCGPU_FAM_LINEAR>(a, st);
+    case MCMCGPU_FAM_LOGISTIC: return launch_f<MCMCGPU_FAM_LOGISTIC>(a, st);
+    case MCMCGPU_FAM_PROBIT: return launch_f<MCMCGPU_FAM_PROBIT>(a, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace mg

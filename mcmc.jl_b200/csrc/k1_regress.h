@@ -1,0 +1,45 @@
+#pragma once
+#include "common.cuh"
+namespace mg {
+
+// K1: fused likelihood + gradient for the regression families (linear / logistic / probit).
+constexpr int K1_ROWS = 32;      // rows of X per shared-memory tile
+constexpr int K1_WARPS = 8;      // consumer warps per CTA; each owns 8 chains
+constexpr int K1_CHAINS = 8 * K1_WARPS;  // chains per CTA (64)
+constexpr int K1_MAX_DK = 13;    // d <= 104 with beta fragments in registers
+
+// Packed design matrix: tile t holds rows [32t, 32t+32) as a ready-made shared-memory image:
+//   double x[32][S]  (row-major, S = 8*DK + 4 so that S = 4 (mod 8): conflict-free fragment loads)
+//   double y[32]
+// One cp.async.bulk per tile brings it in.  Rows >= N are zero.
+struct K1Pack {
+  double* tiles = nullptr;
+  int64_t N = 0, d = 0;
+  int DK = 0;        // ceil(d/8)
+  int S = 0;         // row stride in doubles
+  int64_t ntiles = 0;
+  int64_t tile_doubles = 0;
+};
+
+struct K1Args {
+  K1Pack P;
+  int32_t family;
+  double hyper[4];
+  const double* q;       // [d][Cp] evaluation points
+  double* part;          // [nsplit][d+2][Cp]: rows 0..d-1 X'r, row d loglik, row d+1 non-finite count
+  int64_t Cp;
+  int32_t nsplit;
+  int32_t need_grad;     // 0: log-likelihood only (RWM)
+  const uint8_t* need_ll;  // [Cp] per-chain flag, or null = all chains need the log-likelihood
+  const int32_t* phase;    // [Cp] per-chain phase (PH_DONE chains are skipped), or null
+  const int32_t* remaining; // device counter of unfinished chains, or null
+};
+
+cudaError_t k1_pack(K1Pack& P, const double* dX /* N x d col-major, device */, const double* dy, int64_t N, int64_t d,
+                    cudaStream_t st);
+void k1_free(K1Pack& P);
+int k1_choose_splits(const K1Pack& P, int64_t Cp);
+cudaError_t k1_launch(const K1Args& a, cudaStream_t st);
+bool k1_supported(int64_t d);
+
+}  // namespace mg

@@ -1,0 +1,471 @@
+// transition.cu -- the per-chain state machine of engine "WAVE", plus small layout / utility kernels.
+//
+// A wave is: one likelihood+gradient evaluation for every chain at its pending point q (K1 for the
+// regression families, eval_closed_kernel otherwise), then transition_kernel, which consumes the
+// evaluation and advances each chain by exactly one evaluation's worth of sampler logic: finish the
+// leapfrog / take the Metropolis decision / adapt / store the kept draw / draw the next momentum or
+// proposal and write the next pending point.  Chains are independent, so HMCDA chains with different
+// trajectory lengths simply sit at different phases of the same wave ("leapfrog waves").
+//
+// Sampler arithmetic restates src/samplers/RWM.jl:43-72, MALA.jl:65-126, HMC.jl:81-175,
+// HMCDA.jl:51-143 in the reference's operation order; keep/thin logic src/runners/SerialMC.jl:37-85.
+// Compiled with -fmad=false.
+#include "transition.h"
+#include "families.cuh"
+
+namespace mg {
+
+__device__ __forceinline__ double sum_part(const double* part, int nsplit, int64_t row, int64_t d, int64_t Cp, int64_t c) {
+  double s = part[row * Cp + c];
+  for (int sp = 1; sp < nsplit; sp++) s += part[((int64_t)sp * (d + 2) + row) * Cp + c];
+  return s;
+}
+
+// The model-side finish of an evaluation: prior terms, LLAcc support semantics (M6), gradient of the prior.
+struct EvalFin {
+  double lt;     // log-target at q (NaN when not requested)
+  bool oos;      // DSL families: out of support => (-Inf, zeros)  (modelparser.jl:64-92)
+  double ginv;   // gradient of the prior is (0 - q_j) * ginv  (or -q_j * ginv for probit)
+  int fam;
+};
+
+__device__ __forceinline__ EvalFin finalize_eval(const ModelDev& M, const double* q, const double* part, int nsplit,
+                                                 int64_t Cp, int64_t c, bool want_lt) {
+  EvalFin f; f.fam = M.family; f.oos = false; f.ginv = 0.0; f.lt = CUDART_NAN;
+  const int64_t d = M.d;
+  if (M.family == MCMCGPU_FAM_LINEAR || M.family == MCMCGPU_FAM_LOGISTIC) {
+    const double psd = M.hyper[0];
+    const double lsd = log(psd);
+    double s = 0.0;
+    for (int64_t j = 0; j < d; j++) {   // vars ~ Normal(0, prior_sd)
+      double z = (q[j * Cp + c] - 0.0) / psd;
+      s += -(MG_LN_SQRT_2PI + 0.5 * z * z + lsd);
+    }
+    double acc = 0.0 + s;
+    f.oos = !isfinite(acc);
+    double bad = sum_part(part, nsplit, d + 1, d, Cp, c);
+    if (bad > 0.0) f.oos = true;
+    if (want_lt) {
+      double ll = sum_part(part, nsplit, d, d, Cp, c);
+      double acc2 = acc + ll;
+      if (!isfinite(acc2)) f.oos = true;
+      f.lt = f.oos ? -CUDART_INF : acc2;
+    }
+    f.ginv = 1.0 / (psd * psd);
+  } else if (M.family == MCMCGPU_FAM_PROBIT) {
+    const double psd = M.hyper[0], pvar = psd * psd;
+    if (want_lt) {
+      double qq = 0.0;
+      for (int64_t j = 0; j < d; j++) { double v = q[j * Cp + c]; qq += v * v; }
+      double logprior = -0.5 * ((double)d * MG_LOG2PI + (double)d * log(pvar)) - 0.5 * (qq / pvar);
+      f.lt = logprior + sum_part(part, nsplit, d, d, Cp, c);
+    }
+    f.ginv = pvar;
+  } else {
+    f.lt = part[d * Cp + c];   // closed-form families: eval_closed_kernel wrote final values
+  }
+  return f;
+}
+__device__ __forceinline__ double fin_grad(const EvalFin& f, const ModelDev& M, const double* q, const double* part,
+                                           int nsplit, int64_t Cp, int64_t c, int64_t j) {
+  if (f.fam == MCMCGPU_FAM_LINEAR || f.fam == MCMCGPU_FAM_LOGISTIC) {
+    if (f.oos) return 0.0;
+    double psd = M.hyper[0];
+    return sum_part(part, nsplit, j, M.d, Cp, c) + (0.0 - q[j * Cp + c]) / (psd * psd);
+  } else if (f.fam == MCMCGPU_FAM_PROBIT) {
+    return sum_part(part, nsplit, j, M.d, Cp, c) - q[j * Cp + c] / f.ginv;
+  }
+  return part[j * Cp + c];
+}
+
+__global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const RunnerDev& R = W.R;
+  const SamplerDev& S = W.S;
+  const ModelDev& M = W.M;
+  if (c >= R.C) return;
+  if (*W.remaining == 0) return;
+  const int ph = W.phase[c];
+  if (ph == PH_DONE) return;
+  const int64_t d = M.d, Cp = R.Cp;
+  const uint64_t gchain = (uint64_t)(R.chain_offset + c);
+  const int64_t burnin = R.first - 1;
+  const int kind = S.kind;
+  const bool hmc_like = (kind == MCMCGPU_HMC || kind == MCMCGPU_HMCDA);
+  double* q = W.q;
+  const double* part = W.part;
+  const int ns = W.nsplit;
+
+  int64_t i = W.istep[c];
+  int leap = hmc_like ? W.leap[c] : 0;
+  int nl_cur = hmc_like ? W.nleaps_cur[c] : 0;
+  const bool interior = (ph == PH_LEAP) && (leap + 1 < nl_cur);
+  const EvalFin F = finalize_eval(M, q, part, ns, Cp, c, !interior);
+  const double lt_q = F.lt;
+  unsigned long long nev = 1;
+  bool begin = false;
+  bool accepted_now = false;
+
+  auto uniform = [&](int64_t step) -> double {
+    return W.inj_uniforms ? W.inj_uniforms[step * Cp + c] : philox_uniform(R.seed, gchain, (uint32_t)step);
+  };
+  auto store = [&](int64_t step, bool has_grad, bool acc, double eps, int nl) {
+    // SerialMC.jl:49-66: the post-decision state (ppars / plogtarget / pgrads) is what is kept
+    if (!in_range(step, R.first, R.step, R.last)) return;
+    int64_t k = W.kept[c];
+    for (int64_t j = 0; j < d; j++) W.samples[(k * d + j) * Cp + c] = W.cur_pars[j * Cp + c];
+    if (W.grads) for (int64_t j = 0; j < d; j++) W.grads[(k * d + j) * Cp + c] = has_grad ? W.cur_grad[j * Cp + c] : CUDART_NAN;
+    W.accept[k * Cp + c] = acc ? 1 : 0;
+    if (W.logtarget) W.logtarget[k * Cp + c] = W.cur_lt[c];
+    if (W.eps) W.eps[k * Cp + c] = eps;
+    if (W.nleaps) W.nleaps[k * Cp + c] = nl;
+    W.kept[c] = k + 1;
+  };
+
+  if (ph == PH_INIT) {
+    if (!isfinite(lt_q)) {   // "Initial values out of model support" RWM.jl:55 MALA.jl:85 HMC.jl:121 HMCDA.jl:88
+      W.status[c] = 1; W.phase[c] = PH_DONE; atomicSub(W.remaining, 1); atomicAdd(W.n_evals, nev);
+      return;
+    }
+    W.status[c] = 0;
+    W.cur_lt[c] = lt_q;
+    for (int64_t j = 0; j < d; j++) {
+      W.cur_pars[j * Cp + c] = q[j * Cp + c];
+      if (kind != MCMCGPU_RWM) W.cur_grad[j * Cp + c] = fin_grad(F, M, q, part, ns, Cp, c, j);
+    }
+    if (kind == MCMCGPU_HMCDA) {
+      // HMCDA.jl:90-94; initializeHMCDAStep (HMCDA.jl:51-69) always returns 1.0 (state0.H is NaN, HMC.jl:88)
+      W.da_leapstep[c] = 1.0; W.da_dual[c] = 1.0; W.da_dualH[c] = 0.0;
+    }
+    if (S.tuner_on) { W.tn_step[c] = S.scale; W.tn_nleaps[c] = S.nleaps; W.tn_acc[c] = 0; W.tn_prop[c] = 0; }
+    i = 1;
+    begin = true;
+  } else if (ph == PH_RWM) {
+    // RWM.jl:62-70
+    double ratio = lt_q - W.cur_lt[c];
+    bool acc = ratio > 0 || ratio > log(uniform(i));
+    if (acc) {
+      for (int64_t j = 0; j < d; j++) W.cur_pars[j * Cp + c] = q[j * Cp + c];
+      W.cur_lt[c] = lt_q;
+    }
+    store(i, false, acc, CUDART_NAN, 0);
+    i++; begin = true;
+  } else if (ph == PH_MALA) {
+    // MALA.jl:103-113
+    const double h = W.eps_cur[c];
+    const double lc = log(MG_TWO_PI * h) / 2.0;
+    double qno = 0.0, qon = 0.0;
+    for (int64_t j = 0; j < d; j++) {
+      double pj = W.cur_pars[j * Cp + c], gj = W.cur_grad[j * Cp + c], prop = q[j * Cp + c];
+      double mean = pj + (h / 2.0) * gj;                              // :98 (recomputed, same roundings)
+      double t1 = mean - prop;  qno += -(t1 * t1) / (2.0 * h) - lc;   // :103
+      double mean2 = prop + (h / 2.0) * fin_grad(F, M, q, part, ns, Cp, c, j);  // :104
+      double t2 = mean2 - pj;   qon += -(t2 * t2) / (2.0 * h) - lc;   // :105
+    }
+    double ratio = lt_q + qon - W.cur_lt[c] - qno;                    // :107
+    bool acc = ratio > 0 || ratio > log(uniform(i));                  // :108
+    if (acc) {
+      for (int64_t j = 0; j < d; j++) {
+        W.cur_pars[j * Cp + c] = q[j * Cp + c];
+        W.cur_grad[j * Cp + c] = fin_grad(F, M, q, part, ns, Cp, c, j);
+      }
+      W.cur_lt[c] = lt_q;
+      if (S.tuner_on) W.tn_acc[c] += 1;
+    }
+    store(i, true, acc, h, 0);
+    if (S.tuner_on && i <= burnin && (i % S.adapt_step) == 0) {       // :116-118, adapt! :36-39
+      double rate = (double)W.tn_acc[c] / (double)W.tn_prop[c];
+      W.tn_step[c] *= (1.0 / (1.0 + exp(-11.0 * (rate - S.target_rate))) + 0.5);
+      W.tn_acc[c] = 0; W.tn_prop[c] = 0;
+    }
+    i++; begin = true;
+  } else {  // PH_LEAP: HMC.jl:93-102 second half, then either the next leapfrog or the decision
+    const double eps = W.eps_cur[c];
+    leap += 1;
+    if (leap < nl_cur) {
+      for (int64_t j = 0; j < d; j++) {
+        double gj = fin_grad(F, M, q, part, ns, Cp, c, j);
+        double m = W.mom[j * Cp + c];
+        m += (0.5 * gj) * eps;          // end of this leapfrog      HMC.jl:98
+        m += (0.5 * gj) * eps;          // start of the next one     HMC.jl:95
+        double p = q[j * Cp + c];
+        p += eps * m;                   //                           HMC.jl:96
+        W.mom[j * Cp + c] = m;
+        q[j * Cp + c] = p;
+      }
+      W.leap[c] = leap;
+      W.need_ll[c] = (leap + 1 == nl_cur) ? 1 : 0;
+      atomicAdd(W.n_evals, nev);
+      return;
+    }
+    double mm = 0.0;
+    for (int64_t j = 0; j < d; j++) {
+      double gj = fin_grad(F, M, q, part, ns, Cp, c, j);
+      double m = W.mom[j * Cp + c];
+      m += (0.5 * gj) * eps;            // HMC.jl:98
+      mm += m * m;
+    }
+    const double H = -lt_q + 0.5 * mm;  // update! HMC.jl:91
+    const double e = exp(W.H0[c] - H);
+    const double u = uniform(i);
+    bool acc; double pacc = 0.0;
+    if (kind == MCMCGPU_HMCDA) { pacc = isnan(e) ? 0.0 : (e < 1.0 ? e : 1.0); acc = u < pacc; }  // HMCDA.jl:120-121
+    else acc = u < e;                                                                             // HMC.jl:154
+    if (acc) {
+      for (int64_t j = 0; j < d; j++) {
+        W.cur_pars[j * Cp + c] = q[j * Cp + c];
+        W.cur_grad[j * Cp + c] = fin_grad(F, M, q, part, ns, Cp, c, j);
+      }
+      W.cur_lt[c] = lt_q;
+      if (S.tuner_on) W.tn_acc[c] += 1;
+    }
+    store(i, true, acc, eps, nl_cur);
+    if (kind == MCMCGPU_HMCDA) {
+      if (i < burnin) {                                               // HMCDA.jl:133-138
+        double fi = (double)i;
+        double eta = 1.0 / (fi + S.t0);
+        double dualH = (1.0 - eta) * W.da_dualH[c] + eta * (S.rate - pacc);
+        double ls = exp(log(10.0 * 1.0) - sqrt(fi) * dualH / S.shrinkage);   // mu = log(10*leapStep0), leapStep0 = 1
+        eta = pow(fi, -S.step);
+        W.da_dual[c] = exp((1.0 - eta) * log(W.da_dual[c]) + eta * log(ls));
+        W.da_dualH[c] = dualH; W.da_leapstep[c] = ls;
+      } else {
+        W.da_leapstep[c] = W.da_dual[c];                              // :140
+      }
+    } else if (S.tuner_on && i <= burnin && (i % S.adapt_step) == 0) { // HMC.jl:167-169, adapt! :39-43
+      double rate = (double)W.tn_acc[c] / (double)W.tn_prop[c];
+      double ts = W.tn_step[c] * (1.0 / (1.0 + exp(-11.0 * (rate - S.target_rate))) + 0.5);
+      double cl = ceil(S.target_path / ts);
+      W.tn_step[c] = ts;
+      W.tn_nleaps[c] = (cl < (double)S.max_step) ? (int64_t)cl : (int64_t)S.max_step;
+      W.tn_acc[c] = 0; W.tn_prop[c] = 0;
+    }
+    i++; begin = true;
+    (void)accepted_now;
+  }
+
+  if (begin) {
+    if (i > R.last) {
+      W.phase[c] = PH_DONE;
+      W.istep[c] = i;
+      if (W.final_eps) {
+        double fe = S.scale;
+        if (kind == MCMCGPU_HMCDA) fe = W.da_leapstep[c];
+        else if (S.tuner_on) fe = W.tn_step[c];
+        W.final_eps[c] = fe;
+      }
+      atomicSub(W.remaining, 1);
+      atomicAdd(W.n_evals, nev);
+      return;
+    }
+    W.istep[c] = i;
+    // ---- start step i: draw and write the next pending point ----
+    double eps = S.scale; int nl = 0;
+    if (kind == MCMCGPU_HMCDA) {
+      eps = W.da_leapstep[c];
+      double r = round(S.len / eps);                                  // HMCDA.jl:104
+      if (!(r >= 1.0)) r = 1.0;
+      if (r > (double)S.max_leaps) r = (double)S.max_leaps;
+      nl = (int)r;
+    } else if (kind == MCMCGPU_HMC) {
+      if (S.tuner_on) { W.tn_prop[c] += 1; nl = (int)W.tn_nleaps[c]; eps = W.tn_step[c]; } else nl = S.nleaps;
+    } else if (kind == MCMCGPU_MALA) {
+      if (S.tuner_on) { W.tn_prop[c] += 1; eps = W.tn_step[c]; }
+    }
+    const double sq = (kind == MCMCGPU_MALA) ? sqrt(eps) : 0.0;
+    double mm = 0.0;
+    for (int64_t jb = 0; jb < d; jb += 2) {
+      double z0, z1 = 0.0;
+      if (W.inj_normals) {
+        z0 = W.inj_normals[(i * d + jb) * Cp + c];
+        if (jb + 1 < d) z1 = W.inj_normals[(i * d + jb + 1) * Cp + c];
+      } else {
+        philox_normal_pair(R.seed, gchain, (uint32_t)i, (uint32_t)(jb >> 1), z0, z1);
+      }
+#pragma unroll
+      for (int s = 0; s < 2; s++) {
+        const int64_t j = jb + s;
+        if (j >= d) break;
+        const double z = s ? z1 : z0;
+        const double pj = W.cur_pars[j * Cp + c];
+        if (kind == MCMCGPU_RWM) {
+          q[j * Cp + c] = pj + z * (W.scale[j] * S.scale);            // RWM.jl:52,59
+        } else if (kind == MCMCGPU_MALA) {
+          double mean = pj + (eps / 2.0) * W.cur_grad[j * Cp + c];    // MALA.jl:98
+          q[j * Cp + c] = mean + sq * z;                              // :100
+        } else {
+          double m = z;                                               // HMC.jl:136
+          mm += m * m;
+          m += (0.5 * W.cur_grad[j * Cp + c]) * eps;                  // HMC.jl:95
+          double p = pj;
+          p += eps * m;                                               // HMC.jl:96
+          W.mom[j * Cp + c] = m;
+          q[j * Cp + c] = p;
+        }
+      }
+    }
+    if (hmc_like) {
+      W.H0[c] = -W.cur_lt[c] + 0.5 * mm;                              // update! HMC.jl:91
+      W.leap[c] = 0; W.nleaps_cur[c] = nl;
+      W.need_ll[c] = (nl == 1) ? 1 : 0;
+      W.phase[c] = PH_LEAP;
+    } else {
+      W.need_ll[c] = 1;
+      W.phase[c] = (kind == MCMCGPU_RWM) ? PH_RWM : PH_MALA;
+    }
+    W.eps_cur[c] = eps;
+  }
+  atomicAdd(W.n_evals, nev);
+}
+
+cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st) {
+  int blocks = (int)((W.R.C + 127) / 128);
+  transition_kernel<<<blocks, 128, 0, st>>>(W);
+  return cudaGetLastError();
+}
+
+// ---- closed-form families through the wave engine ---------------------------------------------
+__global__ void eval_closed_kernel(const ModelDev M, const double* q, double* part, int64_t C, int64_t Cp,
+                                   const int32_t* phase, const int32_t* remaining) {
+  extern __shared__ double sh_series[];
+  if (remaining && *remaining == 0) return;
+  if (M.family == MCMCGPU_FAM_OU) {
+    for (int64_t t = threadIdx.x; t < M.N; t += blockDim.x) sh_series[t] = M.series[t];
+    __syncthreads();
+  }
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (phase && phase[c] == PH_DONE) return;
+  const int64_t d = M.d;
+  if (M.family == MCMCGPU_FAM_NORMAL_FN) {
+    double s = 0.0;
+    for (int64_t j = 0; j < d; j++) { double v = q[j * Cp + c]; s += v * v; part[j * Cp + c] = -2.0 * v; }
+    part[d * Cp + c] = -s;
+  } else if (M.family == MCMCGPU_FAM_NORMAL_DSL) {
+    const double mu = M.hyper[0], sigma = M.hyper[1];
+    double s = 0.0;
+    for (int64_t j = 0; j < d; j++) s += logpdf_normal(q[j * Cp + c], mu, sigma);
+    double acc = 0.0 + s;
+    bool oos = !isfinite(acc);
+    for (int64_t j = 0; j < d; j++) part[j * Cp + c] = oos ? 0.0 : (mu - q[j * Cp + c]) / (sigma * sigma);
+    part[d * Cp + c] = oos ? -CUDART_INF : acc;
+  } else {  // OU
+    double v[3] = {q[c], q[Cp + c], q[2 * Cp + c]}, g[3];
+    double lt = Family<MCMCGPU_FAM_OU, 3>::evalallg(M, sh_series, 3, v, g);
+    part[c] = g[0]; part[Cp + c] = g[1]; part[2 * Cp + c] = g[2];
+    part[3 * Cp + c] = lt;
+  }
+  part[(d + 1) * Cp + c] = 0.0;
+}
+
+cudaError_t launch_eval_closed(const ModelDev& M, const double* q, double* part, int64_t C, int64_t Cp,
+                               const int32_t* phase, const int32_t* remaining, cudaStream_t st) {
+  size_t smem = (M.family == MCMCGPU_FAM_OU) ? sizeof(double) * (size_t)M.N : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(eval_closed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  eval_closed_kernel<<<(unsigned)((C + 127) / 128), 128, smem, st>>>(M, q, part, C, Cp, phase, remaining);
+  return cudaGetLastError();
+}
+
+__global__ void finalize_kernel(const ModelDev M, const double* q, const double* part, int nsplit, int64_t C, int64_t Cp,
+                                double* lt, double* grad) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  EvalFin F = finalize_eval(M, q, part, nsplit, Cp, c, true);
+  lt[c] = F.lt;
+  if (grad) for (int64_t j = 0; j < M.d; j++) grad[j * Cp + c] = fin_grad(F, M, q, part, nsplit, Cp, c, j);
+}
+cudaError_t launch_finalize(const ModelDev& M, const double* q, const double* part, int nsplit, int64_t C, int64_t Cp,
+                            double* lt, double* grad, cudaStream_t st) {
+  finalize_kernel<<<(unsigned)((C + 127) / 128), 128, 0, st>>>(M, q, part, nsplit, C, Cp, lt, grad);
+  return cudaGetLastError();
+}
+
+__global__ void reduce_splits_kernel(const double* part, int nsplit, int64_t n, double* red) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = part[i];
+  for (int sp = 1; sp < nsplit; sp++) s += part[(int64_t)sp * n + i];
+  red[i] = s;
+}
+cudaError_t launch_reduce_splits(const double* part, int nsplit, int64_t rows, int64_t Cp, double* red, cudaStream_t st) {
+  int64_t n = rows * Cp;
+  reduce_splits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nsplit, n, red);
+  return cudaGetLastError();
+}
+
+// ---- layout kernels ---------------------------------------------------------------------------
+template <typename T>
+__global__ void transpose_kernel(const T* in, T* out, int64_t rows_in, int64_t cols_in, int64_t in_pitch, int64_t out_pitch,
+                                 int64_t in_col0) {
+  // out[cidx][r] = in[r][in_col0 + cidx] for r < rows_in, cidx < cols_in  (generic tiled transpose)
+  __shared__ T tile[32][33];
+  int64_t bx = (int64_t)blockIdx.x * 32, by = (int64_t)blockIdx.y * 32;
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    int64_t r = by + k, cc = bx + threadIdx.x;
+    if (r < rows_in && cc < cols_in) tile[k][threadIdx.x] = in[r * in_pitch + in_col0 + cc];
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += blockDim.y) {
+    int64_t cc = bx + k, r = by + threadIdx.x;
+    if (r < rows_in && cc < cols_in) out[cc * out_pitch + r] = tile[threadIdx.x][k];
+  }
+}
+static dim3 tgrid(int64_t rows, int64_t cols) { return dim3((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)); }
+
+cudaError_t transpose_to_chain_minor(const double* in, double* out, int64_t C, int64_t K, int64_t Cp, cudaStream_t st) {
+  // in [C][K] -> out [K][Cp]
+  dim3 g = tgrid(C, K);
+  if (g.y > 65535) return cudaErrorInvalidValue;
+  transpose_kernel<double><<<g, dim3(32, 8), 0, st>>>(in, out, C, K, K, Cp, 0);
+  return cudaGetLastError();
+}
+cudaError_t transpose_to_chain_major(const double* in, double* out, int64_t c0, int64_t nc, int64_t K, int64_t Cp, cudaStream_t st) {
+  // in [K][Cp] (columns c0..c0+nc) -> out [nc][K]
+  for (int64_t k0 = 0; k0 < K; k0 += 65535LL * 32) {
+    int64_t kk = K - k0 < 65535LL * 32 ? K - k0 : 65535LL * 32;
+    transpose_kernel<double><<<tgrid(kk, nc), dim3(32, 8), 0, st>>>(in + k0 * Cp, out + k0, kk, nc, Cp, K, c0);
+  }
+  return cudaGetLastError();
+}
+cudaError_t transpose_to_chain_major_u8(const uint8_t* in, uint8_t* out, int64_t c0, int64_t nc, int64_t K, int64_t Cp, cudaStream_t st) {
+  for (int64_t k0 = 0; k0 < K; k0 += 65535LL * 32) {
+    int64_t kk = K - k0 < 65535LL * 32 ? K - k0 : 65535LL * 32;
+    transpose_kernel<uint8_t><<<tgrid(kk, nc), dim3(32, 8), 0, st>>>(in + k0 * Cp, out + k0, kk, nc, Cp, K, c0);
+  }
+  return cudaGetLastError();
+}
+
+__global__ void philox_dump_kernel(uint64_t seed, int64_t chain_offset, int64_t C, int64_t d, int64_t last,
+                                   double* normals, double* uniforms) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * (last + 1)) return;
+  const int64_t c = idx / (last + 1), i = idx % (last + 1);
+  const uint64_t gchain = (uint64_t)(chain_offset + c);
+  for (int64_t jb = 0; jb < d; jb += 2) {
+    double z0, z1;
+    philox_normal_pair(seed, gchain, (uint32_t)i, (uint32_t)(jb >> 1), z0, z1);
+    normals[(c * (last + 1) + i) * d + jb] = z0;
+    if (jb + 1 < d) normals[(c * (last + 1) + i) * d + jb + 1] = z1;
+  }
+  uniforms[c * (last + 1) + i] = philox_uniform(seed, gchain, (uint32_t)i);
+}
+cudaError_t launch_philox_dump(uint64_t seed, int64_t chain_offset, int64_t C, int64_t d, int64_t last,
+                               double* normals, double* uniforms, cudaStream_t st) {
+  int64_t n = C * (last + 1);
+  philox_dump_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seed, chain_offset, C, d, last, normals, uniforms);
+  return cudaGetLastError();
+}
+
+__global__ void fill_kernel(double* p, double v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+cudaError_t launch_fill(double* p, double v, int64_t n, cudaStream_t st) {
+  fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+}  // namespace mg

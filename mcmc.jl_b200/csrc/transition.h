@@ -1,0 +1,55 @@
+#pragma once
+#include "common.cuh"
+namespace mg {
+
+// per-chain phases of the wave engine
+constexpr int PH_INIT = 0;   // q = init has been evaluated
+constexpr int PH_RWM = 1;    // q = RWM proposal has been evaluated
+constexpr int PH_MALA = 2;   // q = MALA proposal has been evaluated
+constexpr int PH_LEAP = 3;   // q = position after a leapfrog position update has been evaluated
+constexpr int PH_DONE = 99;
+
+struct WaveArgs {
+  ModelDev M;
+  SamplerDev S;
+  RunnerDev R;
+  int32_t nsplit;              // partial buffers to sum (1 after an all-reduce)
+  int32_t row_sharded_prior;   // unused placeholder (prior is always added here, once)
+  // evaluation in/out
+  double* q;                   // [d][Cp]
+  const double* part;          // [nsplit][d+2][Cp]
+  // chain state
+  double *cur_pars, *cur_grad, *cur_lt, *mom, *H0;
+  int32_t *phase, *leap, *nleaps_cur;
+  int64_t *istep, *kept;
+  double *eps_cur;
+  double *da_leapstep, *da_dual, *da_dualH;
+  double *tn_step; int64_t *tn_nleaps, *tn_acc, *tn_prop;
+  uint8_t* need_ll;
+  int32_t* status;
+  int32_t* remaining;
+  unsigned long long* n_evals;
+  // inputs
+  const double* init; const double* scale; const double* inj_normals; const double* inj_uniforms;
+  // outputs
+  double* samples; double* grads; uint8_t* accept; double* logtarget; double* eps; int32_t* nleaps;
+  double* final_eps;
+};
+
+cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st);
+// closed-form families through the wave engine: writes part[0][(d+2)][Cp] directly (final lt / grad)
+cudaError_t launch_eval_closed(const ModelDev& M, const double* q, double* part, int64_t C, int64_t Cp,
+                               const int32_t* phase, const int32_t* remaining, cudaStream_t st);
+// finalize an evaluation outside a run (mcmcgpu_logtarget_grad): part -> lt[Cp], grad[d][Cp]
+cudaError_t launch_finalize(const ModelDev& M, const double* q, const double* part, int nsplit, int64_t C, int64_t Cp,
+                            double* lt, double* grad, cudaStream_t st);
+cudaError_t launch_reduce_splits(const double* part, int nsplit, int64_t rows, int64_t Cp, double* red, cudaStream_t st);
+// layout changes between the host's chain-major arrays and the device's chain-minor arrays
+cudaError_t transpose_to_chain_minor(const double* in /*[C][K]*/, double* out /*[K][Cp]*/, int64_t C, int64_t K, int64_t Cp, cudaStream_t st);
+cudaError_t transpose_to_chain_major(const double* in /*[K][Cp]*/, double* out /*[nc][K]*/, int64_t c0, int64_t nc, int64_t K, int64_t Cp, cudaStream_t st);
+cudaError_t transpose_to_chain_major_u8(const uint8_t* in, uint8_t* out, int64_t c0, int64_t nc, int64_t K, int64_t Cp, cudaStream_t st);
+cudaError_t launch_philox_dump(uint64_t seed, int64_t chain_offset, int64_t C, int64_t d, int64_t last,
+                               double* normals /*[C][last+1][d]*/, double* uniforms /*[C][last+1]*/, cudaStream_t st);
+cudaError_t launch_fill(double* p, double v, int64_t n, cudaStream_t st);
+
+}  // namespace mg

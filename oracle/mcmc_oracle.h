@@ -1,0 +1,108 @@
+/*
+ * mcmc_oracle.h -- CPU restatement (plain C99, FP64, scalar, single thread) of the MCMC.jl hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may build, load or
+ * call it, and there only as the checker / the timed CPU baseline.  The product (libmcmcgpu.so)
+ * never links or calls it.
+ *
+ * PARITY STATUS: "parity unpinned".  The reference (dingliumath/MCMC.jl, Julia 0.2) cannot be run
+ * here (no julia; src/dsl/modelparser.jl:13 includes a file from the author's home directory) and
+ * its own tests hold no numeric golden vectors for this path.  The oracle is
+ * therefore anchored on (i) line-by-line restatement, each function citing the reference file:line,
+ * (ii) independent numpy/scipy re-derivations and finite differences in tests/, (iii) the soft
+ * statistical bands of README.md:121-204 and (iv) Random123 known-answer vectors for Philox.
+ *
+ * All matrices are dense column-major double (Julia native layout).
+ */
+#ifndef MCMC_ORACLE_H
+#define MCMC_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Likelihood families. */
+enum {
+  ORC_FAM_NORMAL_FN = 0, /* README.md:60,63  v -> -dot(v,v), grad v -> -2v                         */
+  ORC_FAM_NORMAL_DSL = 1,/* README.md:67-72  v ~ Normal(mu, sigma)         hyper = {mu, sigma}      */
+  ORC_FAM_LINEAR = 2,    /* examples/linear_regression.jl:14-18            hyper = {prior_sd, noise_sd} */
+  ORC_FAM_LOGISTIC = 3,  /* examples/logistic_regression.jl:16-20          hyper = {prior_sd, sign} sign=-1: exp(-X*b) (example); +1: test/test_syntax.jl:18 */
+  ORC_FAM_PROBIT = 4,    /* examples/probit_regression.jl:18-41            hyper = {prior_sd}        */
+  ORC_FAM_OU = 5         /* examples/ornstein.jl:19-27                     hyper = {tau_hi, sigma_hi, mu_hi}; y = series x[0..N-1], d = 3 (tau, sigma, mu) */
+};
+
+typedef struct {
+  int32_t family;
+  int64_t N;       /* observations (rows of X / length of series); 0 for the Normal families */
+  int64_t d;       /* parameter count */
+  const double* X; /* N x d column-major, or NULL */
+  const double* y; /* N, or NULL */
+  double hyper[4];
+} orc_model;
+
+/* Samplers. */
+enum { ORC_RWM = 0, ORC_MALA = 1, ORC_HMC = 2, ORC_HMCDA = 3 };
+
+typedef struct {
+  int32_t kind;
+  double scale;      /* RWM scale (RWM.jl:24-36) | MALA driftStep (MALA.jl:50-62) | HMC leapStep (HMC.jl:53-74) */
+  int32_t nleaps;    /* HMC nLeaps */
+  /* HMCDA (HMCDA.jl:24-43) */
+  double rate, len, shrinkage, t0, step;
+  int64_t max_leaps; /* safety cap on HMCDA nLeaps (documented deviation; 0 = uncapped) */
+  /* EmpMCTuner (samplers.jl:32-50) for MALA / HMC; enabled when tuner_on != 0 */
+  int32_t tuner_on;
+  int32_t adapt_step, max_step;
+  double target_path, target_rate;
+  /* test aid (not in the reference): HMCDA adaptation is a chaotic map once the step size crosses the
+   * integrator's stability limit, so last-bit differences between libm implementations grow without
+   * bound over a burn-in.  When force_eps != NULL (length last+1) the trajectory of step i uses
+   * force_eps[i] while diag_eps still reports the oracle's own adapted value: a one-step-ahead check. */
+  const double* force_eps;
+} orc_sampler;
+
+typedef struct {
+  int64_t first, step, last; /* SerialMC range first:step:last (SerialMC.jl:12-35); burnin = first-1 */
+} orc_range;
+
+/* ---- models ---- */
+double orc_eval(const orc_model* m, const double* beta);                  /* model.eval     */
+double orc_evalallg(const orc_model* m, const double* beta, double* grad); /* model.evalallg */
+double orc_log_ndtr(double x); /* log Phi(x) */
+
+/* ---- one chain, injected draws (SerialMC.jl:37-85 around the sampler loop bodies) ----
+ * normals : d x (last+1) column-major; column 0 is the pre-loop draw (used by HMCDA only,
+ *           HMCDA.jl:90), column i (1-based step index) feeds step i.
+ * uniforms: last+1; entry i feeds the MH test of step i (entry 0 unused).
+ * outputs (any may be NULL): samples d x S, grads d x S (NaN-filled for RWM), accept S,
+ * logtarget S (plogtarget of the produced MCMCSample), diag_eps S (HMCDA leapStep used at the
+ * kept step), diag_nleaps S.  S = number of kept steps = length(first:step:last).
+ * returns 0, or -1 "Initial values out of model support", -2 bad arguments.
+ */
+int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range* r,
+                      const double* init, const double* scale,
+                      const double* normals, const double* uniforms,
+                      double* samples, double* grads, uint8_t* accept, double* logtarget,
+                      double* diag_eps, int64_t* diag_nleaps, int64_t* n_grad_evals);
+int64_t orc_range_length(const orc_range* r);
+
+/* ---- stats over one stored series x[0..n-1] (src/stats) ---- */
+double orc_mean(const double* x, int64_t n);                     /* mean.jl:6         */
+double orc_mcvar_iid(const double* x, int64_t n);                /* var.jl:7-8        */
+double orc_mcvar_bm(const double* x, int64_t n, int64_t batchlen); /* var.jl:20-26    */
+double orc_mcvar_imse(const double* x, int64_t n, int64_t maxlag); /* var.jl:45-75    */
+double orc_mcvar_ipse(const double* x, int64_t n, int64_t maxlag); /* var.jl:95-116   */
+void orc_acov(const double* x, int64_t n, int64_t maxlag, double* acv); /* StatsBase.acf(x, 0:maxlag, correlation=false) */
+
+/* ---- Philox4x32-10 (Random123; Salmon et al. SC'11) and the draw conventions of the engine ---- */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+/* engine conventions: key = (seed lo, seed hi); ctr = (chain lo, chain hi, step, block);
+ * normals block b -> normals 2b, 2b+1 (Box-Muller); uniform for the MH test uses block 0xFFFFFFFF. */
+void orc_draw_normals(uint64_t seed, uint64_t chain, uint32_t step, int64_t d, double* z);
+double orc_draw_uniform(uint64_t seed, uint64_t chain, uint32_t step);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
