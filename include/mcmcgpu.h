@@ -140,6 +140,16 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
                            const double* init, const double* scale, const double* inj_normals,
                            const double* inj_uniforms, mcmcgpu_run** out);
 int32_t mcmcgpu_run_execute(mcmcgpu_run* run, mcmcgpu_run_info* info);
+/* stepwise execution (engine WAVE): advance every chain by nsteps more MCMC steps and pause; a later
+ * call continues exactly where the chains stopped (same Philox counters, same adaptation state). */
+int32_t mcmcgpu_run_execute_steps(mcmcgpu_run* run, int64_t nsteps, mcmcgpu_run_info* info);
+/* true resume (the reference's resume restarts from model.init, SerialMC.jl:93-97): before the first
+ * execute, start the chains at step step0 + 1 (init = the saved positions) and, for HMCDA, restore the
+ * dual-averaging state (arrays of nchains, or all NULL for the reference's initial values). */
+int32_t mcmcgpu_run_set_state(mcmcgpu_run* run, int64_t step0, const double* leapstep, const double* dual_leapstep,
+                              const double* dualH);
+/* current positions (d x nchains) and HMCDA state (nchains each); any pointer may be NULL */
+int32_t mcmcgpu_run_get_state(mcmcgpu_run* run, double* pars, double* leapstep, double* dual_leapstep, double* dualH);
 int32_t mcmcgpu_run_fetch(mcmcgpu_run* run, double* out_samples, double* out_grads, uint8_t* out_accept,
                           double* out_logtarget);
 /* per-chain diagnostics: final leap step (HMCDA/tuned), kept-step leap steps (S x nchains) and leap counts */

@@ -51,7 +51,8 @@ EXPORTS = [
     "mcmcgpu_abi_version", "mcmcgpu_last_error", "mcmcgpu_init", "mcmcgpu_destroy", "mcmcgpu_set_stream",
     "mcmcgpu_set_option", "mcmcgpu_comm_unique_id", "mcmcgpu_comm_init", "mcmcgpu_model_create",
     "mcmcgpu_model_destroy", "mcmcgpu_logtarget_grad", "mcmcgpu_run_chains", "mcmcgpu_run_create",
-    "mcmcgpu_run_execute", "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
+    "mcmcgpu_run_execute", "mcmcgpu_run_execute_steps", "mcmcgpu_run_set_state", "mcmcgpu_run_get_state",
+    "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
     "mcmcgpu_run_destroy", "mcmcgpu_stats", "mcmcgpu_philox_draws",
 ]
 
@@ -84,6 +85,9 @@ def lib():
         L.mcmcgpu_run_create.argtypes = [vp, C.POINTER(SamplerCfg), C.POINTER(RunnerCfg), dp, dp, dp, dp,
                                          C.POINTER(vp)]
         L.mcmcgpu_run_execute.argtypes = [vp, C.POINTER(RunInfo)]
+        L.mcmcgpu_run_execute_steps.argtypes = [vp, C.c_int64, C.POINTER(RunInfo)]
+        L.mcmcgpu_run_set_state.argtypes = [vp, C.c_int64, dp, dp, dp]
+        L.mcmcgpu_run_get_state.argtypes = [vp, dp, dp, dp, dp]
         L.mcmcgpu_run_fetch.argtypes = [vp, dp, dp, C.POINTER(C.c_uint8), dp]
         L.mcmcgpu_run_fetch_diag.argtypes = [vp, dp, C.POINTER(C.c_int64)]
         L.mcmcgpu_run_stats.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, dp]
@@ -234,6 +238,23 @@ class DeviceRun:
         self.info = info.as_dict()
         check(rc)
         return self.info
+
+    def execute_steps(self, nsteps):
+        info = RunInfo()
+        rc = lib().mcmcgpu_run_execute_steps(self.h, int(nsteps), C.byref(info))
+        self.info = info.as_dict()
+        check(rc)
+        return self.info
+
+    def set_state(self, step0, leapstep=None, dual_leapstep=None, dualH=None):
+        a, b, c = f64(leapstep), f64(dual_leapstep), f64(dualH)
+        check(lib().mcmcgpu_run_set_state(self.h, int(step0), dptr(a), dptr(b), dptr(c)))
+
+    def get_state(self):
+        pars = np.empty((self.C, self.d))
+        ls, du, dh = np.empty(self.C), np.empty(self.C), np.empty(self.C)
+        check(lib().mcmcgpu_run_get_state(self.h, dptr(pars), dptr(ls), dptr(du), dptr(dh)))
+        return dict(pars=pars, leapstep=ls, dual_leapstep=du, dualH=dh)
 
     def fetch(self, samples=True, grads=None, accept=True, logtarget=None, out=None):
         grads = self.store_grad if grads is None else grads

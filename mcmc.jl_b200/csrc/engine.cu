@@ -64,8 +64,12 @@ struct mcmcgpu_run {
   mcmcgpu_runner_cfg r;
   int engine = 0;
   int64_t C = 0, Cp = 0, S = 0, d = 0;
-  bool executed = false;
+  bool executed = false;     // at least one execute call has run
+  bool started = false;      // the init wave has run
   bool has_diag = false;
+  int64_t step0 = 0;         // chains start at step step0 + 1 (mcmcgpu_run_set_state)
+  int64_t step_limit = 0;    // last step the chains have been allowed to run so far
+  bool restore_da = false;
   // inputs
   double *init = nullptr, *scale = nullptr, *inj_normals = nullptr, *inj_uniforms = nullptr;
   // outputs
@@ -474,12 +478,16 @@ __global__ void wave_init_kernel(int32_t* phase, int32_t* remaining, double* q, 
   for (int64_t j = 0; j < d; j++) q[j * Cp + c] = (c < C) ? (init_per_chain ? init[j * Cp + c] : init[j]) : 0.0;
 }
 
-int32_t mcmcgpu_run_execute(mcmcgpu_run* R, mcmcgpu_run_info* info) {
-  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) {
   mcmcgpu_model* m = R->m;
   mcmcgpu_ctx* c = m->ctx;
   CU(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
+  const int64_t from = R->started ? R->step_limit : R->step0;
+  if (from >= R->r.last) return fail(MCMCGPU_E_STATE, "run has already reached its last step");
+  int64_t upto = (nsteps < 0 || from + nsteps > R->r.last) ? R->r.last : from + nsteps;
+  const int64_t seg = upto - from;
+  if (seg <= 0) return fail(MCMCGPU_E_ARG, "nsteps must be >= 1");
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
   int64_t launches = 0, waves = 0;
@@ -487,6 +495,8 @@ int32_t mcmcgpu_run_execute(mcmcgpu_run* R, mcmcgpu_run_info* info) {
   CU(cudaMemsetAsync(R->n_evals, 0, sizeof(unsigned long long), st));
   CU(cudaEventRecord(e0, st));
   if (R->engine == MCMCGPU_ENGINE_FUSED) {
+    if (R->started || upto != R->r.last || R->step0 != 0)
+      return fail(MCMCGPU_E_STATE, "engine FUSED runs the whole chain in one launch: use mcmcgpu_run_execute, or engine WAVE for stepwise execution");
     FusedArgs A;
     A.M = m->dev(); A.S = sampler_dev(R); A.R = runner_dev(R);
     A.init = R->init; A.scale = R->scale; A.inj_normals = R->inj_normals; A.inj_uniforms = R->inj_uniforms;
@@ -495,10 +505,11 @@ int32_t mcmcgpu_run_execute(mcmcgpu_run* R, mcmcgpu_run_info* info) {
     A.status = R->status; A.n_evals = R->n_evals;
     CU(launch_fused(A, st));
     launches = 1;
+    R->started = true;
   } else {
     WaveArgs W;
     W.M = m->dev(); W.S = sampler_dev(R); W.R = runner_dev(R);
-    W.nsplit = R->nsplit; W.row_sharded_prior = 0;
+    W.nsplit = R->nsplit; W.resume = 0; W.restore_da = R->restore_da ? 1 : 0; W.step0 = R->step0; W.step_limit = upto;
     W.q = R->q; W.part = R->part;
     W.cur_pars = R->cur_pars; W.cur_grad = R->cur_grad; W.cur_lt = R->cur_lt; W.mom = R->mom; W.H0 = R->H0;
     W.phase = R->phase; W.leap = R->leap; W.nleaps_cur = R->nleaps_cur; W.istep = R->istep; W.kept = R->kept;
@@ -508,19 +519,29 @@ int32_t mcmcgpu_run_execute(mcmcgpu_run* R, mcmcgpu_run_info* info) {
     W.init = R->init; W.scale = R->scale; W.inj_normals = R->inj_normals; W.inj_uniforms = R->inj_uniforms;
     W.samples = R->samples; W.grads = R->grads; W.accept = R->accept; W.logtarget = R->logtarget;
     W.eps = R->eps; W.nleaps = R->nleaps; W.final_eps = R->final_eps;
-    CU(cudaMemsetAsync(R->kept, 0, sizeof(int64_t) * (size_t)R->Cp, st));
-    wave_init_kernel<<<(unsigned)((R->Cp + 127) / 128), 128, 0, st>>>(R->phase, R->remaining, R->q, R->init,
-                                                                       R->r.init_per_chain, R->C, R->Cp, R->d);
-    CU(cudaGetLastError());
-    launches++;
     const int kind = R->s.kind;
     const bool need_grad = (kind != MCMCGPU_RWM);
     // number of waves when it is known in advance; otherwise poll the device counter
     int64_t known = -1;
-    if (kind == MCMCGPU_RWM || kind == MCMCGPU_MALA) known = R->r.last + 1;
-    else if (kind == MCMCGPU_HMC && !R->s.tuner_on) known = 1 + R->r.last * (int64_t)R->s.nleaps;
+    if (kind == MCMCGPU_RWM || kind == MCMCGPU_MALA) known = seg;
+    else if (kind == MCMCGPU_HMC && !R->s.tuner_on) known = seg * (int64_t)R->s.nleaps;
+    bool first = false;
+    if (!R->started) {
+      CU(cudaMemsetAsync(R->kept, 0, sizeof(int64_t) * (size_t)R->Cp, st));
+      wave_init_kernel<<<(unsigned)((R->Cp + 127) / 128), 128, 0, st>>>(R->phase, R->remaining, R->q, R->init,
+                                                                         R->r.init_per_chain, R->C, R->Cp, R->d);
+      CU(cudaGetLastError());
+      launches++;
+      if (known >= 0) known += 1;   // the wave that evaluates the initial point
+      first = true;
+      R->started = true;
+    } else {
+      W.resume = 1;                  // restart the paused chains: they draw and write their next pending point
+      CU(launch_transition(W, st));
+      W.resume = 0;
+      launches++;
+    }
     std::vector<cudaEvent_t> evs;
-    bool first = true;
     for (;;) {
       const double* pp; int ns;
       cudaEvent_t a0 = nullptr, a1 = nullptr;
@@ -555,6 +576,7 @@ int32_t mcmcgpu_run_execute(mcmcgpu_run* R, mcmcgpu_run_info* info) {
   CU(cudaEventElapsedTime(&ms, e0, e1));
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   R->executed = true;
+  R->step_limit = upto;
   unsigned long long nev = 0;
   CU(cudaMemcpy(&nev, R->n_evals, sizeof(nev), cudaMemcpyDeviceToHost));
   if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = waves; info->n_launches = launches; info->eval_ms = eval_ms; }
@@ -564,6 +586,66 @@ int32_t mcmcgpu_run_execute(mcmcgpu_run* R, mcmcgpu_run_info* info) {
   int64_t nbad = 0;
   for (int32_t v : stt) nbad += (v != 0);
   if (nbad) return fail(MCMCGPU_E_SUPPORT, "Initial values out of model support, try other values (" + std::to_string(nbad) + " chain(s))");
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_execute(mcmcgpu_run* R, mcmcgpu_run_info* info) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  return execute_impl(R, -1, info);
+}
+
+int32_t mcmcgpu_run_execute_steps(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  if (nsteps < 1) return fail(MCMCGPU_E_ARG, "nsteps must be >= 1");
+  return execute_impl(R, nsteps, info);
+}
+
+static int upload_chain_vec(mcmcgpu_run* R, double* dst, const double* src) {
+  return cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)R->C, cudaMemcpyHostToDevice, R->m->ctx->stream) == cudaSuccess
+             ? MCMCGPU_OK : fail(MCMCGPU_E_CUDA, "CUDA: state upload failed");
+}
+
+int32_t mcmcgpu_run_set_state(mcmcgpu_run* R, int64_t step0, const double* leapstep, const double* dual_leapstep,
+                              const double* dualH) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  if (R->started) return fail(MCMCGPU_E_STATE, "state must be set before the first execute");
+  if (R->engine != MCMCGPU_ENGINE_WAVE) return fail(MCMCGPU_E_STATE, "mcmcgpu_run_set_state needs engine WAVE");
+  if (step0 < 0 || step0 >= R->r.last) return fail(MCMCGPU_E_ARG, "step0 must be in [0, last)");
+  if (R->r.first <= step0) return fail(MCMCGPU_E_ARG, "the kept range must start after step0");
+  CU(cudaSetDevice(R->m->ctx->device));
+  R->step0 = step0;
+  if (leapstep || dual_leapstep || dualH) {
+    if (R->s.kind != MCMCGPU_HMCDA) return fail(MCMCGPU_E_ARG, "step-size state applies to HMCDA");
+    if (!leapstep || !dual_leapstep || !dualH) return fail(MCMCGPU_E_ARG, "give leapstep, dual_leapstep and dualH together");
+    int rc;
+    if ((rc = upload_chain_vec(R, R->da_leapstep, leapstep))) return rc;
+    if ((rc = upload_chain_vec(R, R->da_dual, dual_leapstep))) return rc;
+    if ((rc = upload_chain_vec(R, R->da_dualH, dualH))) return rc;
+    CU(cudaStreamSynchronize(R->m->ctx->stream));
+    R->restore_da = true;
+  }
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_get_state(mcmcgpu_run* R, double* pars, double* leapstep, double* dual_leapstep, double* dualH) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
+  if (R->engine != MCMCGPU_ENGINE_WAVE) return fail(MCMCGPU_E_STATE, "mcmcgpu_run_get_state needs engine WAVE");
+  CU(cudaSetDevice(R->m->ctx->device));
+  cudaStream_t st = R->m->ctx->stream;
+  if (pars) {
+    double* tmp = nullptr;
+    CU(dalloc(&tmp, (size_t)(R->C * R->d)));
+    CU(transpose_to_chain_major(R->cur_pars, tmp, 0, R->C, R->d, R->Cp, st));
+    CU(cudaMemcpyAsync(pars, tmp, sizeof(double) * (size_t)(R->C * R->d), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  }
+  const double* src[3] = {R->da_leapstep, R->da_dual, R->da_dualH};
+  double* dst[3] = {leapstep, dual_leapstep, dualH};
+  for (int k = 0; k < 3; k++)
+    if (dst[k]) CU(cudaMemcpyAsync(dst[k], src[k], sizeof(double) * (size_t)R->C, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return MCMCGPU_OK;
 }
 

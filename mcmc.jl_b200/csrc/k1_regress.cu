@@ -18,20 +18,22 @@
 //
 // Algorithmic work per (row, chain): 4*d flop (2d for eta, 2d for X'r); bound: FP64 tensor pipe.
 #include "k1_regress.h"
+#include <cmath>
 #include <cstdio>
 
 namespace mg {
 
-constexpr int K1_STAGES = 4;
+constexpr int K1_STAGES = 2;
 constexpr int K1_THREADS = K1_WARPS * 32;
-constexpr int PH_DONE_K1 = 99;  // must equal PH_DONE in transition.h
+constexpr int K1_NR = 4;          // 8-row groups per phase-1 pass (independent DMMA accumulator chains)
+constexpr int PH_IDLE_K1 = 98;  // phases >= PH_PAUSE (98) have no pending evaluation (transition.h)
 
 // row permutation inside an 8-row group: column n of the phase-1 B fragment reads row PI[n]
 // (bank-conflict-free for both phases when the row stride is 4 mod 8 doubles)
 __device__ __forceinline__ int pi8(int n) { return (n < 4) ? n : (n ^ 1); }
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -110,13 +112,18 @@ __device__ __forceinline__ LinkOut link(double eta, double y, const double* hy, 
 }
 
 // ---- the kernel -----------------------------------------------------------------------------
-template <int FAM, int DK>
-__global__ void __launch_bounds__(K1_THREADS, 1) k1_kernel(const K1Args a) {
+// Shared memory per CTA: beta tile [64 chains][S] (A fragments of phase 1), STAGES X tiles, barriers.
+// 256 threads, <= 128 registers, two CTAs per SM: 16 warps keep the DMMA pipe fed while other warps
+// are in the (latency-bound) link-function epilogue.
+template <int FAM, int DK, int NR>
+__global__ void __launch_bounds__(K1_THREADS, 2) k1_kernel(const K1Args a) {
   constexpr int S = 8 * DK + 4;
   constexpr int KS = 2 * DK;                  // k-steps of 4 features in phase 1
   constexpr int TILE_D = K1_ROWS * S + K1_ROWS;
+  constexpr int NG = K1_ROWS / (8 * NR);      // row groups per tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* tiles = reinterpret_cast<double*>(smem_raw);
+  double* betas = reinterpret_cast<double*>(smem_raw);
+  double* tiles = betas + K1_CHAINS * S;
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)K1_STAGES * TILE_D);
   uint64_t* empty = full + K1_STAGES;
 
@@ -129,9 +136,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_kernel(const K1Args a) {
   const int64_t Cp = a.Cp;
   const int d = (int)a.P.d;
 
-  // skip chain tiles whose chains have all finished (asynchronous HMCDA trajectories)
+  // skip chain tiles whose chains have no pending evaluation (asynchronous HMCDA trajectories)
   int alive = 1;
-  if (a.phase) alive = (a.phase[chain0 + (tid & (K1_CHAINS - 1))] != PH_DONE_K1);
+  if (a.phase) alive = (a.phase[chain0 + (tid & (K1_CHAINS - 1))] < PH_IDLE_K1);
   if (!__syncthreads_or(alive)) return;
 
   // tile range of this split
@@ -145,20 +152,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_kernel(const K1Args a) {
     for (int s = 0; s < K1_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K1_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // beta tile: betas[c][j] = q[j][chain0 + c] (zero-padded features)
+  for (int idx = tid; idx < K1_CHAINS * 8 * DK; idx += K1_THREADS) {
+    const int j = idx / K1_CHAINS, c = idx % K1_CHAINS;
+    betas[c * S + j] = (j < d) ? a.q[(int64_t)j * Cp + chain0 + c] : 0.0;
+  }
   __syncthreads();
   if (tid == 0) {
     for (int s = 0; s < K1_STAGES && s < nt; s++) {
       mbar_expect_tx(&full[s], tile_bytes);
       bulk_g2s(tiles + (size_t)s * TILE_D, a.P.tiles + (t0 + s) * a.P.tile_doubles, tile_bytes, &full[s]);
     }
-  }
-
-  // beta fragments: A operand of phase 1, a[ks] = beta[chain g][feature 4ks + t]
-  double bf[KS];
-#pragma unroll
-  for (int ks = 0; ks < KS; ks++) {
-    int j = 4 * ks + t;
-    bf[ks] = (j < d) ? a.q[(int64_t)j * Cp + mychain] : 0.0;
   }
   // per-warp flag: does any of this warp's chains need the log-likelihood value this wave?
   bool need_ll = true;
@@ -172,9 +176,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_kernel(const K1Args a) {
   const double hy[4] = {a.hyper[0], a.hyper[1], a.hyper[2], a.hyper[3]};
   const int64_t N = a.P.N;
 
-  // shared-memory offsets of this lane's fragment elements inside a tile (doubles)
+  // shared-memory offsets of this lane's fragment elements (doubles)
+  //   phase 1 A fragment: beta[chain 8w+g][4ks + t]
   //   phase 1 B fragment: X[8n + pi(g)][4ks + t]
   //   phase 2 B fragment: X[8n + pi(2t+s)][8jb + g]
+  const double* bfrag = betas + (warp * 8 + g) * S + t;
   const int off1 = pi8(g) * S + t;
   const int row2a = pi8(2 * t), row2b = pi8(2 * t + 1);
   const int off2a = row2a * S + g, off2b = row2b * S + g;
@@ -187,41 +193,50 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_kernel(const K1Args a) {
     const double* ys = X + K1_ROWS * S;
     const int64_t rowbase = (t0 + it) * K1_ROWS;
 
-    // ---- phase 1: eta for 32 rows x 8 chains ----
-    double acc[4][2];
+#pragma unroll 1
+    for (int rg = 0; rg < NG; rg++) {
+      const double* Xg = X + rg * (8 * NR) * S;
+      // ---- phase 1: eta for 8*NR rows x 8 chains ----
+      double acc[NR][2];
 #pragma unroll
-    for (int n = 0; n < 4; n++) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+      for (int n = 0; n < NR; n++) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+#pragma unroll 4
+      for (int ks = 0; ks < KS; ks++) {
+        const double av = bfrag[4 * ks];
 #pragma unroll
-    for (int ks = 0; ks < KS; ks++) {
-#pragma unroll
-      for (int n = 0; n < 4; n++) {
-        double b = X[off1 + n * 8 * S + 4 * ks];
-        dmma(acc[n][0], acc[n][1], bf[ks], b);
+        for (int n = 0; n < NR; n++) {
+          double b = Xg[off1 + n * 8 * S + 4 * ks];
+          dmma(acc[n][0], acc[n][1], av, b);
+        }
       }
-    }
-    // ---- epilogue: link function on this lane's 8 (row, chain) elements ----
+      // ---- epilogue: link function on this lane's 2*NR (row, chain) elements ----
 #pragma unroll
-    for (int n = 0; n < 4; n++) {
+      for (int n = 0; n < NR; n++) {
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        const int lr = 8 * n + (s ? row2b : row2a);      // local row of accumulator column 2t+s
-        const double y = ys[lr];
-        LinkOut o = link<FAM>(acc[n][s], y, hy, need_ll);
-        const bool valid = (rowbase + lr) < N;
-        if (valid) { ll1 += o.ll1; ll2 += o.ll2; nbad += o.bad ? 1 : 0; }
-        acc[n][s] = o.r;    // rows >= N have X == 0, so their r never reaches G
+        for (int s = 0; s < 2; s++) {
+          const int lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);   // local row of accumulator column 2t+s
+          const double y = ys[lr];
+          LinkOut o = link<FAM>(acc[n][s], y, hy, need_ll);
+          const bool valid = (rowbase + lr) < N;
+          if (valid) { ll1 += o.ll1; ll2 += o.ll2; nbad += o.bad ? 1 : 0; }
+          acc[n][s] = o.r;    // rows >= N have X == 0, so their r never reaches G
+        }
       }
-    }
-    // ---- phase 2: G += r^T X ----
-    if (a.need_grad) {
+      // ---- phase 2: G += r^T X ----
+      if (a.need_grad) {
+        // consecutive DMMAs go to different accumulators (DK independent chains)
 #pragma unroll
-      for (int n = 0; n < 4; n++) {
+        for (int n = 0; n < NR; n++) {
 #pragma unroll
-        for (int jb = 0; jb < DK; jb++) {
-          double b0 = X[off2a + n * 8 * S + 8 * jb];
-          dmma(G[jb][0], G[jb][1], acc[n][0], b0);
-          double b1 = X[off2b + n * 8 * S + 8 * jb];
-          dmma(G[jb][0], G[jb][1], acc[n][1], b1);
+          for (int jb = 0; jb < DK; jb++) {
+            double b0 = Xg[off2a + n * 8 * S + 8 * jb];
+            dmma(G[jb][0], G[jb][1], acc[n][0], b0);
+          }
+#pragma unroll
+          for (int jb = 0; jb < DK; jb++) {
+            double b1 = Xg[off2b + n * 8 * S + 8 * jb];
+            dmma(G[jb][0], G[jb][1], acc[n][1], b1);
+          }
         }
       }
     }
@@ -293,30 +308,39 @@ cudaError_t k1_pack(K1Pack& P, const double* dX, const double* dy, int64_t N, in
 void k1_free(K1Pack& P) { if (P.tiles) cudaFree(P.tiles); P.tiles = nullptr; }
 
 int k1_choose_splits(const K1Pack& P, int64_t Cp) {
-  int64_t ctiles = Cp / K1_CHAINS;
+  // Row splits: enough CTAs to fill the machine, and a CTA count whose last wave is nearly full
+  // (two resident CTAs per SM).  Every split keeps >= 8 tiles so the prologue stays amortised.
+  const int64_t ctiles = Cp / K1_CHAINS;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  int64_t want = (8LL * sms + ctiles - 1) / ctiles;      // aim for >= 8 CTAs per SM in total
-  int64_t maxs = P.ntiles / (2 * K1_STAGES);             // keep >= 8 tiles per CTA
+  const int64_t slots = 2LL * sms;
+  int64_t maxs = P.ntiles / 8;
   if (maxs < 1) maxs = 1;
-  if (want > maxs) want = maxs;
-  if (want > 64) want = 64;
-  if (want < 1) want = 1;
-  return (int)want;
+  if (maxs > 64) maxs = 64;
+  int best = 1; double beste = -1.0;
+  for (int64_t s = 1; s <= maxs; s++) {
+    const double waves = (double)(ctiles * s) / (double)slots;
+    double eff = waves / std::ceil(waves);
+    if (waves < 1.0) eff = waves;              // not enough CTAs to fill the machine once
+    if (eff > beste + 0.02) { beste = eff; best = (int)s; }   // prefer fewer splits unless clearly better
+  }
+  return best;
 }
 
 template <int FAM, int DK>
 static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
   constexpr int S = 8 * DK + 4;
-  constexpr size_t smem = sizeof(double) * (size_t)K1_STAGES * (K1_ROWS * S + K1_ROWS) + 2 * K1_STAGES * sizeof(uint64_t);
+  constexpr int NR = K1_NR;
+  constexpr size_t smem = sizeof(double) * ((size_t)K1_CHAINS * S + (size_t)K1_STAGES * (K1_ROWS * S + K1_ROWS)) +
+                          2 * K1_STAGES * sizeof(uint64_t);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(k1_kernel<FAM, DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1_kernel<FAM, DK, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   dim3 grid((unsigned)(a.Cp / K1_CHAINS), (unsigned)a.nsplit);
-  k1_kernel<FAM, DK><<<grid, K1_THREADS, smem, st>>>(a);
+  k1_kernel<FAM, DK, NR><<<grid, K1_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 

@@ -84,9 +84,13 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
   const SamplerDev& S = W.S;
   const ModelDev& M = W.M;
   if (c >= R.C) return;
-  if (*W.remaining == 0) return;
+  if (!W.resume && *W.remaining == 0) return;
   const int ph = W.phase[c];
   if (ph == PH_DONE) return;
+  if (W.resume) {
+    if (ph != PH_PAUSE) return;
+    atomicAdd(W.remaining, 1);
+  } else if (ph == PH_PAUSE) return;
   const int64_t d = M.d, Cp = R.Cp;
   const uint64_t gchain = (uint64_t)(R.chain_offset + c);
   const int64_t burnin = R.first - 1;
@@ -100,9 +104,10 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
   int leap = hmc_like ? W.leap[c] : 0;
   int nl_cur = hmc_like ? W.nleaps_cur[c] : 0;
   const bool interior = (ph == PH_LEAP) && (leap + 1 < nl_cur);
-  const EvalFin F = finalize_eval(M, q, part, ns, Cp, c, !interior);
+  EvalFin F; F.lt = CUDART_NAN; F.oos = false; F.ginv = 0.0; F.fam = M.family;
+  if (ph != PH_PAUSE) F = finalize_eval(M, q, part, ns, Cp, c, !interior);
   const double lt_q = F.lt;
-  unsigned long long nev = 1;
+  unsigned long long nev = (ph != PH_PAUSE) ? 1 : 0;
   bool begin = false;
   bool accepted_now = false;
 
@@ -122,7 +127,9 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
     W.kept[c] = k + 1;
   };
 
-  if (ph == PH_INIT) {
+  if (ph == PH_PAUSE) {
+    begin = true;
+  } else if (ph == PH_INIT) {
     if (!isfinite(lt_q)) {   // "Initial values out of model support" RWM.jl:55 MALA.jl:85 HMC.jl:121 HMCDA.jl:88
       W.status[c] = 1; W.phase[c] = PH_DONE; atomicSub(W.remaining, 1); atomicAdd(W.n_evals, nev);
       return;
@@ -133,12 +140,12 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       W.cur_pars[j * Cp + c] = q[j * Cp + c];
       if (kind != MCMCGPU_RWM) W.cur_grad[j * Cp + c] = fin_grad(F, M, q, part, ns, Cp, c, j);
     }
-    if (kind == MCMCGPU_HMCDA) {
+    if (kind == MCMCGPU_HMCDA && !W.restore_da) {
       // HMCDA.jl:90-94; initializeHMCDAStep (HMCDA.jl:51-69) always returns 1.0 (state0.H is NaN, HMC.jl:88)
       W.da_leapstep[c] = 1.0; W.da_dual[c] = 1.0; W.da_dualH[c] = 0.0;
     }
     if (S.tuner_on) { W.tn_step[c] = S.scale; W.tn_nleaps[c] = S.nleaps; W.tn_acc[c] = 0; W.tn_prop[c] = 0; }
-    i = 1;
+    i = W.step0 + 1;
     begin = true;
   } else if (ph == PH_RWM) {
     // RWM.jl:62-70
@@ -259,6 +266,12 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       return;
     }
     W.istep[c] = i;
+    if (i > W.step_limit) {   // pause: mcmcgpu_run_execute_steps continues from here
+      W.phase[c] = PH_PAUSE;
+      atomicSub(W.remaining, 1);
+      atomicAdd(W.n_evals, nev);
+      return;
+    }
     // ---- start step i: draw and write the next pending point ----
     double eps = S.scale; int nl = 0;
     if (kind == MCMCGPU_HMCDA) {
@@ -335,7 +348,7 @@ __global__ void eval_closed_kernel(const ModelDev M, const double* q, double* pa
   }
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (phase && phase[c] == PH_DONE) return;
+  if (phase && phase[c] >= PH_PAUSE) return;
   const int64_t d = M.d;
   if (M.family == MCMCGPU_FAM_NORMAL_FN) {
     double s = 0.0;

@@ -7,6 +7,7 @@ constexpr int PH_INIT = 0;   // q = init has been evaluated
 constexpr int PH_RWM = 1;    // q = RWM proposal has been evaluated
 constexpr int PH_MALA = 2;   // q = MALA proposal has been evaluated
 constexpr int PH_LEAP = 3;   // q = position after a leapfrog position update has been evaluated
+constexpr int PH_PAUSE = 98;  // reached the step limit of this execute call; resumes at the next one
 constexpr int PH_DONE = 99;
 
 struct WaveArgs {
@@ -14,7 +15,10 @@ struct WaveArgs {
   SamplerDev S;
   RunnerDev R;
   int32_t nsplit;              // partial buffers to sum (1 after an all-reduce)
-  int32_t row_sharded_prior;   // unused placeholder (prior is always added here, once)
+  int32_t resume;              // 1: this launch only restarts paused chains (no evaluation is consumed)
+  int32_t restore_da;          // 1: HMCDA adaptation state was set by the host (mcmcgpu_run_set_state)
+  int64_t step0;               // chains start at step step0 + 1
+  int64_t step_limit;          // chains pause before starting a step > step_limit
   // evaluation in/out
   double* q;                   // [d][Cp]
   const double* part;          // [nsplit][d+2][Cp]

