@@ -212,7 +212,7 @@ int32_t mcmcgpu_model_create(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
   if (m->is_regression) {
     if (!X || !y || N < 1) { delete m; return fail(MCMCGPU_E_ARG, "regression families need X (N x d) and y (N)"); }
     if (!(m->hyper[0] > 0)) { delete m; return fail(MCMCGPU_E_ARG, "prior sd must be > 0"); }
-    if (!k1_supported(d)) { delete m; return fail(MCMCGPU_E_ARG, "regression families support 1 <= d <= 104 in this build"); }
+    if (!k1_supported(d)) { delete m; return fail(MCMCGPU_E_ARG, "regression families support 1 <= d <= 200 in this build"); }
     if (row_sharded && !c->comm) { delete m; return fail(MCMCGPU_E_COMM, "row_sharded model needs mcmcgpu_comm_init first"); }
     m->row_sharded = row_sharded != 0;
     double *dX = nullptr, *dy = nullptr;

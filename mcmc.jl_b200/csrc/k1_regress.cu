@@ -116,9 +116,8 @@ __device__ __forceinline__ LinkOut link(double eta, double y, const double* hy, 
 // 256 threads, <= 128 registers, two CTAs per SM: 16 warps keep the DMMA pipe fed while other warps
 // are in the (latency-bound) link-function epilogue.
 template <int FAM, int DK, int NR>
-__global__ void __launch_bounds__(K1_THREADS, 2) k1_kernel(const K1Args a) {
+__global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_2CTA) ? 2 : 1) k1_kernel(const K1Args a) {
   constexpr int S = 8 * DK + 4;
-  constexpr int KS = 2 * DK;                  // k-steps of 4 features in phase 1
   constexpr int TILE_D = K1_ROWS * S + K1_ROWS;
   constexpr int NG = K1_ROWS / (8 * NR);      // row groups per tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -181,6 +180,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_kernel(const K1Args a) {
   //   phase 1 B fragment: X[8n + pi(g)][4ks + t]
   //   phase 2 B fragment: X[8n + pi(2t+s)][8jb + g]
   const double* bfrag = betas + (warp * 8 + g) * S + t;
+  const int ksn = (d + 3) >> 2;               // k-steps that hold real features (<= KS)
   const int off1 = pi8(g) * S + t;
   const int row2a = pi8(2 * t), row2b = pi8(2 * t + 1);
   const int off2a = row2a * S + g, off2b = row2b * S + g;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(K1_THREADS, 2) k1_kernel(const K1Args a) {
 #pragma unroll
       for (int n = 0; n < NR; n++) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
 #pragma unroll 4
-      for (int ks = 0; ks < KS; ks++) {
+      for (int ks = 0; ks < ksn; ks++) {
         const double av = bfrag[4 * ks];
 #pragma unroll
         for (int n = 0; n < NR; n++) {
@@ -292,11 +292,21 @@ __global__ void k1_pack_kernel(double* tiles, const double* X, const double* y, 
   }
 }
 
-bool k1_supported(int64_t d) { return d >= 1 && d <= 8 * K1_MAX_DK; }
+// supported feature-block counts: every DK up to 13 (d <= 104, 128 registers, two CTAs per SM), then 16, 20, 25
+// (d <= 200, one CTA per SM with up to 255 registers for the 2*DK gradient accumulators per thread)
+static int k1_round_dk(int64_t d) {
+  int dk = (int)((d + 7) / 8);
+  if (dk <= K1_MAX_DK_2CTA) return dk;
+  if (dk <= 16) return 16;
+  if (dk <= 20) return 20;
+  if (dk <= 25) return 25;
+  return -1;
+}
+bool k1_supported(int64_t d) { return d >= 1 && k1_round_dk(d) > 0; }
 
 cudaError_t k1_pack(K1Pack& P, const double* dX, const double* dy, int64_t N, int64_t d, cudaStream_t st) {
   P.N = N; P.d = d;
-  P.DK = (int)((d + 7) / 8);
+  P.DK = k1_round_dk(d);
   P.S = 8 * P.DK + 4;
   P.ntiles = (N + K1_ROWS - 1) / K1_ROWS;
   P.tile_doubles = (int64_t)K1_ROWS * P.S + K1_ROWS;
@@ -313,7 +323,7 @@ int k1_choose_splits(const K1Pack& P, int64_t Cp) {
   const int64_t ctiles = Cp / K1_CHAINS;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int64_t slots = 2LL * sms;
+  const int64_t slots = (P.DK <= K1_MAX_DK_2CTA ? 2LL : 1LL) * sms;
   int64_t maxs = P.ntiles / 8;
   if (maxs < 1) maxs = 1;
   if (maxs > 64) maxs = 64;
@@ -360,6 +370,9 @@ static cudaError_t launch_f(const K1Args& a, cudaStream_t st) {
     case 11: return launch_fd<FAM, 11>(a, st);
     case 12: return launch_fd<FAM, 12>(a, st);
     case 13: return launch_fd<FAM, 13>(a, st);
+    case 16: return launch_fd<FAM, 16>(a, st);
+    case 20: return launch_fd<FAM, 20>(a, st);
+    case 25: return launch_fd<FAM, 25>(a, st);
   }
   return cudaErrorInvalidValue;
 }

@@ -6,7 +6,8 @@ namespace mg {
 constexpr int K1_ROWS = 32;      // rows of X per shared-memory tile
 constexpr int K1_WARPS = 8;      // consumer warps per CTA; each owns 8 chains
 constexpr int K1_CHAINS = 8 * K1_WARPS;  // chains per CTA (64)
-constexpr int K1_MAX_DK = 13;    // d <= 104 with beta fragments in registers
+constexpr int K1_MAX_DK_2CTA = 13;  // d <= 104: 128 registers per thread, two CTAs per SM
+constexpr int K1_MAX_D = 200;
 
 // Packed design matrix: tile t holds rows [32t, 32t+32) as a ready-made shared-memory image:
 //   double x[32][S]  (row-major, S = 8*DK + 4 so that S = 4 (mod 8): conflict-free fragment loads)
