@@ -373,7 +373,12 @@ def main():
             per_launch_ms = eval_ms / max(n_eval, 1)
             flop = 4.0 * wl["N"] * d * C
             ach = flop / per_launch_ms / 1e9
-            line["roofline"] = dict(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=None,
+            traffic = None
+            prof = os.path.join(ROOT, "profiles", "k1_full_r01_summary.json")
+            if args.workload == "cfg4" and wl["N"] == 1000000 and C == 10000 and os.path.exists(prof):
+                m = json.load(open(prof))["metrics"]     # one ncu --set full capture of this kernel on this workload
+                traffic = float(m["dram__bytes_read.sum"]["values"][0]) * 1e9 + float(m["dram__bytes_write.sum"]["values"][0]) * 1e6
+            line["roofline"] = dict(bound="tensor", achieved=ach, peak=peak, unit="TFLOP/s", frac=ach / peak, traffic=traffic,
                                     kernel="k1_kernel (FP64 DMMA m8n8k4)", ms_per_launch=per_launch_ms,
                                     share_of_step=eval_ms / ms,
                                     peak_source="cuBLAS FP64 GEMM 8192^3 measured live in this run (MEASURED_PEAKS.json has no FP64 entry)")
