@@ -70,6 +70,9 @@ WORKLOADS = {
                  N=1000000, d=100, chains=10000, sampler="HMCDA", seed=4),
     "cfg3": dict(desc="MALA probit regression N=1e5 d=20, 16384 chains/GPU (BASELINE configs[2])", family="probit",
                  N=100000, d=20, chains=16384, sampler="MALA", seed=3),
+    "cfg5": dict(desc="HMC logistic regression, tall data d=200, rows sharded over the GPUs (6.25e6 rows per GPU; 5e7 at 8 GPUs), "
+                      "256 replicated chains, NCCL all-reduce of (d+2) x C partials per leapfrog (BASELINE configs[4])",
+                 family="logistic", N=6250000, d=200, chains=256, sampler="HMC", seed=5),
     "cfg2": dict(desc="HMC(0.75) 3-D Normal -dot(v,v), 65536 chains/GPU (BASELINE configs[1])", family="normal_fn",
                  N=0, d=3, chains=65536, sampler="HMC", seed=1),
 }
@@ -158,6 +161,9 @@ def sampler_for(wl, capi_or_oracle, is_oracle=False, force_eps=None):
         return mk("HMCDA", **kw)
     if wl["sampler"] == "MALA":
         return mk("MALA", scale=wl.get("drift", 2.4 ** 2 * wl["d"] ** (-1.0 / 3.0) / wl["N"]))
+    if wl["family"] == "logistic":          # cfg5: step size scaled from the cfg4 pilot by sqrt(N) and d^(1/4)
+        ntot = wl["N"] * int(os.environ.get("WORLD_SIZE", "1"))
+        return mk("HMC", scale=CFG4_EPS * (1e6 / ntot) ** 0.5 * (100.0 / wl["d"]) ** 0.25, nleaps=10)
     return mk("HMC", scale=0.75, nleaps=10)
 
 
@@ -235,7 +241,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))   # the WORKLOADS dict is defined above
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--N", type=int, default=0, help="override observation count")
@@ -274,10 +280,29 @@ def main():
         torch.cuda.synchronize()
 
     K, W, C, d = args.steps, args.warmup, wl["chains"], wl["d"]
-    problem = make_problem(wl)
-    X, y, hy, b0 = problem
-    dm = capi.DeviceModel(ctx, wl["family"], d, X, y, hy)
-    offset = rank * C                         # global chain ids: Philox streams differ across ranks
+    row_sharded = (args.workload == "cfg5")
+    if row_sharded:
+        # tall data: every rank generates ITS rows on the device (seeded per rank), chains are replicated
+        if world > 1:
+            uid = mcmc_jl_b200.broadcast_unique_id(dist, capi.Context.comm_unique_id, rank)
+            ctx.comm_init(rank, world, uid)
+        g = torch.Generator(device="cuda"); g.manual_seed(wl["seed"] * 1000 + rank)
+        g0 = torch.Generator(device="cuda"); g0.manual_seed(wl["seed"])
+        b0_t = torch.randn(d, generator=g0, device="cuda", dtype=torch.float64) / d ** 0.5
+        Xt = torch.randn(d, wl["N"], generator=g, device="cuda", dtype=torch.float64)   # (d, N) row-major == N x d column-major
+        Xt[0] = 1.0
+        y_t = (torch.rand(wl["N"], generator=g, device="cuda", dtype=torch.float64) < torch.sigmoid(b0_t @ Xt)).double()
+        torch.cuda.synchronize()
+        dm = capi.DeviceModel.from_device(ctx, "logistic", wl["N"], d, Xt.data_ptr(), y_t.data_ptr(), (1.0, -1.0), row_sharded=world > 1)
+        b0, hy, problem = b0_t.cpu().numpy(), (1.0, -1.0), None
+        del Xt, y_t
+        torch.cuda.empty_cache()
+        offset = 0                            # replicated chains: identical Philox keys on every rank
+    else:
+        problem = make_problem(wl)
+        X, y, hy, b0 = problem
+        dm = capi.DeviceModel(ctx, wl["family"], d, X, y, hy)
+        offset = rank * C                     # global chain ids: Philox streams differ across ranks
     scfg = sampler_for(wl, capi)
     rng = np.random.default_rng(100 + rank)
     peak = dgemm_peak_tflops(torch) if wl["family"] != "normal_fn" else None
@@ -308,7 +333,7 @@ def main():
             step0 = 1000                      # sampling phase: past any burn-in, step size frozen at the adapted value
             set_state = (step0, np.full(C, CFG4_EPS), np.full(C, CFG4_EPS), np.zeros(C))
         else:
-            init_state = b0[None, :] + 1e-3 * rng.standard_normal((C, d))
+            init_state = b0[None, :] + 1e-3 * np.random.default_rng(100).standard_normal((C, d))   # same on every rank
             step0, set_state = 0, None
         r = capi.DeviceRun(dm, scfg, (step0 + 1, 1, step0 + W + K), C, init_state, seed=wl["seed"], chain_offset=offset, engine="wave")
         if set_state:
@@ -353,7 +378,7 @@ def main():
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(evals, op=dist.ReduceOp.SUM)
     ms_max, e2e_ms_max = times.tolist()
-    total_chains = C * world
+    total_chains = C if row_sharded else C * world
     value = total_chains * K / (ms_max / 1e3)
     e2e_value = total_chains * K / (e2e_ms_max / 1e3)
 
@@ -362,7 +387,9 @@ def main():
                     ms_per_step=ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic",
                     config=dict(workload=args.workload, description=wl["desc"], N=wl["N"], d=d, chains_per_gpu=C,
-                                sampler=wl["sampler"], parallelism=f"chains sharded over {world} GPU(s), no collective",
+                                sampler=wl["sampler"],
+                                parallelism=(f"rows sharded over {world} GPU(s) ({wl['N']} rows each), chains replicated, ncclAllReduce per leapfrog"
+                                             if row_sharded else f"chains sharded over {world} GPU(s), no collective"),
                                 l2="inputs larger than L2 (packed X = %.0f MB)" % (wl["N"] * (8 * ((d + 7) // 8) + 4) * 8 / 1e6)
                                 if wl["N"] else "no input data; kept draws written once",
                                 seed=wl["seed"]),
@@ -371,7 +398,7 @@ def main():
                     clocks=clk.summary())
         if args.workload != "cfg2":
             per_launch_ms = eval_ms / max(n_eval, 1)
-            flop = 4.0 * wl["N"] * d * C
+            flop = 4.0 * wl["N"] * d * C             # per GPU (its rows x all chains for cfg5; all rows x its chains otherwise)
             ach = flop / per_launch_ms / 1e9
             traffic = None
             prof = os.path.join(ROOT, "profiles", "k1_full_r01_summary.json")
@@ -390,7 +417,7 @@ def main():
             ach = bytes_per * C * K / (ms / 1e3) / 1e9
             line["roofline"] = dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None,
                                     kernel="fused_chain_kernel", note="store bandwidth of kept draws; the kernel is FP64-ALU/latency bound, see DESIGN.md")
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and not row_sharded:
             cores = os.cpu_count() or 1
             cs = args.cpu_steps if args.workload != "cfg2" else 2000
             cb = cpu_baseline(wl, cs, 1 if args.workload != "cfg2" else 200, cores, problem)

@@ -118,6 +118,11 @@ int32_t mcmcgpu_comm_init(mcmcgpu_ctx* ctx, int32_t rank, int32_t nranks, const 
 int32_t mcmcgpu_model_create(mcmcgpu_ctx* ctx, int32_t family, int64_t N, int64_t d, const double* X,
                              const double* y, const double* hyper, int32_t nhyper, int32_t row_sharded,
                              mcmcgpu_model** out);
+/* same, with X (N x d column-major) and y already resident on this context's device (tall data generated or
+ * loaded shard by shard on the GPU); hyper stays a host pointer. */
+int32_t mcmcgpu_model_create_device(mcmcgpu_ctx* ctx, int32_t family, int64_t N, int64_t d, const double* X_dev,
+                                    const double* y_dev, const double* hyper, int32_t nhyper, int32_t row_sharded,
+                                    mcmcgpu_model** out);
 int32_t mcmcgpu_model_destroy(mcmcgpu_model* m);
 
 /* model.eval / model.evalallg for C parameter vectors at once (likmodel.jl:21,25).

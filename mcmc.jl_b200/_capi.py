@@ -49,7 +49,7 @@ class RunInfo(C.Structure):
 
 EXPORTS = [
     "mcmcgpu_abi_version", "mcmcgpu_last_error", "mcmcgpu_init", "mcmcgpu_destroy", "mcmcgpu_set_stream",
-    "mcmcgpu_set_option", "mcmcgpu_comm_unique_id", "mcmcgpu_comm_init", "mcmcgpu_model_create",
+    "mcmcgpu_set_option", "mcmcgpu_comm_unique_id", "mcmcgpu_comm_init", "mcmcgpu_model_create", "mcmcgpu_model_create_device",
     "mcmcgpu_model_destroy", "mcmcgpu_logtarget_grad", "mcmcgpu_run_chains", "mcmcgpu_run_create",
     "mcmcgpu_run_execute", "mcmcgpu_run_execute_steps", "mcmcgpu_run_set_state", "mcmcgpu_run_get_state",
     "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
@@ -78,6 +78,8 @@ def lib():
         L.mcmcgpu_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
         L.mcmcgpu_model_create.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, dp, dp, dp, C.c_int32, C.c_int32,
                                            C.POINTER(vp)]
+        L.mcmcgpu_model_create_device.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, vp, vp, dp, C.c_int32, C.c_int32,
+                                                  C.POINTER(vp)]
         L.mcmcgpu_model_destroy.argtypes = [vp]
         L.mcmcgpu_logtarget_grad.argtypes = [vp, dp, C.c_int64, dp, dp]
         L.mcmcgpu_run_chains.argtypes = [vp, C.POINTER(SamplerCfg), C.POINTER(RunnerCfg), dp, dp, dp, dp, dp, dp,
@@ -173,6 +175,18 @@ class DeviceModel:
         check(lib().mcmcgpu_model_create(ctx.h, FAM[family], N, self.d, dptr(Xf), dptr(yf), dptr(hy) if len(hy) else None,
                                          len(hy), 1 if row_sharded else 0, C.byref(h)))
         self.h, self.N = h, N
+
+    @classmethod
+    def from_device(cls, ctx, family, N, d, X_ptr, y_ptr, hyper=(), row_sharded=False):
+        """X_ptr / y_ptr: device addresses (e.g. torch tensor .data_ptr()) of an N x d column-major X and y."""
+        self = cls.__new__(cls)
+        self.ctx, self.family, self.d, self.N = ctx, family, int(d), int(N)
+        hy = np.asarray(hyper, dtype=np.float64)
+        h = C.c_void_p()
+        check(lib().mcmcgpu_model_create_device(ctx.h, FAM[family], int(N), int(d), C.c_void_p(X_ptr), C.c_void_p(y_ptr),
+                                                dptr(hy) if len(hy) else None, len(hy), 1 if row_sharded else 0, C.byref(h)))
+        self.h = h
+        return self
 
     def logtarget_grad(self, B, grad=True):
         """B: (C, d) parameter vectors. Returns lt (C,), grad (C, d) or None."""

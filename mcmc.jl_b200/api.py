@@ -39,7 +39,7 @@ class MCMCLikelihoodModel:
     """GPU registry entry standing in for MCMCLikelihoodModel (likmodel.jl:20-58): a likelihood family tag
     plus its data instead of Julia closures.  eval / evalg / evalallg evaluate on the device."""
 
-    def __init__(self, family, init, scale=1.0, pmap=None, X=None, y=None, hyper=(), gradient=True):
+    def __init__(self, family, init, scale=1.0, pmap=None, X=None, y=None, hyper=(), gradient=True, row_sharded=False):
         init = np.atleast_1d(np.asarray(init, dtype=np.float64))          # likmodel.jl:112
         if init.ndim != 1:
             raise ValueError("init must be a vector")
@@ -55,6 +55,7 @@ class MCMCLikelihoodModel:
             raise AssertionError("param map is not a partition of parameter vector")
         self.X, self.y, self.hyper = X, y, tuple(hyper)
         self.has_gradient = bool(gradient)
+        self.row_sharded = bool(row_sharded)      # X, y are THIS rank's rows; needs init_row_sharding() first
         self._dev = None
         lt = self.eval(self.init)
         if not np.isfinite(lt):                                            # likmodel.jl:54
@@ -63,7 +64,8 @@ class MCMCLikelihoodModel:
     # -- device handle (lazy) --
     def device_model(self):
         if self._dev is None:
-            self._dev = capi.DeviceModel(default_context(), self.family, self.size, self.X, self.y, self.hyper)
+            self._dev = capi.DeviceModel(default_context(), self.family, self.size, self.X, self.y, self.hyper,
+                                         row_sharded=self.row_sharded)
         return self._dev
 
     def eval(self, v):                                                     # likmodel.jl:21
@@ -118,14 +120,17 @@ def model(family, *, gradient=True, grad=None, init=None, scale=1.0, **kw):
         X = np.asarray(kw.pop("X"), dtype=np.float64)
         Y = np.asarray(kw.pop("Y", kw.pop("y", None)), dtype=np.float64)
         hy = (kw.pop("prior_sd", 1.0), kw.pop("noise_sd", 1.0)) if family == "linear" else (kw.pop("prior_sd", 1.0), kw.pop("sign", -1.0))
+        rs = bool(kw.pop("row_sharded", False))
         name, v0 = _one_param(kw, ())
-        return MCMCLikelihoodModel(family, v0, scale, pmap=_pmap_of([(name, v0)]), X=X, y=Y, hyper=hy, gradient=gradient)
+        return MCMCLikelihoodModel(family, v0, scale, pmap=_pmap_of([(name, v0)]), X=X, y=Y, hyper=hy, gradient=gradient,
+                                   row_sharded=rs)
     if family == "probit":
         X = np.asarray(kw.pop("X"), dtype=np.float64)
         y = np.asarray(kw.pop("y", kw.pop("Y", None)), dtype=np.float64)
         if init is None:
             raise ValueError("probit needs init=")
-        return MCMCLikelihoodModel("probit", init, scale, X=X, y=y, hyper=(kw.pop("priorstd", 10.0),), gradient=gradient)
+        return MCMCLikelihoodModel("probit", init, scale, X=X, y=y, hyper=(kw.pop("priorstd", 10.0),), gradient=gradient,
+                                   row_sharded=bool(kw.pop("row_sharded", False)))
     if family == "ou":
         x = np.asarray(kw.pop("x"), dtype=np.float64)
         hy = (kw.pop("tau_hi", 100.0), kw.pop("sigma_hi", 2.0), kw.pop("mu_hi", 20.0))
@@ -415,6 +420,40 @@ class MCMCChainBatch:
 
     def close(self):
         self._run.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# tall data: rows of X sharded over the ranks of a torchrun launch
+# ---------------------------------------------------------------------------------------------------
+def shard_rows(N, rank=None, world=None):
+    """rows [lo, hi) of rank g: contiguous blocks [g*N/G, (g+1)*N/G)"""
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    return (rank * N) // world, ((rank + 1) * N) // world
+
+
+def broadcast_unique_id(dist, make_id, rank):
+    """rank 0 creates the 128-byte NCCL unique id, every rank receives it through the process group `dist`
+    (any backend: the id is plain bytes)"""
+    import torch
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).clone()
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    buf = buf.to(dev)
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def init_row_sharding():
+    """one NCCL communicator over all ranks, owned by the library (per-leapfrog all-reduce of the partial
+    log-likelihood and gradient).  torch.distributed must be initialised (it only carries the unique id)."""
+    import torch.distributed as dist
+    ctx = default_context()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = broadcast_unique_id(dist, capi.Context.comm_unique_id, rank)
+    ctx.comm_init(rank, world, uid)
+    return rank, world
 
 
 # ---------------------------------------------------------------------------------------------------

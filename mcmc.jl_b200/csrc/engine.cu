@@ -175,8 +175,8 @@ int32_t mcmcgpu_comm_init(mcmcgpu_ctx* c, int32_t rank, int32_t nranks, const vo
 }
 
 // ---- model ---------------------------------------------------------------------------------------
-int32_t mcmcgpu_model_create(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t d, const double* X, const double* y,
-                             const double* hyper, int32_t nhyper, int32_t row_sharded, mcmcgpu_model** out) {
+static int model_create_impl(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t d, const double* X, const double* y,
+                             const double* hyper, int32_t nhyper, int32_t row_sharded, bool on_device, mcmcgpu_model** out) {
   if (!c || !out) return fail(MCMCGPU_E_ARG, "ctx/out is NULL");
   if (d < 1) return fail(MCMCGPU_E_ARG, "d must be >= 1");
   if (nhyper < 0 || nhyper > 4 || (nhyper > 0 && !hyper)) return fail(MCMCGPU_E_ARG, "bad hyper");
@@ -215,24 +215,40 @@ int32_t mcmcgpu_model_create(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
     if (!k1_supported(d)) { delete m; return fail(MCMCGPU_E_ARG, "regression families support 1 <= d <= 200 in this build"); }
     if (row_sharded && !c->comm) { delete m; return fail(MCMCGPU_E_COMM, "row_sharded model needs mcmcgpu_comm_init first"); }
     m->row_sharded = row_sharded != 0;
-    double *dX = nullptr, *dy = nullptr;
-    CU(dalloc(&dX, (size_t)(N * d)));
-    CU(dalloc(&dy, (size_t)N));
-    CU(cudaMemcpyAsync(dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(dy, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
-    CU(k1_pack(m->pack, dX, dy, N, d, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dX); cudaFree(dy);
+    if (on_device) {
+      CU(k1_pack(m->pack, X, y, N, d, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    } else {
+      double *dX = nullptr, *dy = nullptr;
+      CU(dalloc(&dX, (size_t)(N * d)));
+      CU(dalloc(&dy, (size_t)N));
+      CU(cudaMemcpyAsync(dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(dy, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
+      CU(k1_pack(m->pack, dX, dy, N, d, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      cudaFree(dX); cudaFree(dy);
+    }
     for (int i = 0; i < 4; i++) m->k1_hyper[i] = m->hyper[i];
     if (family == MCMCGPU_FAM_LINEAR) m->k1_hyper[3] = std::log(m->hyper[1]);
   }
   if (family == MCMCGPU_FAM_OU) {
     CU(dalloc(&m->d_series, (size_t)N));
-    CU(cudaMemcpyAsync(m->d_series, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(m->d_series, y, sizeof(double) * (size_t)N, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
   *out = m;
   return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_model_create(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t d, const double* X, const double* y,
+                             const double* hyper, int32_t nhyper, int32_t row_sharded, mcmcgpu_model** out) {
+  return model_create_impl(c, family, N, d, X, y, hyper, nhyper, row_sharded, false, out);
+}
+
+int32_t mcmcgpu_model_create_device(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t d, const double* X_dev,
+                                    const double* y_dev, const double* hyper, int32_t nhyper, int32_t row_sharded,
+                                    mcmcgpu_model** out) {
+  return model_create_impl(c, family, N, d, X_dev, y_dev, hyper, nhyper, row_sharded, true, out);
 }
 
 int32_t mcmcgpu_model_destroy(mcmcgpu_model* m) {

@@ -326,7 +326,7 @@ int k1_choose_splits(const K1Pack& P, int64_t Cp) {
   const int64_t slots = (P.DK <= K1_MAX_DK_2CTA ? 2LL : 1LL) * sms;
   int64_t maxs = P.ntiles / 8;
   if (maxs < 1) maxs = 1;
-  if (maxs > 64) maxs = 64;
+  if (maxs > 512) maxs = 512;
   int best = 1; double beste = -1.0;
   for (int64_t s = 1; s <= maxs; s++) {
     const double waves = (double)(ctiles * s) / (double)slots;
