@@ -163,7 +163,7 @@ def sampler_for(wl, capi_or_oracle, is_oracle=False, force_eps=None):
         return mk("MALA", scale=wl.get("drift", 2.4 ** 2 * wl["d"] ** (-1.0 / 3.0) / wl["N"]))
     if wl["family"] == "logistic":          # cfg5: step size scaled from the cfg4 pilot by sqrt(N) and d^(1/4)
         ntot = wl["N"] * int(os.environ.get("WORLD_SIZE", "1"))
-        return mk("HMC", scale=CFG4_EPS * (1e6 / ntot) ** 0.5 * (100.0 / wl["d"]) ** 0.25, nleaps=10)
+        return mk("HMC", scale=0.8 * CFG4_EPS * (1e6 / ntot) ** 0.5 * (100.0 / wl["d"]) ** 0.25, nleaps=10)
     return mk("HMC", scale=0.75, nleaps=10)
 
 

@@ -33,7 +33,8 @@ def _lt_grad_check(O, capi, ctx, fam, N, d, C, seed, spread=0.3):
 
 
 @pytest.mark.parametrize("fam", ["linear", "logistic", "probit"])
-@pytest.mark.parametrize("N,d,C", [(1000, 10, 70), (39, 3, 1), (31, 1, 5), (33, 8, 64), (4097, 100, 130), (257, 104, 65), (2048, 20, 129)])
+@pytest.mark.parametrize("N,d,C", [(1000, 10, 70), (39, 3, 1), (31, 1, 5), (33, 8, 64), (4097, 100, 130), (257, 104, 65), (2048, 20, 129),
+                                   (300, 105, 66), (513, 150, 64), (777, 200, 70)])
 def test_regression_logtarget_gradient(O, capi, ctx, fam, N, d, C):
     # ragged everything: N not a multiple of the 32-row tile, C not a multiple of the 64-chain tile, d = 1 and d = 104
     _lt_grad_check(O, capi, ctx, fam, N, d, C, seed=N + d)
@@ -322,7 +323,7 @@ def test_error_paths(capi, ctx):
             capi.DeviceRun(dm, bad, (1, 1, 10), 4, np.array([20.0, 0.1, 10.0]))
     dm.close()
     with pytest.raises(capi.MCMCGPUError):
-        capi.DeviceModel(ctx, "logistic", 200, np.zeros((10, 200)), np.zeros(10), (1.0, -1.0))        # d > 104 in this build
+        capi.DeviceModel(ctx, "logistic", 201, np.zeros((10, 201)), np.zeros(10), (1.0, -1.0))        # d > 200 in this build
     with pytest.raises(capi.MCMCGPUError):
         ctx.stats(np.zeros((2, 50, 1)), "bm", batchlen=40)                                             # var.jl:22
 
