@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 # dual-averaged HMCDA step size after burn-in on cfg4 (median over 512 pilot chains; profiles/pilot_cfg4.json)
 CFG4_EPS = 1.97e-3
 CFG4_LEN = 0.02
+CFG2_STEPS_PER_STEP = 200     # cfg2: MCMC steps per bench "step" (a single MCMC step of 65 536 3-D chains is ~2 us of work)
 
 
 def synth_logistic(N, d, seed):
@@ -246,6 +247,7 @@ def main():
     ap.add_argument("--chains", type=int, default=0, help="override chains per GPU")
     ap.add_argument("--N", type=int, default=0, help="override observation count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ess", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
@@ -313,6 +315,7 @@ def main():
         # fused engine: the whole chain is one launch, so warm-up and timed region are separate runs of W and K steps
         def fresh(nsteps):
             return capi.DeviceRun(dm, scfg, (1, 1, nsteps), C, np.ones(d), seed=wl["seed"], chain_offset=offset, engine="fused")
+        K, W = K * CFG2_STEPS_PER_STEP, W * CFG2_STEPS_PER_STEP     # one launch covers the whole chain: time K*200 MCMC steps
         r = fresh(W); r.execute(); r.close()
         r = fresh(K)
         barrier()
@@ -383,8 +386,8 @@ def main():
     e2e_value = total_chains * K / (e2e_ms_max / 1e3)
 
     if rank == 0:
-        line = dict(metric="chain-steps/s", value=value, unit="chain-steps/s", n_gpus=world, steps=K, warmup=W,
-                    ms_per_step=ms_max / K, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+        line = dict(metric="chain-steps/s", value=value, unit="chain-steps/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_max / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
                     data="synthetic",
                     config=dict(workload=args.workload, description=wl["desc"], N=wl["N"], d=d, chains_per_gpu=C,
                                 sampler=wl["sampler"],
@@ -417,6 +420,27 @@ def main():
             ach = bytes_per * C * K / (ms / 1e3) / 1e9
             line["roofline"] = dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None,
                                     kernel="fused_chain_kernel", note="store bandwidth of kept draws; the kernel is FP64-ALU/latency bound, see DESIGN.md")
+        if not args.no_ess and not row_sharded:
+            # min-ESS/s (BASELINE metric): ESS per chain-step of this sampler on this target, measured with the
+            # device stats pass (Geyer IMSE, ess.jl:6-10) on a bounded pilot of the same chains, times the measured chain-steps/s
+            if args.workload == "cfg2":
+                ce, se = C, 2000
+                rr = capi.DeviceRun(dm, scfg, (201, 1, se), ce, np.ones(d), seed=wl["seed"], chain_offset=offset, engine="fused",
+                                    store_grad=False, store_logtarget=False)
+                rr.execute()
+            else:
+                ce, se = 256, 300
+                rr = capi.DeviceRun(dm, scfg, (step0 + 51, 1, step0 + se), ce, init_state[:ce], seed=wl["seed"] + 7, engine="wave",
+                                    store_grad=False, store_logtarget=False)
+                if set_state:
+                    rr.set_state(set_state[0], *(a[:ce] for a in set_state[1:]))
+                rr.execute()
+            st = rr.stats("imse")
+            kept = rr.S
+            ess_per_step = float(np.median(st["ess"].min(axis=1)) / kept)
+            rr.close()
+            line["min_ess_per_s"] = dict(value=ess_per_step * value, unit="min-ESS/s (min over parameters, summed over chains)",
+                                         ess_per_chain_step=ess_per_step, sample=f"{ce} chains x {kept} kept steps, Geyer IMSE on the device")
         if not args.no_cpu_baseline and not row_sharded:
             cores = os.cpu_count() or 1
             cs = args.cpu_steps if args.workload != "cfg2" else 2000
