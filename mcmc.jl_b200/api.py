@@ -96,7 +96,9 @@ def _ispartition(pmap, n):                                                 # mcm
 
 
 def model(family, *, gradient=True, grad=None, init=None, scale=1.0, **kw):
-    """Front door (mcmcmodels.jl:27-33).  `family` selects the built-in likelihood:
+    """Front door (mcmcmodels.jl:27-33).  `family` is either the text of a model expression in the reference's DSL
+    (recognised shapes: mcmc.jl_b200/dsl.py; note the reference defaults to gradient=false for expressions, pass it
+    explicitly) or the name of a built-in likelihood:
 
       "normal"      v -> -dot(v,v) (README.md:60,63); init=...; gradient/grad=False drops grad v -> -2v
       "normal_dsl"  v ~ Normal(mu, sigma) (README.md:67-72); v=<init>, mu=0, sigma=1
@@ -108,6 +110,13 @@ def model(family, *, gradient=True, grad=None, init=None, scale=1.0, **kw):
     """
     if grad is False:
         gradient = False
+    if "~" in family:                                                      # a DSL expression (mcmcmodels.jl:27, likmodel.jl:72-96)
+        from .dsl import recognise
+        if init is not None:                                               # likmodel.jl:80
+            raise AssertionError("'init' kwargs not allowed for model as expression")
+        r = recognise(family, kw)
+        return MCMCLikelihoodModel(r["family"], r["init"], scale, pmap=r["pmap"], X=r["X"], y=r["y"], hyper=r["hyper"],
+                                   gradient=gradient)
     if family == "normal":
         if init is None:
             init = [1.0]                                                   # likmodel.jl:107

@@ -302,6 +302,7 @@ int32_t mcmcgpu_logtarget_grad(mcmcgpu_model* m, const double* B, int64_t C, dou
   const int64_t d = m->d, Cp = round_up(C, K1_CHAINS);
   int nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp)) : 1;
   double *hB = nullptr, *q = nullptr, *part = nullptr, *red = nullptr, *lt = nullptr, *grad = nullptr, *gout = nullptr;
+  struct Freer { double** p[7]; ~Freer() { for (auto pp : p) if (*pp) { cudaFree(*pp); *pp = nullptr; } } } freer{{&hB, &q, &part, &red, &lt, &grad, &gout}};
   CU(dalloc(&hB, (size_t)(C * d)));
   CU(dalloc(&q, (size_t)(d * Cp)));
   CU(dalloc(&part, (size_t)(nsplit * (d + 2) * Cp)));
@@ -322,8 +323,7 @@ int32_t mcmcgpu_logtarget_grad(mcmcgpu_model* m, const double* B, int64_t C, dou
     CU(cudaMemcpyAsync(out_grad, gout, sizeof(double) * (size_t)(C * d), cudaMemcpyDeviceToHost, st));
   }
   CU(cudaStreamSynchronize(st));
-  cudaFree(hB); cudaFree(q); cudaFree(part); cudaFree(red); cudaFree(lt); cudaFree(grad); cudaFree(gout);
-  return MCMCGPU_OK;
+  return MCMCGPU_OK;   // temporaries are released by `freer` on every path
 }
 
 // ---- run -----------------------------------------------------------------------------------------

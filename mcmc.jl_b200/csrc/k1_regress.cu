@@ -360,11 +360,13 @@ static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
   constexpr int NR = K1_NR;
   constexpr size_t smem = sizeof(double) * ((size_t)K1_CHAINS * S + (size_t)K1_STAGES * (K1_ROWS * S + K1_ROWS)) +
                           2 * K1_STAGES * sizeof(uint64_t);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {false};      // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k1_kernel<FAM, DK, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
   dim3 grid((unsigned)(a.Cp / K1_CHAINS), (unsigned)a.nsplit);
   k1_kernel<FAM, DK, NR><<<grid, K1_THREADS, smem, st>>>(a);

@@ -118,3 +118,37 @@ def test_rank_slices_cover_all_chains(monkeypatch):
             lo, n = api._rank_slice(10000)
             seen += list(range(lo, lo + n))
         assert seen == list(range(10000))
+
+
+def test_dsl_recogniser():
+    """the example models of the reference, written in its DSL, map onto the GPU families"""
+    from mcmc_jl_b200.dsl import recognise
+    X, Y = np.ones((5, 3)), np.arange(5.0)
+    r = recognise("v ~ Normal(0, 1)", dict(v=np.ones(3)))                          # README.md:67-72
+    assert (r["family"], r["hyper"], r["pmap"]) == ("normal_dsl", (0.0, 1.0), {"v": (1, (3,))})
+    lin = """
+        vars ~ Normal(0, 1.0)  # Normal prior, std 1.0 for predictors
+        resid = Y - X * vars
+        resid ~ Normal(0, 1.0)
+    """                                                                            # examples/linear_regression.jl:14-18
+    r = recognise(lin, dict(vars=np.zeros(3), X=X, Y=Y))
+    assert r["family"] == "linear" and r["hyper"] == (1.0, 1.0) and r["X"] is not None and list(r["pmap"]) == ["vars"]
+    log_ = "vars ~ Normal(0, 1.0)\n prob = 1 / (1. + exp(- X * vars))\n Y ~ Bernoulli(prob)"   # examples/logistic_regression.jl:16-20
+    assert recognise(log_, dict(vars=np.zeros(3), X=X, Y=Y))["hyper"] == (1.0, -1.0)
+    log2 = "vars ~ Normal(0, 1.0); prob = 1 / (1. + exp(X * vars)); Y ~ Bernoulli(prob)"         # test/test_syntax.jl:16-20
+    assert recognise(log2, dict(vars=np.zeros(3), X=X, Y=Y))["hyper"] == (1.0, 1.0)
+    ou = """
+        tau ~ Uniform(0, 100)
+        sigma ~ Uniform(0, 2)
+        mu ~ Uniform(0, 20)
+        fac = exp(- 1. / tau)
+        resid = x[2:end] - x[1:end-1] * fac - mu * (1. - fac)
+        resid ~ Normal(0, sigma)
+    """                                                                            # examples/ornstein.jl:19-27
+    r = recognise(ou, dict(tau=0.05, sigma=1.0, mu=1.0, x=np.arange(10.0)))
+    assert r["family"] == "ou" and r["hyper"] == (100.0, 2.0, 20.0) and list(r["init"]) == [0.05, 1.0, 1.0]
+    assert list(r["pmap"]) == ["tau", "sigma", "mu"]
+    with pytest.raises(NotImplementedError):
+        recognise("y = abs(x)\n y ~ Gamma(2, 3)", dict(x=0.0))
+    with pytest.raises(ValueError):
+        recognise(lin, dict(vars=np.zeros(3), X=X))                                # Y missing

@@ -406,3 +406,67 @@ def test_linear_regression_posterior_moments(capi, ctx):
     assert np.all(np.abs(last.mean(0) - mu) < 5 * np.sqrt(np.diag(cov) / C))
     assert np.all(np.abs(last.var(0) / np.diag(cov) - 1) < 5 * math.sqrt(2 / C))
     run.close(); dm.close()
+
+
+def test_dsl_models_end_to_end(O):
+    """model(expression, ...) for the reference's example models, as test/test_syntax.jl:9-34 uses them"""
+    import mcmc_jl_b200 as mj
+    rng = np.random.default_rng(1)
+    n, nbeta = 1000, 10
+    X = np.concatenate([np.ones((n, 1)), rng.standard_normal((n, nbeta - 1))], axis=1)
+    beta0 = rng.standard_normal(nbeta)
+    Y = (rng.random(n) < 1 / (1 + np.exp(-X @ beta0))).astype(float)
+    ex = """
+        vars ~ Normal(0, 1.0)  # Normal prior, std 1.0 for predictors
+        prob = 1 / (1. + exp(- X * vars))
+        Y ~ Bernoulli(prob)
+    """
+    m = mj.model(ex, vars=np.zeros(nbeta), gradient=True, X=X, Y=Y)
+    om = O.Model("logistic", nbeta, X, Y, (1.0, -1.0))
+    lt, g = m.evalallg(m.init)
+    olt, og = om.evalallg(np.zeros(nbeta))
+    assert abs(lt - olt) <= 1e-12 * abs(olt) and np.allclose(g, og, rtol=1e-11, atol=1e-9)
+    for smp in (mj.RWM(0.05), mj.HMC(2, 0.1), mj.MALA(0.001)):                       # test/test_syntax.jl:25-28
+        res = mj.run(m * smp * mj.SerialMC(100, 1000))
+        assert res.samples.shape == (901, nbeta) and list(res.samples.columns)[:2] == ["vars.1", "vars.2"]
+        assert np.isfinite(res.samples.values).all()
+    res = mj.run(m, mj.HMC(2, 0.1), mj.SerialMC(thinning=10, burnin=0))              # test_syntax.jl:33
+    assert res.samples.shape == (10, nbeta)
+    m0 = mj.model(ex, vars=np.zeros(nbeta), gradient=False, X=X, Y=Y)
+    with pytest.raises(AssertionError):
+        mj.run(m0 * mj.HMC(2, 0.1) * mj.SerialMC(1, 10))                             # HMC.jl:111
+    ou = mj.model("""tau ~ Uniform(0, 100)
+                     sigma ~ Uniform(0, 2)
+                     mu ~ Uniform(0, 20)
+                     fac = exp(- 1. / tau)
+                     resid = x[2:end] - x[1:end-1] * fac - mu * (1. - fac)
+                     resid ~ Normal(0, sigma)""", tau=0.05, sigma=1.0, mu=1.0, gradient=True, x=ou_series(1000, 1),
+                  scale=np.array([1000.0, 1.0, 10.0]))
+    res = mj.run(ou * mj.HMC(5, 0.002) * mj.SerialMC(1000, 2000))                    # examples/ornstein.jl:38
+    assert list(res.samples.columns) == ["tau", "sigma", "mu"] and res.samples.shape == (1001, 3)
+
+
+def test_run_chains_single_call(O, capi, ctx):
+    """mcmcgpu_run_chains: the one-call form the Julia glue uses (create + execute + fetch + destroy)"""
+    import ctypes as C
+    d, Cn, rngt = 3, 17, (11, 3, 100)
+    S = len(range(rngt[0], rngt[2] + 1, rngt[1]))
+    dm = capi.DeviceModel(ctx, "normal_fn", d)
+    scfg = capi.sampler_cfg("HMC", scale=0.75, nleaps=10)
+    r = capi.RunnerCfg()
+    r.first, r.step, r.last, r.nchains, r.chain_offset, r.seed = rngt[0], rngt[1], rngt[2], Cn, 0, 0
+    rng = np.random.default_rng(4)
+    zn = rng.standard_normal((Cn, rngt[2] + 1, d)); un = rng.random((Cn, rngt[2] + 1))
+    samples = np.empty((Cn, S, d)); grads = np.empty((Cn, S, d)); acc = np.empty((Cn, S), dtype=np.uint8); lt = np.empty((Cn, S))
+    info = capi.RunInfo()
+    init = np.ones(d)
+    capi.check(capi.lib().mcmcgpu_run_chains(dm.h, C.byref(scfg), C.byref(r), capi.dptr(init), None, capi.dptr(zn), capi.dptr(un),
+                                            capi.dptr(samples), capi.dptr(grads), acc.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                            capi.dptr(lt), C.byref(info)))
+    om = O.Model("normal_fn", d)
+    for c in range(Cn):
+        ref = O.run_chain(om, O.sampler("HMC", scale=0.75, nleaps=10), rngt, init, None, zn[c], un[c])
+        assert np.array_equal(ref["samples"], samples[c]) and np.array_equal(ref["accept"], acc[c])
+        assert np.array_equal(ref["grads"], grads[c]) and np.array_equal(ref["logtarget"], lt[c])
+    assert info.n_launches == 1 and info.n_grad_evals == Cn * (1 + rngt[2] * 10)
+    dm.close()
