@@ -42,6 +42,7 @@ extern "C" {
 #define MCMCGPU_FAM_LOGISTIC 3   /* examples/logistic_regression.jl:16-20      hyper = {prior_sd, sign}  (sign -1: exp(-X*b); +1: test/test_syntax.jl:18) */
 #define MCMCGPU_FAM_PROBIT 4     /* examples/probit_regression.jl:18-41        hyper = {prior_sd}        */
 #define MCMCGPU_FAM_OU 5         /* examples/ornstein.jl:19-27                 hyper = {tau_hi, sigma_hi, mu_hi}; y = series, d = 3 */
+#define MCMCGPU_FAM_ABS_NORMAL 6 /* README.md:253-259  y = abs(x); y ~ Normal(mu, sigma)   hyper = {mu, sigma} (the SeqMC ladder) */
 
 /* samplers: src/samplers/RWM.jl:24-36, MALA.jl:50-62, HMC.jl:53-74, HMCDA.jl:24-43 */
 #define MCMCGPU_RWM 0
@@ -171,6 +172,30 @@ int32_t mcmcgpu_run_destroy(mcmcgpu_run* run);
 int32_t mcmcgpu_stats(mcmcgpu_ctx* ctx, const double* samples, int64_t S, int64_t d, int64_t C, int32_t vtype,
                       int64_t maxlag, int64_t batchlen, double* out_mean, double* out_var_iid, double* out_var,
                       double* out_ess, double* out_actime);
+
+/* ---- population runners (closed-form families NORMAL_FN / NORMAL_DSL / ABS_NORMAL, d <= 8) ----
+ * nt tasks share family and size; task t has hypers[4*t .. 4*t+3] and samplers[t] (RWM / MALA / HMC, no tuner).
+ *
+ * mcmcgpu_run_seqmc stands in for run(targets::Array{MCMCTask}; particles=...) with SeqMC runners
+ * (src/runners/SeqMC.jl:39-122): one thread mutates one particle per target; weights, the variance trigger, the
+ * cumulative sum and the multinomial resampling (prefix sum + binary search) stay on the device.
+ * particles d x npart; injected draws (all NULL for Philox): normals d x npart x nt x steps, uniforms and
+ * res_uniforms npart x nt x steps.  out_samples d x ((steps-burnin)*npart), out_weights (steps-burnin)*npart.
+ *
+ * mcmcgpu_run_serialtemp stands in for run(tasks) with SerialTempMC runners (src/runners/SerialTempMC.jl:31-85)
+ * for nrep independent replicas at once.  inits d x nt; injected draws (all NULL for Philox): normals
+ * d x (steps+2) x nrep, uniforms (steps+2) x nrep, pick and swap (steps+1) x nrep.
+ * out_samples d x (steps-burnin) x nrep, out_at (steps-burnin) x nrep (0-based task index, may be NULL). */
+int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* ctx, int32_t family, int64_t d, int32_t nt, const double* hypers,
+                          const mcmcgpu_sampler_cfg* samplers, int64_t steps, int64_t burnin, double trigger,
+                          int64_t npart, const double* particles, uint64_t seed, const double* inj_normals,
+                          const double* inj_uniforms, const double* inj_res_uniforms, double* out_samples,
+                          double* out_weights, int64_t* out_nresamples, mcmcgpu_run_info* info);
+int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* ctx, int32_t family, int64_t d, int32_t nt, const double* hypers,
+                               const mcmcgpu_sampler_cfg* samplers, int64_t steps, int64_t burnin, int64_t swap_period,
+                               int64_t nrep, const double* inits, uint64_t seed, const double* inj_normals,
+                               const double* inj_uniforms, const double* inj_pick, const double* inj_swap,
+                               double* out_samples, int32_t* out_at, mcmcgpu_run_info* info);
 
 /* the engine's own draws, for draw-matched replay through another implementation:
  * normals d x (last+1) x nchains and uniforms (last+1) x nchains exactly as the samplers consume them */

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcmcgpu.so")
 
 OK, E_ARG, E_SUPPORT, E_NOGRAD, E_CUDA, E_COMM, E_STATE = 0, -1, -2, -3, -4, -5, -6
-FAM = dict(normal_fn=0, normal_dsl=1, linear=2, logistic=3, probit=4, ou=5)
+FAM = dict(normal_fn=0, normal_dsl=1, linear=2, logistic=3, probit=4, ou=5, abs_normal=6)
 KIND = dict(RWM=0, MALA=1, HMC=2, HMCDA=3)
 ENGINE = dict(auto=0, fused=1, wave=2)
 VTYPE = dict(iid=0, bm=1, imse=2, ipse=3)
@@ -53,7 +53,7 @@ EXPORTS = [
     "mcmcgpu_model_destroy", "mcmcgpu_logtarget_grad", "mcmcgpu_run_chains", "mcmcgpu_run_create",
     "mcmcgpu_run_execute", "mcmcgpu_run_execute_steps", "mcmcgpu_run_set_state", "mcmcgpu_run_get_state",
     "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
-    "mcmcgpu_run_destroy", "mcmcgpu_stats", "mcmcgpu_philox_draws",
+    "mcmcgpu_run_destroy", "mcmcgpu_stats", "mcmcgpu_philox_draws", "mcmcgpu_run_seqmc", "mcmcgpu_run_serialtemp",
 ]
 
 _lib = None
@@ -96,6 +96,12 @@ def lib():
         L.mcmcgpu_run_destroy.argtypes = [vp]
         L.mcmcgpu_stats.argtypes = [vp, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                     dp, dp, dp, dp, dp]
+        L.mcmcgpu_run_seqmc.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(SamplerCfg), C.c_int64, C.c_int64,
+                                        C.c_double, C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int64),
+                                        C.POINTER(RunInfo)]
+        L.mcmcgpu_run_serialtemp.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(SamplerCfg), C.c_int64, C.c_int64,
+                                             C.c_int64, C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int32),
+                                             C.POINTER(RunInfo)]
         L.mcmcgpu_philox_draws.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, dp, dp]
         for n in EXPORTS:
             if n not in ("mcmcgpu_last_error",):
@@ -155,6 +161,42 @@ class Context:
         check(lib().mcmcgpu_stats(self.h, dptr(s), S, d, Cn, VTYPE[vtype], maxlag, batchlen, dptr(outs["mean"]),
                                   dptr(outs["var_iid"]), dptr(outs["var"]), dptr(outs["ess"]), dptr(outs["actime"])))
         return {k: v for k, v in outs.items() if v is not None}
+
+    def _tasks(self, hypers, samplers):
+        hy = np.zeros((len(samplers), 4))
+        for t, h in enumerate(hypers):
+            hy[t, :len(h)] = h
+        return hy, (SamplerCfg * len(samplers))(*samplers)
+
+    def run_seqmc(self, family, d, hypers, samplers, steps, burnin, trigger, particles, seed=0, normals=None, uniforms=None,
+                  res_uniforms=None):
+        """particles (npart, d); injected draws: normals (steps, nt, npart, d), uniforms / res_uniforms (steps, nt, npart).
+        Returns dict(samples ((steps-burnin)*npart, d), weights, n_resamples, info)."""
+        particles = f64(particles)
+        npart, nt = particles.shape[0], len(samplers)
+        hy, sc = self._tasks(hypers, samplers)
+        S = max(steps - burnin, 0) * npart
+        samples, weights = np.empty((S, d)), np.empty(S)
+        nres, info = C.c_int64(0), RunInfo()
+        zn, un, ru = f64(normals), f64(uniforms), f64(res_uniforms)
+        check(lib().mcmcgpu_run_seqmc(self.h, FAM[family], d, nt, dptr(hy), sc, steps, burnin, trigger, npart, dptr(particles), seed,
+                                      dptr(zn), dptr(un), dptr(ru), dptr(samples), dptr(weights), C.byref(nres), C.byref(info)))
+        return dict(samples=samples, weights=weights, n_resamples=nres.value, info=info.as_dict())
+
+    def run_serialtemp(self, family, d, hypers, samplers, steps, burnin, swap_period, nrep, inits, seed=0, normals=None,
+                       uniforms=None, pick=None, swap=None):
+        """inits (nt, d); injected draws per replica: normals (nrep, steps+2, d), uniforms (nrep, steps+2), pick / swap
+        (nrep, steps+1).  Returns dict(samples (nrep, steps-burnin, d), at (nrep, steps-burnin), info)."""
+        inits = f64(inits)
+        nt = len(samplers)
+        hy, sc = self._tasks(hypers, samplers)
+        S = max(steps - burnin, 0)
+        samples, at, info = np.empty((nrep, S, d)), np.empty((nrep, S), dtype=np.int32), RunInfo()
+        zn, un, pk, sw = f64(normals), f64(uniforms), f64(pick), f64(swap)
+        check(lib().mcmcgpu_run_serialtemp(self.h, FAM[family], d, nt, dptr(hy), sc, steps, burnin, swap_period, nrep, dptr(inits), seed,
+                                           dptr(zn), dptr(un), dptr(pk), dptr(sw), dptr(samples),
+                                           at.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info)))
+        return dict(samples=samples, at=at, info=info.as_dict())
 
     def close(self):
         if self.h:

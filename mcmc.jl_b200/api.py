@@ -121,9 +121,9 @@ def model(family, *, gradient=True, grad=None, init=None, scale=1.0, **kw):
         if init is None:
             init = [1.0]                                                   # likmodel.jl:107
         return MCMCLikelihoodModel("normal_fn", init, scale, gradient=gradient)
-    if family == "normal_dsl":
+    if family in ("normal_dsl", "abs_normal"):
         name, v0 = _one_param(kw, ("mu", "sigma"))
-        return MCMCLikelihoodModel("normal_dsl", v0, scale, pmap=_pmap_of([(name, v0)]),
+        return MCMCLikelihoodModel(family, v0, scale, pmap=_pmap_of([(name, v0)]),
                                    hyper=(kw.get("mu", 0.0), kw.get("sigma", 1.0)), gradient=gradient)
     if family in ("linear", "logistic"):
         X = np.asarray(kw.pop("X"), dtype=np.float64)
@@ -313,6 +313,32 @@ class GPUMC(SerialMC):
         assert nchains >= 1
         assert shard in ("chains", "rows")
         self.nchains, self.seed, self.shard, self.store_gradients, self.engine = int(nchains), int(seed), shard, store_gradients, engine
+
+
+class SeqMC:
+    """SeqMC.jl:24-37: SeqMC(steps=, burnin=, trigger=)"""
+    nchains = 1
+
+    def __init__(self, steps=1, burnin=0, trigger=1e-10):
+        assert burnin >= 0, f"Burnin rounds ({burnin}) should be >= 0"
+        assert steps > burnin, f"Steps ({steps}) should be > to burnin ({burnin})"
+        self.steps, self.burnin, self.trigger = int(steps), int(burnin), float(trigger)
+
+    def __rmul__(self, other):
+        return _combine(other, self)
+
+
+class SerialTempMC:
+    """SerialTempMC.jl:16-29: SerialTempMC(steps=, burnin=, swapPeriod=)"""
+    nchains = 1
+
+    def __init__(self, steps=1, burnin=0, swapPeriod=5):
+        assert burnin >= 0, f"Burnin rounds ({burnin}) should be >= 0"
+        assert steps > burnin, f"Steps ({steps}) should be > to burnin ({burnin})"
+        self.steps, self.burnin, self.swapPeriod = int(steps), int(burnin), int(swapPeriod)
+
+    def __rmul__(self, other):
+        return _combine(other, self)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -512,6 +538,10 @@ def run(*args, **kw):
     if isinstance(t, (list, tuple)):
         last = t[-1].runner
         assert all(type(x.runner) is type(last) for x in t), "Runners do not have the same runner type"  # runners.jl:19
+        if isinstance(last, SeqMC):                                        # runners.jl:29-30
+            return _run_seqmc(list(t), **kw)
+        if isinstance(last, SerialTempMC):                                 # runners.jl:27-28
+            return _run_serialtempmc(list(t), **kw)
         return [run(x, **kw) for x in t]
     batch = _run_task(t, **kw)
     if isinstance(t.runner, GPUMC):
@@ -520,6 +550,61 @@ def run(*args, **kw):
     chain.runTime = batch.runTime
     batch.close()
     return chain
+
+
+def _population_tasks(tasks):
+    m0 = tasks[-1].model
+    assert all(t.model.size == m0.size for t in tasks), "Models do not have the same parameter vector size"   # SeqMC.jl:47
+    if any(t.model.family != m0.family for t in tasks):
+        raise NotImplementedError("population runners need every task on the same likelihood family")
+    for t in tasks:
+        if t.sampler.needs_gradient and not t.model.has_gradient:
+            raise AssertionError(f"{type(t.sampler).__name__} sampler requires model with gradient function")
+        if getattr(t.sampler, "tuner", None) is not None or isinstance(t.sampler, HMCDA):
+            raise NotImplementedError("population runners take RWM, MALA or HMC tasks without tuner")
+    return m0, [t.model.hyper for t in tasks], [t.sampler._cfg() for t in tasks]
+
+
+def _run_seqmc(tasks, particles=None, seed=0, normals=None, uniforms=None, res_uniforms=None):
+    """run(targets; particles=...) with SeqMC runners (SeqMC.jl:39-122): one MCMCChain holding (steps-burnin)*npart
+    samples, diagnostics "weigths" (sic, SeqMC.jl:119) and "particle"."""
+    t0 = time.time()
+    r = tasks[-1].runner
+    m0, hypers, samplers = _population_tasks(tasks)
+    if particles is None:                                                  # SeqMC.jl:39 default: 100 particles of randn()
+        particles = np.random.default_rng(seed).standard_normal((100, m0.size))
+    particles = np.asarray([np.atleast_1d(p) for p in particles], dtype=np.float64)
+    res = default_context().run_seqmc(m0.family, m0.size, hypers, samplers, r.steps, r.burnin, r.trigger, particles, seed=seed,
+                                      normals=normals, uniforms=uniforms, res_uniforms=res_uniforms)
+    npart, S = particles.shape[0], (r.steps - r.burnin) * particles.shape[0]
+    diags = {"weigths": res["weights"], "particle": np.tile(np.arange(1, npart + 1), r.steps - r.burnin)}
+    chain = MCMCChain(range(r.burnin + 1, S + 1), res["samples"], None, diags, tasks, time.time() - t0, _colnames(m0))
+    chain.info = res["info"]
+    chain.n_resamples = res["n_resamples"]
+    return chain
+
+
+def _run_serialtempmc(tasks, nreplicas=1, seed=0, **draws):
+    """run(tasks) with SerialTempMC runners (SerialTempMC.jl:31-85): one MCMCChain of steps-burnin draws (the reference
+    stores them column-per-step, :47,77; here rows are draws like every other chain) and the visited task in
+    diagnostics["task"]; nreplicas > 1 returns a list of independent replicas."""
+    t0 = time.time()
+    r = tasks[-1].runner
+    m0, hypers, samplers = _population_tasks(tasks)
+    inits = np.stack([t.model.init for t in tasks])
+    try:
+        res = default_context().run_serialtemp(m0.family, m0.size, hypers, samplers, r.steps, r.burnin, r.swapPeriod, nreplicas,
+                                               inits, seed=seed, **draws)
+    except MCMCGPUError as e:
+        if e.code == capi.E_SUPPORT:
+            raise AssertionError("Initial values out of model support, try other values") from e
+        raise
+    chains = []
+    for c in range(nreplicas):
+        ch = MCMCChain(range(1, 3), res["samples"][c], None, {"task": res["at"][c] + 1}, tasks, time.time() - t0, _colnames(m0))
+        ch.info = res["info"]
+        chains.append(ch)
+    return chains[0] if nreplicas == 1 else chains
 
 
 def prun(tasks, **kw):

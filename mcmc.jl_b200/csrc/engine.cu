@@ -11,6 +11,7 @@
 #include "fused_chain.h"
 #include "k1_regress.h"
 #include "nccl_dyn.h"
+#include "population.h"
 #include "stats.h"
 #include "transition.h"
 
@@ -97,6 +98,23 @@ struct mcmcgpu_run {
 };
 
 // ------------------------------------------------------------------------------------------------
+struct DevBufs {   // frees everything on scope exit
+  std::vector<void*> v;
+  ~DevBufs() { for (void* p : v) cudaFree(p); }
+  template <typename T> cudaError_t get(T** p, size_t n, cudaStream_t st, bool zero = true) {
+    cudaError_t e = dalloc(p, n);
+    if (e != cudaSuccess) return e;
+    v.push_back((void*)*p);
+    return zero ? cudaMemsetAsync(*p, 0, sizeof(T) * (n ? n : 1), st) : cudaSuccess;
+  }
+  template <typename T> cudaError_t up(T** p, const T* host, size_t n, cudaStream_t st) {
+    cudaError_t e = get(p, n, st, false);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(*p, host, sizeof(T) * n, cudaMemcpyHostToDevice, st);
+  }
+};
+
+
 extern "C" {
 
 int32_t mcmcgpu_abi_version(void) { return MCMCGPU_ABI_VERSION; }
@@ -186,6 +204,7 @@ static int model_create_impl(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
   for (int i = 0; i < nhyper; i++) m->hyper[i] = hyper[i];
   switch (family) {
     case MCMCGPU_FAM_NORMAL_FN: m->N = 0; break;
+    case MCMCGPU_FAM_ABS_NORMAL:
     case MCMCGPU_FAM_NORMAL_DSL:
       m->N = 0;
       if (nhyper < 2) { m->hyper[0] = 0.0; m->hyper[1] = 1.0; }
@@ -841,6 +860,140 @@ int32_t mcmcgpu_philox_draws(mcmcgpu_ctx* c, uint64_t seed, int64_t chain_offset
   CU(cudaMemcpyAsync(out_uniforms, un, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   cudaFree(zn); cudaFree(un);
+  return MCMCGPU_OK;
+}
+
+// ---- population runners ----------------------------------------------------------------
+static int fill_tasks(PopTasks& T, int32_t family, int64_t d, int32_t nt, const double* hypers, const mcmcgpu_sampler_cfg* samplers) {
+  if (!pop_supported(family, d)) return fail(MCMCGPU_E_ARG, "population runners support the closed-form families (normal, normal_dsl, abs_normal) with d <= 8");
+  if (nt < 1 || nt > POP_MAX_TASKS) return fail(MCMCGPU_E_ARG, "between 1 and 64 tasks");
+  if (!hypers || !samplers) return fail(MCMCGPU_E_ARG, "NULL argument");
+  T.nt = nt; T.family = family; T.d = (int32_t)d;
+  for (int t = 0; t < nt; t++) {
+    T.hyper[t][0] = hypers[4 * t]; T.hyper[t][1] = hypers[4 * t + 1];
+    const mcmcgpu_sampler_cfg& s = samplers[t];
+    if (s.tuner_on || (s.kind != MCMCGPU_RWM && s.kind != MCMCGPU_MALA && s.kind != MCMCGPU_HMC))
+      return fail(MCMCGPU_E_ARG, "population runners take RWM, MALA or HMC tasks without tuner");
+    if (!(s.scale > 0) || (s.kind == MCMCGPU_HMC && s.nleaps <= 0)) return fail(MCMCGPU_E_ARG, "bad sampler parameters");
+    if ((family == MCMCGPU_FAM_NORMAL_DSL || family == MCMCGPU_FAM_ABS_NORMAL) && !(T.hyper[t][1] > 0)) return fail(MCMCGPU_E_ARG, "sigma must be > 0");
+    T.kind[t] = s.kind; T.nleaps[t] = s.nleaps; T.scale[t] = s.scale;
+  }
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt, const double* hypers,
+                          const mcmcgpu_sampler_cfg* samplers, int64_t steps, int64_t burnin, double trigger, int64_t npart,
+                          const double* particles, uint64_t seed, const double* inj_normals, const double* inj_uniforms,
+                          const double* inj_res_uniforms, double* out_samples, double* out_weights, int64_t* out_nresamples,
+                          mcmcgpu_run_info* info) {
+  if (!c || !particles || !out_samples || !out_weights) return fail(MCMCGPU_E_ARG, "NULL argument");
+  if (burnin < 0) return fail(MCMCGPU_E_ARG, "Burnin rounds should be >= 0");                   // SeqMC.jl:29
+  if (steps <= burnin) return fail(MCMCGPU_E_ARG, "Steps should be > to burnin");               // SeqMC.jl:30
+  if (npart < 2) return fail(MCMCGPU_E_ARG, "at least 2 particles");
+  const bool inj = inj_normals != nullptr;
+  if (inj != (inj_uniforms != nullptr) || inj != (inj_res_uniforms != nullptr)) return fail(MCMCGPU_E_ARG, "inject all three draw arrays or none");
+  SeqArgs A;
+  int rc = fill_tasks(A.T, family, d, nt, hypers, samplers);
+  if (rc != MCMCGPU_OK) return rc;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  DevBufs B;
+  const int64_t Np = round_up(npart, 64), S = (steps - burnin) * npart, K = steps * nt * npart;
+  A.npart = npart; A.Np = Np; A.steps = steps; A.burnin = burnin; A.seed = seed; A.trigger = trigger;
+  double* hp = nullptr;
+  CU(B.up(&hp, particles, (size_t)(npart * d), st));
+  CU(B.get(&A.pars, (size_t)(d * Np), st));
+  CU(transpose_to_chain_minor(hp, A.pars, npart, d, Np, st));
+  CU(B.get(&A.pars_tmp, (size_t)(d * Np), st));
+  CU(B.get(&A.logW, (size_t)Np, st)); CU(B.get(&A.logtarget, (size_t)Np, st)); CU(B.get(&A.lt_tmp, (size_t)Np, st));
+  CU(B.get(&A.W, (size_t)Np, st)); CU(B.get(&A.cp, (size_t)Np, st));
+  CU(B.get(&A.samples, (size_t)(S * d), st, false)); CU(B.get(&A.weights, (size_t)S, st, false));
+  CU(B.get(&A.nres, 1, st)); CU(B.get(&A.nevals, 1, st));
+  A.inj_normals = A.inj_uniforms = A.inj_res = nullptr;
+  if (inj) {
+    double *a = nullptr, *b = nullptr, *r = nullptr;
+    CU(B.up(&a, inj_normals, (size_t)(K * d), st)); CU(B.up(&b, inj_uniforms, (size_t)K, st)); CU(B.up(&r, inj_res_uniforms, (size_t)K, st));
+    A.inj_normals = a; A.inj_uniforms = b; A.inj_res = r;
+  }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, st));
+  int64_t launches = 0;
+  for (int64_t i = 1; i <= steps; i++) {                                                        // SeqMC.jl:62
+    A.iter = i;
+    for (int t = 0; t < nt; t++) {                                                              // :64
+      A.target = t;
+      CU(launch_seqmc_mutate(A, st));
+      CU(launch_seqmc_resample(A, st));
+      launches += 2;
+    }
+    CU(launch_seqmc_store(A, st));
+    launches++;
+  }
+  CU(cudaEventRecord(e1, st));
+  CU(cudaMemcpyAsync(out_samples, A.samples, sizeof(double) * (size_t)(S * d), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_weights, A.weights, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, st));
+  unsigned long long nres = 0, nev = 0;
+  CU(cudaMemcpyAsync(&nres, A.nres, sizeof(nres), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&nev, A.nevals, sizeof(nev), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (out_nresamples) *out_nresamples = (int64_t)nres;
+  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = steps * nt; info->n_launches = launches; info->eval_ms = 0; }
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt, const double* hypers,
+                               const mcmcgpu_sampler_cfg* samplers, int64_t steps, int64_t burnin, int64_t swap_period, int64_t nrep,
+                               const double* inits, uint64_t seed, const double* inj_normals, const double* inj_uniforms,
+                               const double* inj_pick, const double* inj_swap, double* out_samples, int32_t* out_at,
+                               mcmcgpu_run_info* info) {
+  if (!c || !inits || !out_samples) return fail(MCMCGPU_E_ARG, "NULL argument");
+  if (burnin < 0) return fail(MCMCGPU_E_ARG, "Burnin rounds should be >= 0");                   // SerialTempMC.jl:22
+  if (steps <= burnin) return fail(MCMCGPU_E_ARG, "Steps should be > to burnin");               // SerialTempMC.jl:23
+  if (nt < 2 || swap_period < 1 || nrep < 1) return fail(MCMCGPU_E_ARG, "need >= 2 tasks, swapPeriod >= 1, nrep >= 1");
+  const bool inj = inj_normals != nullptr;
+  if (inj != (inj_uniforms != nullptr) || inj != (inj_pick != nullptr) || inj != (inj_swap != nullptr))
+    return fail(MCMCGPU_E_ARG, "inject all four draw arrays or none");
+  TempArgs A;
+  int rc = fill_tasks(A.T, family, d, nt, hypers, samplers);
+  if (rc != MCMCGPU_OK) return rc;
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  DevBufs B;
+  const int64_t S = steps - burnin;
+  A.nrep = nrep; A.steps = steps; A.burnin = burnin; A.swap_period = swap_period; A.seed = seed;
+  double* di = nullptr;
+  CU(B.up(&di, inits, (size_t)(d * nt), st));
+  A.inits = di;
+  A.inj_normals = A.inj_uniforms = A.inj_pick = A.inj_swap = nullptr;
+  if (inj) {
+    double *a = nullptr, *b = nullptr, *p = nullptr, *w = nullptr;
+    CU(B.up(&a, inj_normals, (size_t)(nrep * (steps + 2) * d), st)); CU(B.up(&b, inj_uniforms, (size_t)(nrep * (steps + 2)), st));
+    CU(B.up(&p, inj_pick, (size_t)(nrep * (steps + 1)), st)); CU(B.up(&w, inj_swap, (size_t)(nrep * (steps + 1)), st));
+    A.inj_normals = a; A.inj_uniforms = b; A.inj_pick = p; A.inj_swap = w;
+  }
+  CU(B.get(&A.samples, (size_t)(nrep * S * d), st, false));
+  A.at = nullptr;
+  if (out_at) CU(B.get(&A.at, (size_t)(nrep * S), st));
+  CU(B.get(&A.status, (size_t)nrep, st)); CU(B.get(&A.nevals, 1, st));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(cudaEventRecord(e0, st));
+  CU(launch_serialtemp(A, st));
+  CU(cudaEventRecord(e1, st));
+  CU(cudaMemcpyAsync(out_samples, A.samples, sizeof(double) * (size_t)(nrep * S * d), cudaMemcpyDeviceToHost, st));
+  if (out_at) CU(cudaMemcpyAsync(out_at, A.at, sizeof(int32_t) * (size_t)(nrep * S), cudaMemcpyDeviceToHost, st));
+  std::vector<int32_t> stt((size_t)nrep);
+  unsigned long long nev = 0;
+  CU(cudaMemcpyAsync(stt.data(), A.status, sizeof(int32_t) * (size_t)nrep, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(&nev, A.nevals, sizeof(nev), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = 0; info->n_launches = 1; info->eval_ms = 0; }
+  for (int32_t v : stt) if (v) return fail(MCMCGPU_E_SUPPORT, "Initial values out of model support, try other values");
   return MCMCGPU_OK;
 }
 

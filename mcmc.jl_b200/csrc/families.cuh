@@ -45,6 +45,30 @@ struct Family<MCMCGPU_FAM_NORMAL_DSL, D> {
   }
 };
 
+// README.md:253-259 `y = abs(x); y ~ Normal(mu, sigma)`: abs rule dx += sign(x)*ds, Normal rule MCMCDerivRules.jl:57
+template <int D>
+struct Family<MCMCGPU_FAM_ABS_NORMAL, D> {
+  static __device__ __forceinline__ double evalallg(const ModelDev& M, const double*, int d, const double (&v)[D],
+                                                    double (&g)[D]) {
+    const double mu = M.hyper[0], sigma = M.hyper[1];
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) if (j < d) s += logpdf_normal(fabs(v[j]), mu, sigma);
+    double acc = 0.0 + s;
+    if (!isfinite(acc)) {
+#pragma unroll
+      for (int j = 0; j < D; j++) g[j] = 0.0;
+      return -CUDART_INF;
+    }
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      double sg = (v[j] > 0.0) ? 1.0 : ((v[j] < 0.0) ? -1.0 : 0.0);
+      g[j] = (j < d) ? sg * ((mu - fabs(v[j])) / (sigma * sigma)) : 0.0;
+    }
+    return acc;
+  }
+};
+
 // examples/ornstein.jl:19-27; parameter vector (tau, sigma, mu); series staged in shared memory
 template <int D>
 struct Family<MCMCGPU_FAM_OU, D> {

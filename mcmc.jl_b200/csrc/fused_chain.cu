@@ -257,7 +257,8 @@ static cudaError_t launch_d(const FusedArgs& A, cudaStream_t st) {
 }
 
 bool fused_supported(int family, int64_t d, int64_t N) {
-  if (family == MCMCGPU_FAM_NORMAL_FN || family == MCMCGPU_FAM_NORMAL_DSL) return d >= 1 && d <= FUSED_MAX_D;
+  if (family == MCMCGPU_FAM_NORMAL_FN || family == MCMCGPU_FAM_NORMAL_DSL || family == MCMCGPU_FAM_ABS_NORMAL)
+    return d >= 1 && d <= FUSED_MAX_D;
   if (family == MCMCGPU_FAM_OU) return d == 3 && N >= 2 && N * 8 <= 200 * 1024;
   return false;
 }
@@ -266,6 +267,7 @@ cudaError_t launch_fused(const FusedArgs& A, cudaStream_t st) {
   switch (A.M.family) {
     case MCMCGPU_FAM_NORMAL_FN: return launch_d<MCMCGPU_FAM_NORMAL_FN>(A, st);
     case MCMCGPU_FAM_NORMAL_DSL: return launch_d<MCMCGPU_FAM_NORMAL_DSL>(A, st);
+    case MCMCGPU_FAM_ABS_NORMAL: return launch_d<MCMCGPU_FAM_ABS_NORMAL>(A, st);
     case MCMCGPU_FAM_OU: return launch_one<MCMCGPU_FAM_OU, 3>(A, st);
   }
   return cudaErrorInvalidValue;

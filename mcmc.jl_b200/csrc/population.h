@@ -1,0 +1,42 @@
+#pragma once
+#include "common.cuh"
+namespace mg {
+constexpr int POP_MAX_TASKS = 64;
+struct PopTasks {            // per-task model hyper-parameters and sampler settings (kernel argument, by value)
+  int32_t nt, family, d;
+  double hyper[POP_MAX_TASKS][2];
+  int32_t kind[POP_MAX_TASKS], nleaps[POP_MAX_TASKS];
+  double scale[POP_MAX_TASKS];
+};
+struct SeqArgs {
+  PopTasks T;
+  int64_t npart, Np;         // particles, pitch
+  int64_t iter, target;      // current iteration (1-based) and target (0-based)
+  int64_t steps, burnin;
+  uint64_t seed;
+  double trigger;
+  double *pars, *pars_tmp;   // [d][Np]
+  double *logW, *logtarget, *lt_tmp, *W, *cp;   // [Np]
+  const double *inj_normals, *inj_uniforms, *inj_res;   // host layouts, or null
+  double* samples; double* weights;   // host layouts: d x S*npart, S*npart
+  unsigned long long* nres;
+  unsigned long long* nevals;
+};
+cudaError_t launch_seqmc_mutate(const SeqArgs& A, cudaStream_t st);
+cudaError_t launch_seqmc_resample(const SeqArgs& A, cudaStream_t st);
+cudaError_t launch_seqmc_store(const SeqArgs& A, cudaStream_t st);
+
+struct TempArgs {
+  PopTasks T;
+  int64_t nrep, steps, burnin, swap_period;
+  uint64_t seed;
+  const double* inits;       // d x nt (host layout)
+  const double *inj_normals, *inj_uniforms, *inj_pick, *inj_swap;
+  double* samples;           // d x S x nrep (host layout)
+  int32_t* at;               // S x nrep or null
+  int32_t* status;           // [nrep]
+  unsigned long long* nevals;
+};
+cudaError_t launch_serialtemp(const TempArgs& A, cudaStream_t st);
+bool pop_supported(int family, int64_t d);
+}  // namespace mg

@@ -362,6 +362,18 @@ __global__ void eval_closed_kernel(const ModelDev M, const double* q, double* pa
     bool oos = !isfinite(acc);
     for (int64_t j = 0; j < d; j++) part[j * Cp + c] = oos ? 0.0 : (mu - q[j * Cp + c]) / (sigma * sigma);
     part[d * Cp + c] = oos ? -CUDART_INF : acc;
+  } else if (M.family == MCMCGPU_FAM_ABS_NORMAL) {
+    const double mu = M.hyper[0], sigma = M.hyper[1];
+    double s = 0.0;
+    for (int64_t j = 0; j < d; j++) s += logpdf_normal(fabs(q[j * Cp + c]), mu, sigma);
+    double acc = 0.0 + s;
+    bool oos = !isfinite(acc);
+    for (int64_t j = 0; j < d; j++) {
+      double v = q[j * Cp + c];
+      double sg = (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : 0.0);
+      part[j * Cp + c] = oos ? 0.0 : sg * ((mu - fabs(v)) / (sigma * sigma));
+    }
+    part[d * Cp + c] = oos ? -CUDART_INF : acc;
   } else {  // OU
     double v[3] = {q[c], q[Cp + c], q[2 * Cp + c]}, g[3];
     double lt = Family<MCMCGPU_FAM_OU, 3>::evalallg(M, sh_series, 3, v, g);

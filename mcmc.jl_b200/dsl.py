@@ -31,6 +31,7 @@ def _m(pattern, s):
 
 SHAPES = """recognised model shapes:
   v ~ Normal(mu, sigma)                                                      (README.md:67-72)
+  y = abs(x); y ~ Normal(mu, sigma)                                          (README.md:253-259, the SeqMC ladder)
   vars ~ Normal(0, s); resid = Y - X * vars; resid ~ Normal(0, s2)           (examples/linear_regression.jl:14-18)
   vars ~ Normal(0, s); prob = 1 / (1. + exp(-X * vars)); Y ~ Bernoulli(prob) (examples/logistic_regression.jl:16-20;
                                                                               exp(X * vars) as in test/test_syntax.jl:18)
@@ -55,6 +56,15 @@ def recognise(text, kwargs):
             v0 = np.atleast_1d(np.asarray(need(m["v"]), dtype=np.float64))
             return dict(family="normal_dsl", init=v0, pmap={m["v"]: (1, tuple(np.shape(need(m["v"]))))}, X=None, y=None,
                         hyper=(float(m["mu"]), float(m["sd"])))
+    # --- folded Normal of the SeqMC example (README.md:253-259)
+    if len(st) == 2:
+        a = _m(rf"(?P<y>{_ID})=abs\((?P<x>{_ID})\)", st[0])
+        if a:
+            n = _m(rf"{a['y']}~Normal\((?P<mu>{_NUM}),(?P<sd>{_NUM})\)", st[1])
+            if n:
+                v0 = np.atleast_1d(np.asarray(need(a["x"]), dtype=np.float64))
+                return dict(family="abs_normal", init=v0, pmap={a["x"]: (1, tuple(np.shape(need(a["x"]))))}, X=None, y=None,
+                            hyper=(float(n["mu"]), float(n["sd"])))
     # --- regressions
     if len(st) == 3:
         prior = _m(rf"(?P<b>{_ID})~Normal\(0(?:\.0*)?,(?P<sd>{_NUM})\)", st[0])

@@ -222,8 +222,23 @@ static double eval_ou(const orc_model* m, const double* v, double* grad) {
   return acc;
 }
 
+static double eval_abs_normal(const orc_model* m, const double* v, double* grad) {
+  /* README.md:253-259: y = abs(x); y ~ Normal(mu, sigma).  abs rule: dx += sign(x) * ds; Normal rule MCMCDerivRules.jl:57 */
+  double mu = m->hyper[0], sigma = m->hyper[1];
+  double s = 0.0;
+  for (int64_t j = 0; j < m->d; j++) s += logpdf_normal(fabs(v[j]), mu, sigma);
+  double acc = 0.0 + s;
+  if (!isfinite(acc)) OOS_RETURN(grad, m->d);
+  if (grad) for (int64_t j = 0; j < m->d; j++) {
+    double sg = (v[j] > 0.0) ? 1.0 : ((v[j] < 0.0) ? -1.0 : 0.0);
+    grad[j] = sg * ((mu - fabs(v[j])) / (sigma * sigma));
+  }
+  return acc;
+}
+
 static double eval_any(const orc_model* m, const double* beta, double* grad) {
   switch (m->family) {
+    case ORC_FAM_ABS_NORMAL: return eval_abs_normal(m, beta, grad);
     case ORC_FAM_NORMAL_FN: return eval_normal_fn(m, beta, grad);
     case ORC_FAM_NORMAL_DSL: return eval_normal_dsl(m, beta, grad);
     case ORC_FAM_LINEAR: return eval_linear(m, beta, grad);
@@ -483,6 +498,176 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
   }
   if (n_grad_evals) *n_grad_evals = nev;
   return rc;
+}
+
+
+/* ------------------------------------------------------------------------------------------ */
+/* population runners                                                                          */
+/* ------------------------------------------------------------------------------------------ */
+
+static double sample_var(const double* x, int64_t n);
+
+/* reset(t, pars) followed by one consume(t.task): the sampler's reset hook re-evaluates the log-target
+ * (and gradient) at pars (RWM.jl:49, MALA.jl:75-78, HMC.jl:114-116), then one loop body runs.
+ * In: pars.  Out: ppars (post-decision state), *plt (its log-target), *lt0 (log-target at pars before the step). */
+static void reset_and_step(const orc_model* m, const orc_sampler* s, const double* pars, const double* z, double u,
+                           double* ppars, double* plt, double* lt0) {
+  int64_t d = m->d;
+  double* prop = (double*)malloc(sizeof(double) * (size_t)d);
+  double* grad = (double*)malloc(sizeof(double) * (size_t)d);
+  double* pg = (double*)malloc(sizeof(double) * (size_t)d);
+  double* mom = (double*)malloc(sizeof(double) * (size_t)d);
+  int acc = 0;
+  double lt, l2 = NAN;
+  if (s->kind == ORC_RWM) {
+    lt = orc_eval(m, pars);
+    for (int64_t j = 0; j < d; j++) prop[j] = pars[j] + z[j] * (1.0 * s->scale);   /* model.scale = ones (RWM.jl:52,59) */
+    l2 = orc_eval(m, prop);
+    double ratio = l2 - lt;
+    acc = ratio > 0 || ratio > log(u);                                             /* RWM.jl:63 */
+  } else if (s->kind == ORC_MALA) {
+    double h = s->scale, sq = sqrt(h), lc = log(TWO_PI * h) / 2.0, qno = 0.0, qon = 0.0;
+    lt = orc_evalallg(m, pars, grad);
+    for (int64_t j = 0; j < d; j++) { mom[j] = pars[j] + (h / 2.0) * grad[j]; prop[j] = mom[j] + sq * z[j]; }  /* MALA.jl:98-100 */
+    l2 = orc_evalallg(m, prop, pg);
+    for (int64_t j = 0; j < d; j++) { double t = mom[j] - prop[j]; qno += -(t * t) / (2.0 * h) - lc; }
+    for (int64_t j = 0; j < d; j++) { double m2 = prop[j] + (h / 2.0) * pg[j]; double t = m2 - pars[j]; qon += -(t * t) / (2.0 * h) - lc; }
+    double ratio = l2 + qon - lt - qno;
+    acc = ratio > 0 || ratio > log(u);                                             /* MALA.jl:107-108 */
+  } else {  /* HMC, fixed nLeaps (HMC.jl:136-158) */
+    double eps = s->scale;
+    lt = orc_evalallg(m, pars, grad);
+    double H0 = -lt + 0.5 * dotp(z, z, d);
+    for (int64_t j = 0; j < d; j++) { mom[j] = z[j]; prop[j] = pars[j]; pg[j] = grad[j]; }
+    l2 = lt;
+    for (int l = 0; l < s->nleaps; l++) {
+      for (int64_t j = 0; j < d; j++) mom[j] += (0.5 * pg[j]) * eps;
+      for (int64_t j = 0; j < d; j++) prop[j] += eps * mom[j];
+      l2 = orc_evalallg(m, prop, pg);
+      for (int64_t j = 0; j < d; j++) mom[j] += (0.5 * pg[j]) * eps;
+    }
+    double H = -l2 + 0.5 * dotp(mom, mom, d);
+    acc = u < exp(H0 - H);
+  }
+  if (acc) { memcpy(ppars, prop, sizeof(double) * (size_t)d); *plt = l2; }
+  else { memcpy(ppars, pars, sizeof(double) * (size_t)d); *plt = lt; }
+  *lt0 = lt;
+  free(prop); free(grad); free(pg); free(mom);
+}
+
+int32_t orc_run_seqmc(const orc_model* models, const orc_sampler* samplers, int32_t nt, int64_t steps, int64_t burnin,
+                      double trigger, int64_t npart, const double* particles, const double* normals,
+                      const double* uniforms, const double* res_uniforms, double* samples, double* weights,
+                      int64_t* n_resamples) {
+  /* SeqMC.jl:39-122 */
+  if (burnin < 0 || steps <= burnin || nt < 1 || npart < 2) return -2;        /* :29-30 */
+  int64_t d = models[0].d;
+  for (int t = 0; t < nt; t++) if (models[t].d != d) return -2;               /* :47 */
+  double* pars = (double*)malloc(sizeof(double) * (size_t)(d * npart));
+  double* tmp = (double*)malloc(sizeof(double) * (size_t)(d * npart));
+  double* logW = (double*)calloc((size_t)npart, sizeof(double));
+  double* logtarget = (double*)calloc((size_t)npart, sizeof(double));
+  double* W = (double*)malloc(sizeof(double) * (size_t)npart);
+  double* cp = (double*)malloc(sizeof(double) * (size_t)npart);
+  double* lt2 = (double*)malloc(sizeof(double) * (size_t)npart);
+  int64_t* rs = (int64_t*)malloc(sizeof(int64_t) * (size_t)npart);
+  double* pp = (double*)malloc(sizeof(double) * (size_t)d);
+  memcpy(pars, particles, sizeof(double) * (size_t)(d * npart));               /* :58 */
+  int64_t nres = 0;
+  for (int64_t i = 1; i <= steps; i++) {
+    for (int t = 0; t < nt; t++) {
+      for (int64_t n = 0; n < npart; n++) {                                    /* :66-72 mutate each particle with task t */
+        int64_t k = ((i - 1) * nt + t) * npart + n;
+        double plt, ll0;
+        reset_and_step(&models[t], &samplers[t], pars + n * d, normals + k * d, uniforms[k], pp, &plt, &ll0);
+        memcpy(pars + n * d, pp, sizeof(double) * (size_t)d);
+        logW[n] += ll0 - logtarget[n];
+        logtarget[n] = plt;
+      }
+      for (int64_t n = 0; n < npart; n++) W[n] = exp(logW[n]);                 /* :76 */
+      if (sample_var(W, npart) < trigger) {                                    /* :77 */
+        double c = 0.0, tot = 0.0;
+        for (int64_t n = 0; n < npart; n++) tot += W[n];
+        for (int64_t n = 0; n < npart; n++) { c += W[n]; cp[n] = c / tot; }     /* :78 cumsum(W) / sum(W) */
+        for (int64_t n = 0; n < npart; n++) {                                  /* :80-83 */
+          double l = res_uniforms[((i - 1) * nt + t) * npart + n];
+          int64_t f = npart - 1;
+          for (int64_t q = 0; q < npart; q++) if (cp[q] >= l) { f = q; break; }
+          rs[n] = f;
+        }
+        for (int64_t n = 0; n < npart; n++) { memcpy(tmp + n * d, pars + rs[n] * d, sizeof(double) * (size_t)d); lt2[n] = logtarget[rs[n]]; }
+        memcpy(pars, tmp, sizeof(double) * (size_t)(d * npart));               /* :84 */
+        memcpy(logtarget, lt2, sizeof(double) * (size_t)npart);                /* :86 */
+        for (int64_t n = 0; n < npart; n++) logW[n] = 0.0;                     /* :85 */
+        nres++;
+      }
+    }
+    for (int64_t n = 0; n < npart; n++) logtarget[n] = 0.0;                    /* :92 */
+    if (i > burnin) {                                                          /* :94-100 */
+      int64_t pos = (i - burnin - 1) * npart;
+      for (int64_t n = 0; n < npart; n++) {
+        memcpy(samples + (pos + n) * d, pars + n * d, sizeof(double) * (size_t)d);
+        weights[pos + n] = exp(logW[n]);
+      }
+    }
+  }
+  if (n_resamples) *n_resamples = nres;
+  free(pars); free(tmp); free(logW); free(logtarget); free(W); free(cp); free(lt2); free(rs); free(pp);
+  return 0;
+}
+
+int32_t orc_run_serialtemp(const orc_model* models, const orc_sampler* samplers, int32_t nt, int64_t steps, int64_t burnin,
+                           int64_t swap_period, const double* inits, const double* normals, const double* uniforms,
+                           const double* u_pick, const double* u_swap, double* samples, int32_t* at_out) {
+  /* SerialTempMC.jl:31-85.  Only the active task's sampler state matters: any other task is reset (:62) before it is
+   * consumed.  s = (ppars, logtarget, pars) is the last accepted-as-current MCMCSample (:53,71). */
+  if (burnin < 0 || steps <= burnin || nt < 2 || swap_period < 1) return -2;   /* :22-23 */
+  int64_t d = models[0].d;
+  for (int t = 0; t < nt; t++) {
+    if (models[t].d != d) return -2;                                           /* :39 */
+    if (!isfinite(orc_eval(&models[t], inits + t * d))) return -1;             /* every task is started (:44) */
+  }
+  double* state = (double*)malloc(sizeof(double) * (size_t)d);  /* internal pars of the active task (post-decision) */
+  double* ppars = (double*)malloc(sizeof(double) * (size_t)d);  /* s.ppars */
+  double* pars = (double*)malloc(sizeof(double) * (size_t)d);   /* s.pars: the state BEFORE the step that produced s */
+  double* pp2 = (double*)malloc(sizeof(double) * (size_t)d);
+  int at = 0;
+  double plt, lt0, logtarget;
+  /* :44 map(t -> consume(t.task), tasks): first step of every task from its model.init; only task 1's persists */
+  reset_and_step(&models[0], &samplers[0], inits, normals + 0 * d, uniforms[0], state, &plt, &lt0);
+  /* :51 s = consume(tasks[at].task): task 1's second step, from its own state (draw column 1) */
+  memcpy(pars, state, sizeof(double) * (size_t)d);
+  reset_and_step(&models[0], &samplers[0], pars, normals + 1 * d, uniforms[1], ppars, &plt, &lt0);
+  memcpy(state, ppars, sizeof(double) * (size_t)d);
+  logtarget = lt0;                                                             /* s.logtarget (:53) */
+  for (int64_t i = 1; i <= steps; i++) {
+    const double* z = normals + (i + 1) * d;
+    const double u = uniforms[i + 1];
+    if (i % swap_period == 0) {                                                /* :57 attempt a task switch */
+      int at2 = (int)floor(u_pick[i] * (double)(nt - 1));                      /* :59 rand(1:(nmods-1)), 0-based here */
+      if (at2 > nt - 2) at2 = nt - 2;
+      if (at2 >= at) at2 += 1;                                                 /* :60 */
+      double plt2, lt02;
+      reset_and_step(&models[at2], &samplers[at2], pars, z, u, pp2, &plt2, &lt02);   /* :62-63 reset to s.pars, consume */
+      if (u_swap[i] < exp(logtarget - lt02 + 0.0 - 0.0)) {                     /* :64; logW stays 0 (:48,:70) */
+        at = at2;                                                              /* :65 at, s = at2, s2 */
+        memcpy(ppars, pp2, sizeof(double) * (size_t)d);
+        memcpy(state, pp2, sizeof(double) * (size_t)d);
+        logtarget = lt02;                                                      /* s2.pars == pars already */
+      }
+    } else {                                                                   /* :68 */
+      memcpy(pars, state, sizeof(double) * (size_t)d);
+      reset_and_step(&models[at], &samplers[at], pars, z, u, ppars, &plt, &lt0);
+      memcpy(state, ppars, sizeof(double) * (size_t)d);
+      logtarget = lt0;
+    }
+    if (i > burnin) {                                                          /* :73-76 */
+      memcpy(samples + (i - burnin - 1) * d, ppars, sizeof(double) * (size_t)d);
+      if (at_out) at_out[i - burnin - 1] = at;
+    }
+  }
+  free(state); free(ppars); free(pars); free(pp2);
+  return 0;
 }
 
 /* ------------------------------------------------------------------------------------------ */

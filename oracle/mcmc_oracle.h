@@ -29,7 +29,8 @@ enum {
   ORC_FAM_LINEAR = 2,    /* examples/linear_regression.jl:14-18            hyper = {prior_sd, noise_sd} */
   ORC_FAM_LOGISTIC = 3,  /* examples/logistic_regression.jl:16-20          hyper = {prior_sd, sign} sign=-1: exp(-X*b) (example); +1: test/test_syntax.jl:18 */
   ORC_FAM_PROBIT = 4,    /* examples/probit_regression.jl:18-41            hyper = {prior_sd}        */
-  ORC_FAM_OU = 5         /* examples/ornstein.jl:19-27                     hyper = {tau_hi, sigma_hi, mu_hi}; y = series x[0..N-1], d = 3 (tau, sigma, mu) */
+  ORC_FAM_OU = 5,        /* examples/ornstein.jl:19-27                     hyper = {tau_hi, sigma_hi, mu_hi}; y = series x[0..N-1], d = 3 (tau, sigma, mu) */
+  ORC_FAM_ABS_NORMAL = 6 /* README.md:253-259  y = abs(x); y ~ Normal(mu, sigma)   hyper = {mu, sigma}  (the SeqMC ladder) */
 };
 
 typedef struct {
@@ -86,6 +87,27 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
                       double* samples, double* grads, uint8_t* accept, double* logtarget,
                       double* diag_eps, int64_t* diag_nleaps, int64_t* n_grad_evals);
 int64_t orc_range_length(const orc_range* r);
+
+/* ---- population runners --------------------------------------------------------------
+ * Targets/tasks t = 0..nt-1 share family and size; models[t], samplers[t] (RWM / MALA / HMC without tuner).
+ *
+ * SeqMC (src/runners/SeqMC.jl:39-122): particles npart x d (column-major d x npart).  Draw layout, all indexed by
+ * k = ((i-1)*nt + t)*npart + n for iteration i (1-based), target t, particle n:
+ *   normals d x K, uniforms K (MH test), res_uniforms K (multinomial resampling, used only when it triggers).
+ * Outputs: samples d x ((steps-burnin)*npart), weights (steps-burnin)*npart, n_resamples.
+ *
+ * SerialTempMC (src/runners/SerialTempMC.jl:31-85), one replica: inits d x nt (model.init of every task),
+ * normals d x (steps+2) and uniforms steps+2 (MH tests): column 0 = the first consume of task 1 (:44), column 1 = the
+ * consume before the loop (:51), column i+1 = iteration i; u_pick steps+1 (at2 = floor(u*(nt-1)) shifted past `at`,
+ * :59-60) and u_swap steps+1 (:64), both indexed by iteration i (entry 0 unused).
+ * Outputs: samples d x (steps-burnin) (ppars, :73-75), at (steps-burnin) the task the replica is on. */
+int32_t orc_run_seqmc(const orc_model* models, const orc_sampler* samplers, int32_t nt, int64_t steps, int64_t burnin,
+                      double trigger, int64_t npart, const double* particles, const double* normals,
+                      const double* uniforms, const double* res_uniforms, double* samples, double* weights,
+                      int64_t* n_resamples);
+int32_t orc_run_serialtemp(const orc_model* models, const orc_sampler* samplers, int32_t nt, int64_t steps, int64_t burnin,
+                           int64_t swap_period, const double* inits, const double* normals, const double* uniforms,
+                           const double* u_pick, const double* u_swap, double* samples, int32_t* at_out);
 
 /* ---- stats over one stored series x[0..n-1] (src/stats) ---- */
 double orc_mean(const double* x, int64_t n);                     /* mean.jl:6         */

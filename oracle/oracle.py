@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libmcmc_oracle.so")
 
-FAM = dict(normal_fn=0, normal_dsl=1, linear=2, logistic=3, probit=4, ou=5)
+FAM = dict(normal_fn=0, normal_dsl=1, linear=2, logistic=3, probit=4, ou=5, abs_normal=6)
 KIND = dict(RWM=0, MALA=1, HMC=2, HMCDA=3)
 
 
@@ -157,6 +157,50 @@ def run_chain(model, smp, rng, init, scale=None, normals=None, uniforms=None):
                              _dp(lt), _dp(eps), nl.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nev))
     return dict(samples=samples, grads=grads, accept=accept, logtarget=lt, eps=eps, nleaps=nl,
                 n_grad_evals=nev.value, rc=rc)
+
+
+def _arrays(models, samplers):
+    ms = (_Model * len(models))(*[m._c for m in models])
+    ss = (_Sampler * len(samplers))(*samplers)
+    return ms, ss
+
+
+def run_seqmc(models, samplers, steps, burnin, trigger, particles, normals, uniforms, res_uniforms):
+    """particles (npart, d); normals (steps, nt, npart, d); uniforms / res_uniforms (steps, nt, npart)."""
+    nt, d = len(models), models[0].d
+    particles = np.ascontiguousarray(particles, dtype=np.float64)
+    npart = particles.shape[0]
+    normals = np.ascontiguousarray(normals, dtype=np.float64); uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+    res_uniforms = np.ascontiguousarray(res_uniforms, dtype=np.float64)
+    assert normals.shape == (steps, nt, npart, d) and uniforms.shape == (steps, nt, npart) == res_uniforms.shape
+    S = (steps - burnin) * npart
+    samples = np.full((max(S, 0), d), np.nan); weights = np.full(max(S, 0), np.nan)
+    nres = C.c_int64(0)
+    ms, ss = _arrays(models, samplers)
+    L = lib()
+    L.orc_run_seqmc.restype = C.c_int32
+    rc = L.orc_run_seqmc(ms, ss, C.c_int32(nt), C.c_int64(steps), C.c_int64(burnin), C.c_double(trigger), C.c_int64(npart),
+                         _dp(particles), _dp(normals), _dp(uniforms), _dp(res_uniforms), _dp(samples), _dp(weights), C.byref(nres))
+    return dict(samples=samples, weights=weights, n_resamples=nres.value, rc=rc)
+
+
+def run_serialtemp(models, samplers, steps, burnin, swap_period, inits, normals, uniforms, u_pick, u_swap):
+    """inits (nt, d); normals (steps+2, d); uniforms (steps+2,); u_pick, u_swap (steps+1,)."""
+    nt, d = len(models), models[0].d
+    inits = np.ascontiguousarray(inits, dtype=np.float64)
+    normals = np.ascontiguousarray(normals, dtype=np.float64); uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+    u_pick = np.ascontiguousarray(u_pick, dtype=np.float64); u_swap = np.ascontiguousarray(u_swap, dtype=np.float64)
+    assert inits.shape == (nt, d) and normals.shape == (steps + 2, d) and uniforms.shape == (steps + 2,)
+    assert u_pick.shape == (steps + 1,) == u_swap.shape
+    S = steps - burnin
+    samples = np.full((max(S, 0), d), np.nan); at = np.zeros(max(S, 0), dtype=np.int32)
+    ms, ss = _arrays(models, samplers)
+    L = lib()
+    L.orc_run_serialtemp.restype = C.c_int32
+    rc = L.orc_run_serialtemp(ms, ss, C.c_int32(nt), C.c_int64(steps), C.c_int64(burnin), C.c_int64(swap_period), _dp(inits),
+                              _dp(normals), _dp(uniforms), _dp(u_pick), _dp(u_swap), _dp(samples),
+                              at.ctypes.data_as(C.POINTER(C.c_int32)))
+    return dict(samples=samples, at=at, rc=rc)
 
 
 def mean(x):
