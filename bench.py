@@ -379,7 +379,8 @@ def main():
     evals = torch.tensor([float(info["n_grad_evals"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(evals, op=dist.ReduceOp.SUM)
+        if not row_sharded:                   # replicated chains: every rank counts the same evaluations
+            dist.all_reduce(evals, op=dist.ReduceOp.SUM)
     ms_max, e2e_ms_max = times.tolist()
     total_chains = C if row_sharded else C * world
     value = total_chains * K / (ms_max / 1e3)

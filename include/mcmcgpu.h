@@ -181,6 +181,10 @@ int32_t mcmcgpu_stats(mcmcgpu_ctx* ctx, const double* samples, int64_t S, int64_
  * cumulative sum and the multinomial resampling (prefix sum + binary search) stay on the device.
  * particles d x npart; injected draws (all NULL for Philox): normals d x npart x nt x steps, uniforms and
  * res_uniforms npart x nt x steps.  out_samples d x ((steps-burnin)*npart), out_weights (steps-burnin)*npart.
+ * With a communicator (mcmcgpu_comm_init) the population is sharded: npart is THIS rank's share (equal on every
+ * rank, global particle g = rank*npart + n), the ranks exchange (pars, logtarget, logW) with one ncclAllGather per
+ * target and resample their own slots from the global weights; injected draws are then the GLOBAL arrays
+ * (npart*nranks particles) and the outputs hold this rank's particles only.
  *
  * mcmcgpu_run_serialtemp stands in for run(tasks) with SerialTempMC runners (src/runners/SerialTempMC.jl:31-85)
  * for nrep independent replicas at once.  inits d x nt; injected draws (all NULL for Philox): normals

@@ -898,15 +898,28 @@ int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt,
   CU(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   DevBufs B;
-  const int64_t Np = round_up(npart, 64), S = (steps - burnin) * npart, K = steps * nt * npart;
+  const int64_t Np = round_up(npart, 64), S = (steps - burnin) * npart, K = steps * nt * npart * (c->comm ? c->nranks : 1);
   A.npart = npart; A.Np = Np; A.steps = steps; A.burnin = burnin; A.seed = seed; A.trigger = trigger;
+  // particles sharded over the ranks of the context's communicator: npart is THIS rank's share (equal on all ranks);
+  // per target the ranks exchange (pars, logtarget, logW) with one ncclAllGather and resample their own slots
+  A.rank = c->comm ? c->rank : 0; A.nranks = c->comm ? c->nranks : 1;
+  A.gpart = npart * A.nranks; A.sendbuf = nullptr; A.gathered = nullptr;
+  const NcclApi* api = nullptr;
+  if (A.nranks > 1) {
+    api = nccl_api(nullptr);
+    if (!api) return fail(MCMCGPU_E_COMM, "NCCL unavailable");
+    double* gb = nullptr;
+    CU(B.get(&A.sendbuf, (size_t)((d + 2) * Np), st));
+    CU(B.get(&gb, (size_t)(A.nranks * (d + 2) * Np), st));
+    A.gathered = gb;
+  }
   double* hp = nullptr;
   CU(B.up(&hp, particles, (size_t)(npart * d), st));
   CU(B.get(&A.pars, (size_t)(d * Np), st));
   CU(transpose_to_chain_minor(hp, A.pars, npart, d, Np, st));
   CU(B.get(&A.pars_tmp, (size_t)(d * Np), st));
   CU(B.get(&A.logW, (size_t)Np, st)); CU(B.get(&A.logtarget, (size_t)Np, st)); CU(B.get(&A.lt_tmp, (size_t)Np, st));
-  CU(B.get(&A.W, (size_t)Np, st)); CU(B.get(&A.cp, (size_t)Np, st));
+  CU(B.get(&A.W, (size_t)(Np * (c->comm ? c->nranks : 1)), st)); CU(B.get(&A.cp, (size_t)(Np * (c->comm ? c->nranks : 1)), st));
   CU(B.get(&A.samples, (size_t)(S * d), st, false)); CU(B.get(&A.weights, (size_t)S, st, false));
   CU(B.get(&A.nres, 1, st)); CU(B.get(&A.nevals, 1, st));
   A.inj_normals = A.inj_uniforms = A.inj_res = nullptr;
@@ -924,6 +937,12 @@ int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt,
     for (int t = 0; t < nt; t++) {                                                              // :64
       A.target = t;
       CU(launch_seqmc_mutate(A, st));
+      if (A.nranks > 1) {
+        CU(launch_seqmc_pack(A, st));
+        int nrc = api->AllGather(A.sendbuf, (void*)A.gathered, (size_t)((d + 2) * Np), NCCL_FLOAT64, c->comm, st);
+        if (nrc != 0) return fail(MCMCGPU_E_COMM, std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(nrc) : "error"));
+        launches++;
+      }
       CU(launch_seqmc_resample(A, st));
       launches += 2;
     }

@@ -19,9 +19,10 @@ const NcclApi* nccl_api(const char** err) {
       g_api.GetUniqueId = (int (*)(NcclUniqueId*))dlsym(g_api.handle, "ncclGetUniqueId");
       g_api.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int))dlsym(g_api.handle, "ncclCommInitRank");
       g_api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))dlsym(g_api.handle, "ncclAllReduce");
+      g_api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))dlsym(g_api.handle, "ncclAllGather");
       g_api.CommDestroy = (int (*)(NcclComm))dlsym(g_api.handle, "ncclCommDestroy");
       g_api.GetErrorString = (const char* (*)(int))dlsym(g_api.handle, "ncclGetErrorString");
-      if (!g_api.GetUniqueId || !g_api.CommInitRank || !g_api.AllReduce || !g_api.CommDestroy) g_err = "libnccl lacks required symbols";
+      if (!g_api.GetUniqueId || !g_api.CommInitRank || !g_api.AllReduce || !g_api.AllGather || !g_api.CommDestroy) g_err = "libnccl lacks required symbols";
     }
   }
   if (g_err) { if (err) *err = g_err; return nullptr; }

@@ -12,6 +12,7 @@ struct NcclApi {
   int (*GetUniqueId)(NcclUniqueId*) = nullptr;
   int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t /*sendcount*/, int /*dtype*/, NcclComm, cudaStream_t) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(128) seqmc_mutate_kernel(const SeqArgs A) {
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= A.npart) return;
   const int d = A.T.d, t = (int)A.target;
-  const int64_t k = ((A.iter - 1) * A.T.nt + t) * A.npart + n;
+  const int64_t gn = (int64_t)A.rank * A.npart + n;     // global particle id (Philox key / injected-draw index)
+  const int64_t k = ((A.iter - 1) * A.T.nt + t) * A.gpart + gn;
   const uint32_t pstep = (uint32_t)((A.iter - 1) * A.T.nt + t + 1);
   double pars[D], z[D], pp[D];
 #pragma unroll
@@ -95,11 +96,11 @@ __global__ void __launch_bounds__(128) seqmc_mutate_kernel(const SeqArgs A) {
 #pragma unroll
     for (int b = 0; 2 * b < D; b++) {
       double z0 = 0.0, z1 = 0.0;
-      if (2 * b < d) philox_normal_pair(A.seed, (uint64_t)n, pstep, (uint32_t)b, z0, z1);
+      if (2 * b < d) philox_normal_pair(A.seed, (uint64_t)gn, pstep, (uint32_t)b, z0, z1);
       z[2 * b] = z0;
       if (2 * b + 1 < D) z[2 * b + 1] = (2 * b + 1 < d) ? z1 : 0.0;
     }
-    u = philox_uniform(A.seed, (uint64_t)n, pstep);
+    u = philox_uniform(A.seed, (uint64_t)gn, pstep);
   }
   double plt, ll0;
   unsigned long long nev = 0;
@@ -111,50 +112,77 @@ __global__ void __launch_bounds__(128) seqmc_mutate_kernel(const SeqArgs A) {
   atomicAdd(A.nevals, nev);
 }
 
+// accessors over the population: local arrays on one GPU, the all-gathered [rank][d+2][Np] image otherwise
+__device__ __forceinline__ double g_logW(const SeqArgs& A, int64_t gn) {
+  if (A.nranks == 1) return A.logW[gn];
+  const int64_t r = gn / A.npart, l = gn % A.npart;
+  return A.gathered[(r * (A.T.d + 2) + A.T.d + 1) * A.Np + l];
+}
+__device__ __forceinline__ double g_lt(const SeqArgs& A, int64_t gn) {
+  if (A.nranks == 1) return A.logtarget[gn];
+  const int64_t r = gn / A.npart, l = gn % A.npart;
+  return A.gathered[(r * (A.T.d + 2) + A.T.d) * A.Np + l];
+}
+__device__ __forceinline__ double g_par(const SeqArgs& A, int j, int64_t gn) {
+  if (A.nranks == 1) return A.pars[j * A.Np + gn];
+  const int64_t r = gn / A.npart, l = gn % A.npart;
+  return A.gathered[(r * (A.T.d + 2) + j) * A.Np + l];
+}
+
+__global__ void seqmc_pack_kernel(const SeqArgs A) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= A.npart) return;
+  const int d = A.T.d;
+  for (int j = 0; j < d; j++) A.sendbuf[j * A.Np + n] = A.pars[j * A.Np + n];
+  A.sendbuf[d * A.Np + n] = A.logtarget[n];
+  A.sendbuf[(d + 1) * A.Np + n] = A.logW[n];
+}
+
 __global__ void __launch_bounds__(1024) seqmc_resample_kernel(const SeqArgs A) {
-  // SeqMC.jl:74-89.  One block.  The sums that decide and define the resampling are taken sequentially by one thread,
-  // in the reference's order (var two-pass, cumsum), so that the resampled indices are reproducible bit for bit;
-  // the per-particle binary searches and the gather are done by all threads.
+  // SeqMC.jl:74-89.  One block (every rank runs it on the same gathered population).  The sums that decide and define
+  // the resampling are taken sequentially by one thread, in the reference's order (var two-pass, cumsum), so that the
+  // resampled indices are reproducible bit for bit; the binary searches and the gather are done by all threads.
   __shared__ int do_res;
-  const int64_t np = A.npart;
-  for (int64_t n = threadIdx.x; n < np; n += blockDim.x) A.W[n] = exp(A.logW[n]);          // :76
+  const int64_t gp = A.gpart;
+  for (int64_t n = threadIdx.x; n < gp; n += blockDim.x) A.W[n] = exp(g_logW(A, n));         // :76
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int64_t n = 0; n < np; n++) s += A.W[n];
-    const double mean = s / (double)np;
+    for (int64_t n = 0; n < gp; n++) s += A.W[n];
+    const double mean = s / (double)gp;
     double ss = 0.0;
-    for (int64_t n = 0; n < np; n++) { double v = A.W[n] - mean; ss += v * v; }
-    const double var = ss / (double)(np - 1);
-    do_res = (var < A.trigger) ? 1 : 0;                                                    // :77
+    for (int64_t n = 0; n < gp; n++) { double v = A.W[n] - mean; ss += v * v; }
+    const double var = ss / (double)(gp - 1);
+    do_res = (var < A.trigger) ? 1 : 0;                                                      // :77
     if (do_res) {
       double c = 0.0;
-      for (int64_t n = 0; n < np; n++) { c += A.W[n]; A.cp[n] = c / s; }                   // :78 cumsum(W) / sum(W)
+      for (int64_t n = 0; n < gp; n++) { c += A.W[n]; A.cp[n] = c / s; }                     // :78 cumsum(W) / sum(W)
       atomicAdd(A.nres, 1ull);
     }
   }
   __syncthreads();
   if (!do_res) return;
   const int d = A.T.d;
-  const int64_t kbase = ((A.iter - 1) * A.T.nt + A.target) * np;
+  const int64_t kbase = ((A.iter - 1) * A.T.nt + A.target) * gp;
   const uint32_t pstep = (uint32_t)((A.iter - 1) * A.T.nt + A.target + 1);
-  for (int64_t n = threadIdx.x; n < np; n += blockDim.x) {
+  for (int64_t n = threadIdx.x; n < A.npart; n += blockDim.x) {                              // this rank's slots
+    const int64_t gn = (int64_t)A.rank * A.npart + n;
     double l;
-    if (A.inj_res) l = A.inj_res[kbase + n];
+    if (A.inj_res) l = A.inj_res[kbase + gn];
     else {
-      u4 o = philox4x32_10((uint32_t)n, (uint32_t)((uint64_t)n >> 32), pstep, 0xFFFFFFFEu, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+      u4 o = philox4x32_10((uint32_t)gn, (uint32_t)((uint64_t)gn >> 32), pstep, 0xFFFFFFFEu, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
       l = u01(o.x, o.y);
     }
-    int64_t lo = 0, hi = np - 1;                                                           // :82 findfirst(p -> p >= l, cp)
+    int64_t lo = 0, hi = gp - 1;                                                             // :82 findfirst(p -> p >= l, cp)
     while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (A.cp[mid] >= l) hi = mid; else lo = mid + 1; }
-    for (int j = 0; j < d; j++) A.pars_tmp[j * A.Np + n] = A.pars[j * A.Np + lo];          // :84 pars = pars[rs]
-    A.lt_tmp[n] = A.logtarget[lo];                                                         // :86
+    for (int j = 0; j < d; j++) A.pars_tmp[j * A.Np + n] = g_par(A, j, lo);                  // :84 pars = pars[rs]
+    A.lt_tmp[n] = g_lt(A, lo);                                                               // :86
   }
   __syncthreads();
-  for (int64_t n = threadIdx.x; n < np; n += blockDim.x) {
+  for (int64_t n = threadIdx.x; n < A.npart; n += blockDim.x) {
     for (int j = 0; j < d; j++) A.pars[j * A.Np + n] = A.pars_tmp[j * A.Np + n];
     A.logtarget[n] = A.lt_tmp[n];
-    A.logW[n] = 0.0;                                                                       // :85
+    A.logW[n] = 0.0;                                                                         // :85
   }
 }
 
@@ -190,6 +218,10 @@ cudaError_t launch_seqmc_mutate(const SeqArgs& A, cudaStream_t st) {
 }
 cudaError_t launch_seqmc_resample(const SeqArgs& A, cudaStream_t st) {
   seqmc_resample_kernel<<<1, 1024, 0, st>>>(A);
+  return cudaGetLastError();
+}
+cudaError_t launch_seqmc_pack(const SeqArgs& A, cudaStream_t st) {
+  seqmc_pack_kernel<<<(unsigned)((A.npart + 127) / 128), 128, 0, st>>>(A);
   return cudaGetLastError();
 }
 cudaError_t launch_seqmc_store(const SeqArgs& A, cudaStream_t st) {

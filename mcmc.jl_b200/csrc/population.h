@@ -10,7 +10,11 @@ struct PopTasks {            // per-task model hyper-parameters and sampler sett
 };
 struct SeqArgs {
   PopTasks T;
-  int64_t npart, Np;         // particles, pitch
+  int64_t npart, Np;         // particles held by THIS rank, pitch
+  int64_t gpart;             // particles over all ranks (== npart on one GPU)
+  int32_t rank, nranks;
+  double* sendbuf;           // [d+2][Np]: pars rows, logtarget, logW of this rank (multi-GPU only)
+  const double* gathered;    // [nranks][d+2][Np] after ncclAllGather (multi-GPU only)
   int64_t iter, target;      // current iteration (1-based) and target (0-based)
   int64_t steps, burnin;
   uint64_t seed;
@@ -25,6 +29,7 @@ struct SeqArgs {
 cudaError_t launch_seqmc_mutate(const SeqArgs& A, cudaStream_t st);
 cudaError_t launch_seqmc_resample(const SeqArgs& A, cudaStream_t st);
 cudaError_t launch_seqmc_store(const SeqArgs& A, cudaStream_t st);
+cudaError_t launch_seqmc_pack(const SeqArgs& A, cudaStream_t st);
 
 struct TempArgs {
   PopTasks T;

@@ -17,3 +17,13 @@ def test_row_sharded_matches_unsharded():
            "--master-port", "29611", os.path.join(ROOT, "tests", "multigpu_rowshard.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "ROWSHARD_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+def test_seqmc_population_sharded_over_two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29613", os.path.join(ROOT, "tests", "multigpu_seqmc.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "SEQMC_SHARDED_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
