@@ -49,6 +49,7 @@ extern "C" {
 #define MCMCGPU_MALA 1
 #define MCMCGPU_HMC 2
 #define MCMCGPU_HMCDA 3
+#define MCMCGPU_RAM 4          /* src/samplers/RAM.jl:24-36: scale, rate (robust adaptive Metropolis); d <= 8 fused, d <= 16 wave */
 
 /* engines */
 #define MCMCGPU_ENGINE_AUTO 0
@@ -69,8 +70,8 @@ typedef struct mcmcgpu_run mcmcgpu_run;
 typedef struct {
   int32_t kind;        /* MCMCGPU_RWM | MALA | HMC | HMCDA                                           */
   int32_t nleaps;      /* HMC.nLeaps   (HMC.jl:54)                                                   */
-  double scale;        /* RWM.scale (RWM.jl:25) | MALA.driftStep (MALA.jl:51) | HMC.leapStep (HMC.jl:55) */
-  double rate, len, shrinkage, t0, step; /* HMCDA fields HMCDA.jl:25-29                              */
+  double scale;        /* RWM.scale (RWM.jl:25) | MALA.driftStep (MALA.jl:51) | HMC.leapStep (HMC.jl:55) | RAM.scale (RAM.jl:25) */
+  double rate, len, shrinkage, t0, step; /* HMCDA fields HMCDA.jl:25-29; rate is also RAM.rate (RAM.jl:26) */
   int64_t max_leaps;   /* cap on HMCDA nLeaps = max(1, round(len/leapStep)) (HMCDA.jl:104); 0 = library default 1<<20 */
   int32_t tuner_on;    /* EmpMCTuner attached (samplers.jl:32-50); MALA/HMC only                     */
   int32_t adapt_step, max_step;

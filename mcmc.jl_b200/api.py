@@ -207,6 +207,19 @@ class RWM(_Sampler):
         return capi.sampler_cfg("RWM", scale=self.scale)
 
 
+class RAM(_Sampler):
+    """RAM.jl:24-36: RAM() = (1.0, 0.234); RAM(scale); RAM(scale, rate)"""
+    needs_gradient = False
+
+    def __init__(self, scale=1.0, rate=0.234):
+        assert scale > 0, "scale should be > 0"
+        assert 0.0 < rate < 1.0, f"target acceptance rate ({rate}) should be between 0 and 1"
+        self.scale, self.rate, self.tuner = float(scale), float(rate), None
+
+    def _cfg(self):
+        return capi.sampler_cfg("RAM", scale=self.scale, rate=self.rate)
+
+
 class MALA(_Sampler):
     """MALA.jl:50-62"""
 

@@ -79,6 +79,8 @@ struct mcmcgpu_run {
   int32_t *nleaps = nullptr, *status = nullptr;
   unsigned long long* n_evals = nullptr;
   // wave state
+  double *ram_S = nullptr, *ram_al = nullptr;
+  uint8_t* ram_pending = nullptr;
   double *q = nullptr, *part = nullptr, *red = nullptr, *cur_pars = nullptr, *cur_grad = nullptr, *cur_lt = nullptr,
          *mom = nullptr, *H0 = nullptr, *eps_cur = nullptr, *da_leapstep = nullptr, *da_dual = nullptr, *da_dualH = nullptr,
          *tn_step = nullptr;
@@ -360,6 +362,10 @@ static int check_cfg(const mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
       if (s->nleaps <= 0) return fail(MCMCGPU_E_ARG, "inner steps should be > 0");                                // HMC.jl:60
       if (!(s->scale > 0)) return fail(MCMCGPU_E_ARG, "inner steps scaling should be > 0");                       // HMC.jl:61
       break;
+    case MCMCGPU_RAM:                                                                                             // RAM.jl:29-30
+      if (!(s->scale > 0)) return fail(MCMCGPU_E_ARG, "scale should be > 0");
+      if (!(s->rate > 0 && s->rate < 1)) return fail(MCMCGPU_E_ARG, "target acceptance rate should be between 0 and 1");
+      break;
     case MCMCGPU_HMCDA:                                                                                           // HMCDA.jl:33-36
       if (!(s->rate > 0 && s->rate < 1)) return fail(MCMCGPU_E_ARG, "Target acceptance rate should be between 0 and 1");
       if (!(s->len > 0)) return fail(MCMCGPU_E_ARG, "len parameter of HMCDA sampler must be non-negative");
@@ -407,7 +413,8 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   if (engine == MCMCGPU_ENGINE_FUSED && !can_fuse) { delete R; return fail(MCMCGPU_E_ARG, "engine FUSED supports the closed-form families with d <= 8"); }
   if (engine != MCMCGPU_ENGINE_FUSED && engine != MCMCGPU_ENGINE_WAVE) { delete R; return fail(MCMCGPU_E_ARG, "unknown engine"); }
   R->engine = engine;
-  R->has_diag = (s->kind == MCMCGPU_HMCDA) || s->tuner_on;
+  R->has_diag = (s->kind == MCMCGPU_HMCDA) || (s->kind == MCMCGPU_RAM) || s->tuner_on;
+  if (s->kind == MCMCGPU_RAM && engine == MCMCGPU_ENGINE_WAVE && d > RAM_WAVE_MAX_D) { delete R; return fail(MCMCGPU_E_ARG, "RAM supports d <= 16"); }
 #define RCU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { std::string msg = std::string("CUDA: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__); mcmcgpu_run_destroy(R); return fail(MCMCGPU_E_CUDA, msg); } } while (0)
   // inputs
   if (r->init_per_chain) {
@@ -482,6 +489,11 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     RCU(R->alloc(&R->tn_acc, (size_t)Cp));
     RCU(R->alloc(&R->tn_prop, (size_t)Cp));
     RCU(R->alloc(&R->need_ll, (size_t)Cp));
+    if (s->kind == MCMCGPU_RAM) {
+      RCU(R->alloc(&R->ram_S, (size_t)(d * d * Cp)));
+      RCU(R->alloc(&R->ram_al, (size_t)Cp));
+      RCU(R->alloc(&R->ram_pending, (size_t)Cp));
+    }
   }
   RCU(cudaStreamSynchronize(st));
   *out = R;
@@ -550,15 +562,17 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     W.phase = R->phase; W.leap = R->leap; W.nleaps_cur = R->nleaps_cur; W.istep = R->istep; W.kept = R->kept;
     W.eps_cur = R->eps_cur; W.da_leapstep = R->da_leapstep; W.da_dual = R->da_dual; W.da_dualH = R->da_dualH;
     W.tn_step = R->tn_step; W.tn_nleaps = R->tn_nleaps; W.tn_acc = R->tn_acc; W.tn_prop = R->tn_prop;
+    W.ram_S = R->ram_S; W.ram_al = R->ram_al; W.ram_pending = R->ram_pending;
     W.need_ll = R->need_ll; W.status = R->status; W.remaining = R->remaining; W.n_evals = R->n_evals;
     W.init = R->init; W.scale = R->scale; W.inj_normals = R->inj_normals; W.inj_uniforms = R->inj_uniforms;
     W.samples = R->samples; W.grads = R->grads; W.accept = R->accept; W.logtarget = R->logtarget;
     W.eps = R->eps; W.nleaps = R->nleaps; W.final_eps = R->final_eps;
     const int kind = R->s.kind;
-    const bool need_grad = (kind != MCMCGPU_RWM);
+    const bool need_grad = (kind != MCMCGPU_RWM && kind != MCMCGPU_RAM);
+    const bool is_ram = (kind == MCMCGPU_RAM);
     // number of waves when it is known in advance; otherwise poll the device counter
     int64_t known = -1;
-    if (kind == MCMCGPU_RWM || kind == MCMCGPU_MALA) known = seg;
+    if (kind == MCMCGPU_RWM || kind == MCMCGPU_MALA || kind == MCMCGPU_RAM) known = seg;
     else if (kind == MCMCGPU_HMC && !R->s.tuner_on) known = seg * (int64_t)R->s.nleaps;
     bool first = false;
     if (!R->started) {
@@ -570,11 +584,13 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       if (known >= 0) known += 1;   // the wave that evaluates the initial point
       first = true;
       R->started = true;
+      if (is_ram) { CU(launch_ram(W, true, st)); launches++; }
     } else {
       W.resume = 1;                  // restart the paused chains: they draw and write their next pending point
       CU(launch_transition(W, st));
       W.resume = 0;
       launches++;
+      if (is_ram) { CU(launch_ram(W, false, st)); launches++; }
     }
     std::vector<cudaEvent_t> evs;
     for (;;) {
@@ -587,6 +603,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       if (c->time_eval) { CU(cudaEventRecord(a1, st)); evs.push_back(a0); evs.push_back(a1); }
       W.part = pp; W.nsplit = ns;
       CU(launch_transition(W, st));
+      if (is_ram) { CU(launch_ram(W, false, st)); launches++; }
       launches += 2 + (m->row_sharded ? 1 : 0);
       waves++;
       first = false;

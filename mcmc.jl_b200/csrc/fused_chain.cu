@@ -150,6 +150,78 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
       }
     }
     if (A.final_eps) A.final_eps[c] = S.tuner_on ? tune_step : S.scale;
+  } else if (S.kind == MCMCGPU_RAM) {
+    // RAM.jl:41-80 (Vihola 2012): proposal pars + S*rvec, then S = chol(S (I + eta (alpha - rate) r r'/|r|^2) S')'
+    double Sm[D][D], Am[D][D], Bm[D][D];
+#pragma unroll
+    for (int a = 0; a < D; a++)
+#pragma unroll
+      for (int b = 0; b < D; b++) Sm[a][b] = (a == b && a < d) ? A.scale[a] * S.scale : 0.0;   // :50,55
+    for (int64_t i = 1; i <= R.last; i++) {
+      double z[D], prop[D], pg[D];
+      draw_normals(i, z);                                                       // :59
+#pragma unroll
+      for (int a = 0; a < D; a++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int b = 0; b < D; b++) if (b < d) acc += Sm[a][b] * z[b];
+        prop[a] = pars[a] + acc;                                                // :60
+      }
+      double plt = Family<FAM, D>::evalallg(M, sh_series, d, prop, pg);         // :61
+      nev++;
+      double ratio = plt - lt;                                                  // :63
+      double tr = 0.0;
+#pragma unroll
+      for (int a = 0; a < D; a++) if (a < d) tr += Sm[a][a];                    // "scale" => trace(S)
+      bool acc = ratio > 0 || ratio > log(draw_uniform(i));                     // :64
+      if (acc) {
+        store(i, prop, plt, pg, false, true, tr, 0);
+#pragma unroll
+        for (int j = 0; j < D; j++) pars[j] = prop[j];
+        lt = plt;
+      } else {
+        store(i, pars, lt, pg, false, false, tr, 0);
+      }
+      double eta = (double)d * pow((double)i, -2.0 / 3.0);                      // :74
+      if (!(eta < 1.0)) eta = 1.0;
+      const double er = exp(ratio);
+      const double al = isnan(er) ? 0.0 : (er < 1.0 ? er : 1.0);               // min(1, exp(ratio)); NaN => 0 (documented)
+      double zz = 0.0;
+#pragma unroll
+      for (int a = 0; a < D; a++) if (a < d) zz += z[a] * z[a];
+#pragma unroll
+      for (int a = 0; a < D; a++)
+#pragma unroll
+        for (int b = 0; b < D; b++) Am[a][b] = ((a == b) ? 1.0 : 0.0) + (z[a] * z[b]) / zz * eta * (al - S.rate);   // :76
+#pragma unroll
+      for (int a = 0; a < D; a++)
+#pragma unroll
+        for (int b = 0; b < D; b++) {                                           // S * (I + SS)
+          double s2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) if (k < d) s2 += Sm[a][k] * Am[k][b];
+          Bm[a][b] = s2;
+        }
+#pragma unroll
+      for (int a = 0; a < D; a++)
+#pragma unroll
+        for (int b = 0; b < D; b++) {                                           // ... * S'   (:77)
+          double s2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; k++) if (k < d) s2 += Bm[a][k] * Sm[b][k];
+          Am[a][b] = s2;
+        }
+#pragma unroll
+      for (int a = 0; a < D; a++)                                               // S = chol(SS)' (:78), lower factor row by row
+#pragma unroll
+        for (int b = 0; b < D; b++) {
+          if (b > a || a >= d) { Sm[a][b] = 0.0; continue; }
+          double s2 = Am[a][b];
+#pragma unroll
+          for (int k = 0; k < D; k++) if (k < b) s2 -= Sm[a][k] * Sm[b][k];
+          Sm[a][b] = (a == b) ? sqrt(s2) : s2 / Sm[b][b];
+        }
+    }
   } else {
     // HMC.jl:106-175 and HMCDA.jl:72-143 share HMCSample / leapfrog (HMC.jl:81-102)
     const bool da = (S.kind == MCMCGPU_HMCDA);

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
     W.cur_lt[c] = lt_q;
     for (int64_t j = 0; j < d; j++) {
       W.cur_pars[j * Cp + c] = q[j * Cp + c];
-      if (kind != MCMCGPU_RWM) W.cur_grad[j * Cp + c] = fin_grad(F, M, q, part, ns, Cp, c, j);
+      if (kind != MCMCGPU_RWM && kind != MCMCGPU_RAM) W.cur_grad[j * Cp + c] = fin_grad(F, M, q, part, ns, Cp, c, j);
     }
     if (kind == MCMCGPU_HMCDA && !W.restore_da) {
       // HMCDA.jl:90-94; initializeHMCDAStep (HMCDA.jl:51-69) always returns 1.0 (state0.H is NaN, HMC.jl:88)
@@ -148,14 +148,22 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
     i = W.step0 + 1;
     begin = true;
   } else if (ph == PH_RWM) {
-    // RWM.jl:62-70
+    // RWM.jl:62-70 (and RAM.jl:63-71, the same Metropolis test)
     double ratio = lt_q - W.cur_lt[c];
     bool acc = ratio > 0 || ratio > log(uniform(i));
     if (acc) {
       for (int64_t j = 0; j < d; j++) W.cur_pars[j * Cp + c] = q[j * Cp + c];
       W.cur_lt[c] = lt_q;
     }
-    store(i, false, acc, CUDART_NAN, 0);
+    double diag = CUDART_NAN;
+    if (kind == MCMCGPU_RAM) {
+      diag = 0.0;
+      for (int64_t j = 0; j < d; j++) diag += W.ram_S[(j * d + j) * Cp + c];     // "scale" => trace(S) (RAM.jl:65,69)
+      const double er = exp(ratio);
+      W.ram_al[c] = isnan(er) ? 0.0 : (er < 1.0 ? er : 1.0);                     // min(1, exp(ratio)) (RAM.jl:76); NaN => 0
+      W.ram_pending[c] = 1;
+    }
+    store(i, false, acc, diag, 0);
     i++; begin = true;
   } else if (ph == PH_MALA) {
     // MALA.jl:103-113
@@ -272,6 +280,11 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       atomicAdd(W.n_evals, nev);
       return;
     }
+    if (kind == MCMCGPU_RAM) {   // the proposal needs the updated factor: ram_kernel makes it
+      W.phase[c] = PH_RAM_BEGIN;
+      atomicAdd(W.n_evals, nev);
+      return;
+    }
     // ---- start step i: draw and write the next pending point ----
     double eps = S.scale; int nl = 0;
     if (kind == MCMCGPU_HMCDA) {
@@ -334,6 +347,90 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
 cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st) {
   int blocks = (int)((W.R.C + 127) / 128);
   transition_kernel<<<blocks, 128, 0, st>>>(W);
+  return cudaGetLastError();
+}
+
+
+// ---- RAM (robust adaptive Metropolis) for the wave engine ----------------------------------------------
+__global__ void __launch_bounds__(128) ram_kernel(const WaveArgs W, int init) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const RunnerDev& R = W.R;
+  if (c >= R.C) return;
+  const int d = (int)W.M.d;
+  const int64_t Cp = R.Cp;
+  constexpr int MD = RAM_WAVE_MAX_D;
+  if (init) {                                                   // RAM.jl:50,55: S = diag(model.scale * sampler.scale)
+    for (int a = 0; a < d; a++)
+      for (int b = 0; b < d; b++) W.ram_S[((int64_t)a * d + b) * Cp + c] = (a == b) ? W.scale[a] * W.S.scale : 0.0;
+    W.ram_pending[c] = 0;
+    return;
+  }
+  const int ph = W.phase[c];
+  if (!W.ram_pending[c] && ph != PH_RAM_BEGIN) return;
+  double Sm[MD * MD], Am[MD * MD], Bm[MD * MD], z[MD];
+  for (int a = 0; a < d; a++)
+    for (int b = 0; b < d; b++) Sm[a * d + b] = W.ram_S[((int64_t)a * d + b) * Cp + c];
+  if (W.ram_pending[c]) {                                       // RAM.jl:73-78 for the step just decided
+    const int64_t i = W.istep[c] - 1;
+    for (int a = 0; a < d; a++) z[a] = W.mom[(int64_t)a * Cp + c];
+    double eta = (double)d * pow((double)i, -2.0 / 3.0);
+    if (!(eta < 1.0)) eta = 1.0;
+    const double al = W.ram_al[c];
+    double zz = 0.0;
+    for (int a = 0; a < d; a++) zz += z[a] * z[a];
+    for (int a = 0; a < d; a++)
+      for (int b = 0; b < d; b++) Am[a * d + b] = ((a == b) ? 1.0 : 0.0) + (z[a] * z[b]) / zz * eta * (al - W.S.rate);
+    for (int a = 0; a < d; a++)
+      for (int b = 0; b < d; b++) {
+        double s2 = 0.0;
+        for (int k = 0; k < d; k++) s2 += Sm[a * d + k] * Am[k * d + b];
+        Bm[a * d + b] = s2;
+      }
+    for (int a = 0; a < d; a++)
+      for (int b = 0; b < d; b++) {
+        double s2 = 0.0;
+        for (int k = 0; k < d; k++) s2 += Bm[a * d + k] * Sm[b * d + k];
+        Am[a * d + b] = s2;
+      }
+    for (int a = 0; a < d; a++)
+      for (int b = 0; b < d; b++) {
+        if (b > a) { Sm[a * d + b] = 0.0; continue; }
+        double s2 = Am[a * d + b];
+        for (int k = 0; k < b; k++) s2 -= Sm[a * d + k] * Sm[b * d + k];
+        Sm[a * d + b] = (a == b) ? sqrt(s2) : s2 / Sm[b * d + b];
+      }
+    for (int a = 0; a < d; a++)
+      for (int b = 0; b < d; b++) W.ram_S[((int64_t)a * d + b) * Cp + c] = Sm[a * d + b];
+    W.ram_pending[c] = 0;
+  }
+  if (ph != PH_RAM_BEGIN) return;
+  // RAM.jl:59-60: rvec = randn(d); proposedPars = pars + S * rvec
+  const int64_t i = W.istep[c];
+  const uint64_t gchain = (uint64_t)(R.chain_offset + c);
+  for (int jb = 0; jb < d; jb += 2) {
+    double z0, z1 = 0.0;
+    if (W.inj_normals) {
+      z0 = W.inj_normals[(i * d + jb) * Cp + c];
+      if (jb + 1 < d) z1 = W.inj_normals[(i * d + jb + 1) * Cp + c];
+    } else {
+      philox_normal_pair(R.seed, gchain, (uint32_t)i, (uint32_t)(jb >> 1), z0, z1);
+    }
+    z[jb] = z0;
+    if (jb + 1 < d) z[jb + 1] = z1;
+  }
+  for (int a = 0; a < d; a++) {
+    double acc = 0.0;
+    for (int b = 0; b < d; b++) acc += Sm[a * d + b] * z[b];
+    W.q[(int64_t)a * Cp + c] = W.cur_pars[(int64_t)a * Cp + c] + acc;
+    W.mom[(int64_t)a * Cp + c] = z[a];
+  }
+  W.need_ll[c] = 1;
+  W.eps_cur[c] = W.S.scale;
+  W.phase[c] = PH_RWM;
+}
+
+cudaError_t launch_ram(const WaveArgs& W, bool init, cudaStream_t st) {
+  ram_kernel<<<(unsigned)((W.R.C + 127) / 128), 128, 0, st>>>(W, init ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -7,6 +7,7 @@ constexpr int PH_INIT = 0;   // q = init has been evaluated
 constexpr int PH_RWM = 1;    // q = RWM proposal has been evaluated
 constexpr int PH_MALA = 2;   // q = MALA proposal has been evaluated
 constexpr int PH_LEAP = 3;   // q = position after a leapfrog position update has been evaluated
+constexpr int PH_RAM_BEGIN = 4;  // RAM: the next proposal is made by ram_kernel (after the factor update)
 constexpr int PH_PAUSE = 98;  // reached the step limit of this execute call; resumes at the next one
 constexpr int PH_DONE = 99;
 
@@ -29,6 +30,9 @@ struct WaveArgs {
   double *eps_cur;
   double *da_leapstep, *da_dual, *da_dualH;
   double *tn_step; int64_t *tn_nleaps, *tn_acc, *tn_prop;
+  double* ram_S;               // RAM: [d*d][Cp] lower-triangular proposal factor (row-major index a*d+b)
+  double* ram_al;              // RAM: min(1, exp(ratio)) of the step just decided
+  uint8_t* ram_pending;        // RAM: factor update pending for that step
   uint8_t* need_ll;
   int32_t* status;
   int32_t* remaining;
@@ -41,6 +45,8 @@ struct WaveArgs {
 };
 
 cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st);
+constexpr int RAM_WAVE_MAX_D = 16;
+cudaError_t launch_ram(const WaveArgs& W, bool init, cudaStream_t st);   // RAM.jl:50-60,73-78 for the wave engine
 // closed-form families through the wave engine: writes part[0][(d+2)][Cp] directly (final lt / grad)
 cudaError_t launch_eval_closed(const ModelDev& M, const double* q, double* part, int64_t C, int64_t Cp,
                                const int32_t* phase, const int32_t* remaining, cudaStream_t st);

@@ -493,6 +493,65 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
       }
     }
     hs_free(&st0); hs_free(&st);
+  } else if (s->kind == ORC_RAM) {
+    /* RAM.jl:41-80 (Vihola 2012).  diag_eps carries the "scale" diagnostic trace(S) of the kept step (:65,69). */
+    double* pars = (double*)malloc(sizeof(double) * (size_t)d);
+    double* prop = (double*)malloc(sizeof(double) * (size_t)d);
+    double* S = (double*)calloc((size_t)(d * d), sizeof(double));     /* row-major S[a*d+b] */
+    double* A = (double*)malloc(sizeof(double) * (size_t)(d * d));
+    double* Bm = (double*)malloc(sizeof(double) * (size_t)(d * d));
+    for (int64_t j = 0; j < d; j++) S[j * d + j] = scale[j] * s->scale;       /* :50,55 */
+    memcpy(pars, init, sizeof(double) * (size_t)d);
+    double lt = orc_eval(m, pars);
+    if (!isfinite(lt)) rc = -1;                                               /* :53 */
+    for (int64_t i = 1; rc == 0 && i <= len; i++) {
+      const double* z = normals + i * d;                                      /* :59 rvec */
+      for (int64_t a = 0; a < d; a++) {                                       /* :60 pars + S * rvec */
+        double acc = 0.0;
+        for (int64_t b = 0; b < d; b++) acc += S[a * d + b] * z[b];
+        prop[a] = pars[a] + acc;
+      }
+      double plt = orc_eval(m, prop);                                         /* :61 */
+      double ratio = plt - lt;                                                /* :63 */
+      double tr = 0.0;
+      for (int64_t j = 0; j < d; j++) tr += S[j * d + j];                     /* trace(S) */
+      if (ratio > 0 || ratio > log(uniforms[i])) {                            /* :64 */
+        STORE(prop, plt, (const double*)NULL, 1, tr, 0);
+        memcpy(pars, prop, sizeof(double) * (size_t)d); lt = plt;
+      } else {
+        STORE(pars, lt, (const double*)NULL, 0, tr, 0);
+      }
+      /* scale tuning :73-78 */
+      double eta = (double)d * pow((double)i, -2.0 / 3.0);
+      if (!(eta < 1.0)) eta = 1.0;                                            /* min(1, .) */
+      double er = exp(ratio);
+      double al = isnan(er) ? 0.0 : (er < 1.0 ? er : 1.0);                    /* min(1, exp(ratio)); NaN => 0 (documented) */
+      double zz = dotp(z, z, d);
+      for (int64_t a = 0; a < d; a++)                                         /* I + (r r')/dot(r,r) * eta * (al - rate) */
+        for (int64_t b = 0; b < d; b++)
+          A[a * d + b] = ((a == b) ? 1.0 : 0.0) + (z[a] * z[b]) / zz * eta * (al - s->rate);
+      for (int64_t a = 0; a < d; a++)                                         /* Bm = S * A */
+        for (int64_t b = 0; b < d; b++) {
+          double acc = 0.0;
+          for (int64_t k = 0; k < d; k++) acc += S[a * d + k] * A[k * d + b];
+          Bm[a * d + b] = acc;
+        }
+      for (int64_t a = 0; a < d; a++)                                         /* A = Bm * S' */
+        for (int64_t b = 0; b < d; b++) {
+          double acc = 0.0;
+          for (int64_t k = 0; k < d; k++) acc += Bm[a * d + k] * S[b * d + k];
+          A[a * d + b] = acc;
+        }
+      /* S = chol(SS)' : lower Cholesky factor, row by row (Cholesky-Banachiewicz) */
+      for (int64_t a = 0; a < d; a++)
+        for (int64_t b = 0; b < d; b++) {
+          if (b > a) { S[a * d + b] = 0.0; continue; }
+          double acc = A[a * d + b];
+          for (int64_t k = 0; k < b; k++) acc -= S[a * d + k] * S[b * d + k];
+          S[a * d + b] = (a == b) ? sqrt(acc) : acc / S[b * d + b];
+        }
+    }
+    free(pars); free(prop); free(S); free(A); free(Bm);
   } else {
     rc = -2;
   }

@@ -43,7 +43,7 @@ typedef struct {
 } orc_model;
 
 /* Samplers. */
-enum { ORC_RWM = 0, ORC_MALA = 1, ORC_HMC = 2, ORC_HMCDA = 3 };
+enum { ORC_RWM = 0, ORC_MALA = 1, ORC_HMC = 2, ORC_HMCDA = 3, ORC_RAM = 4 /* src/samplers/RAM.jl: scale, rate */ };
 
 typedef struct {
   int32_t kind;

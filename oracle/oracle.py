@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "libmcmc_oracle.so")
 
 FAM = dict(normal_fn=0, normal_dsl=1, linear=2, logistic=3, probit=4, ou=5, abs_normal=6)
-KIND = dict(RWM=0, MALA=1, HMC=2, HMCDA=3)
+KIND = dict(RWM=0, MALA=1, HMC=2, HMCDA=3, RAM=4)
 
 
 def build(force=False):

@@ -470,3 +470,41 @@ def test_run_chains_single_call(O, capi, ctx):
         assert np.array_equal(ref["grads"], grads[c]) and np.array_equal(ref["logtarget"], lt[c])
     assert info.n_launches == 1 and info.n_grad_evals == Cn * (1 + rngt[2] * 10)
     dm.close()
+
+
+@pytest.mark.parametrize("engine", ["fused", "wave"])
+@pytest.mark.parametrize("fam,d,hy", [("normal_fn", 3, ()), ("normal_dsl", 6, (0.5, 2.0)), ("normal_fn", 1, ())])
+def test_ram_closed_form(O, capi, ctx, engine, fam, d, hy):
+    """RAM.jl:41-80: the factor update S = chol(S (I + eta (alpha - rate) r r'/|r|^2) S')' in the reference's
+    operation order; pow() differs in the last bit between CUDA and glibc, hence a tolerance instead of bit equality"""
+    C, rngt = 40, (51, 1, 400)
+    out, diag, refs, _ = _run_both(O, capi, ctx, fam, d, None, None, hy, "RAM", dict(scale=1.0, rate=0.234), rngt, C, np.ones(d), engine)
+    for c in range(C):
+        assert np.array_equal(refs[c]["accept"], out["accept"][c])
+        assert np.allclose(refs[c]["samples"], out["samples"][c], rtol=1e-9, atol=1e-12)
+        assert np.allclose(diag[0][c], refs[c]["eps"], rtol=1e-9)           # "scale" diagnostic = trace(S)
+        assert np.all(np.isnan(out["grads"][c]))
+    acc = out["accept"][:, 200:].mean()
+    assert 0.15 < acc < 0.40                                                 # coerced towards the target rate 0.234
+
+
+def test_ram_examples(O, capi, ctx):
+    """examples/linear_regression.jl:26 `RAM(1., 0.3)` (d = 10, wave engine) and examples/ornstein.jl:33 `RAM()` with m.scale"""
+    X, y, hy, _ = make_regression("linear", 1000, 10, 3)
+    out, diag, refs, _ = _run_both(O, capi, ctx, "linear", 10, X, y, hy, "RAM", dict(scale=1.0, rate=0.3), (101, 1, 400), 24, np.zeros(10), "wave")
+    for c in range(24):
+        assert np.array_equal(refs[c]["accept"], out["accept"][c])
+        assert np.allclose(refs[c]["samples"], out["samples"][c], rtol=1e-8, atol=1e-11)
+        assert np.allclose(diag[0][c], refs[c]["eps"], rtol=1e-8)
+    x = ou_series(300, 4)
+    sc = np.array([1000.0, 1.0, 10.0])
+    for engine in ("fused", "wave"):
+        out, diag, refs, _ = _run_both(O, capi, ctx, "ou", 3, None, x, (100.0, 2.0, 20.0), "RAM", dict(scale=1.0, rate=0.234), (1, 1, 200), 16,
+                                       np.array([20.0, 0.1, 10.0]), engine, scale=sc)
+        for c in range(16):
+            assert np.array_equal(refs[c]["accept"], out["accept"][c])
+            assert np.allclose(refs[c]["samples"], out["samples"][c], rtol=1e-8, atol=0)
+    import mcmc_jl_b200 as mj
+    m = mj.model("linear", X=X, Y=y, vars=np.zeros(10))
+    ch = mj.run(m * mj.RAM(1.0, 0.3) * mj.SerialMC(1000, 5000))
+    assert 20 < mj.acceptance(ch) < 40                                       # linear_regression.jl:27 "~ 29.7%"
