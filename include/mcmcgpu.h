@@ -167,6 +167,11 @@ int32_t mcmcgpu_run_fetch_diag(mcmcgpu_run* run, double* out_eps, int64_t* out_n
 int32_t mcmcgpu_run_stats(mcmcgpu_run* run, int32_t vtype, int64_t maxlag, int64_t batchlen, double* out_mean,
                           double* out_var_iid, double* out_var, double* out_ess, double* out_actime,
                           double* out_accept_rate);
+/* zero-variance control variates on the device-resident draws and gradients (needs store_grad):
+ * linearZv (order 1) / quadraticZv (order 2) of src/stats/zv.jl:8-66 for every chain.
+ * out_zv d x S x nchains (may be NULL), out_a k x d x nchains with k = d (order 1) or d(d+3)/2 (order 2),
+ * element (p, i, c) at out_a[(c*k + p)*d + i]  (row-major k x d per chain, as the reference's `a`). */
+int32_t mcmcgpu_run_zv(mcmcgpu_run* run, int32_t order, double* out_zv, double* out_a);
 int32_t mcmcgpu_run_destroy(mcmcgpu_run* run);
 
 /* src/stats from host draws: samples d x S x C (the layout mcmcgpu_run_chains fills) */
@@ -201,6 +206,10 @@ int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* ctx, int32_t family, int64_t d, int3
                                int64_t nrep, const double* inits, uint64_t seed, const double* inj_normals,
                                const double* inj_uniforms, const double* inj_pick, const double* inj_swap,
                                double* out_samples, int32_t* out_at, mcmcgpu_run_info* info);
+
+/* zero-variance control variates from host draws / gradients (layouts as mcmcgpu_run_chains fills them) */
+int32_t mcmcgpu_zv(mcmcgpu_ctx* ctx, const double* samples, const double* grads, int64_t S, int64_t d, int64_t C,
+                   int32_t order, double* out_zv, double* out_a);
 
 /* the engine's own draws, for draw-matched replay through another implementation:
  * normals d x (last+1) x nchains and uniforms (last+1) x nchains exactly as the samplers consume them */

@@ -53,7 +53,7 @@ EXPORTS = [
     "mcmcgpu_model_destroy", "mcmcgpu_logtarget_grad", "mcmcgpu_run_chains", "mcmcgpu_run_create",
     "mcmcgpu_run_execute", "mcmcgpu_run_execute_steps", "mcmcgpu_run_set_state", "mcmcgpu_run_get_state",
     "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
-    "mcmcgpu_run_destroy", "mcmcgpu_stats", "mcmcgpu_philox_draws", "mcmcgpu_run_seqmc", "mcmcgpu_run_serialtemp",
+    "mcmcgpu_run_destroy", "mcmcgpu_stats", "mcmcgpu_philox_draws", "mcmcgpu_run_seqmc", "mcmcgpu_run_serialtemp", "mcmcgpu_run_zv", "mcmcgpu_zv",
 ]
 
 _lib = None
@@ -102,6 +102,8 @@ def lib():
         L.mcmcgpu_run_serialtemp.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(SamplerCfg), C.c_int64, C.c_int64,
                                              C.c_int64, C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int32),
                                              C.POINTER(RunInfo)]
+        L.mcmcgpu_run_zv.argtypes = [vp, C.c_int32, dp, dp]
+        L.mcmcgpu_zv.argtypes = [vp, dp, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, dp, dp]
         L.mcmcgpu_philox_draws.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, dp, dp]
         for n in EXPORTS:
             if n not in ("mcmcgpu_last_error",):
@@ -161,6 +163,16 @@ class Context:
         check(lib().mcmcgpu_stats(self.h, dptr(s), S, d, Cn, VTYPE[vtype], maxlag, batchlen, dptr(outs["mean"]),
                                   dptr(outs["var_iid"]), dptr(outs["var"]), dptr(outs["ess"]), dptr(outs["actime"])))
         return {k: v for k, v in outs.items() if v is not None}
+
+    def zv(self, samples, grads, order=1, want_chain=True):
+        """samples, grads: (C, S, d).  Returns (zvchain (C, S, d) or None, a (C, k, d)) -- linearZv / quadraticZv per chain."""
+        s, g = f64(samples), f64(grads)
+        Cn, S, d = s.shape
+        k = d if order == 1 else d * (d + 3) // 2
+        zv = np.empty((Cn, S, d)) if want_chain else None
+        a = np.empty((Cn, k, d))
+        check(lib().mcmcgpu_zv(self.h, dptr(s), dptr(g), S, d, Cn, order, dptr(zv), dptr(a)))
+        return zv, a
 
     def _tasks(self, hypers, samplers):
         hy = np.zeros((len(samplers), 4))
@@ -343,6 +355,13 @@ class DeviceRun:
                                       dptr(outs["var"]), dptr(outs["ess"]), dptr(outs["actime"]), dptr(rate)))
         outs["accept_rate"] = rate
         return {k: v for k, v in outs.items() if v is not None}
+
+    def zv(self, order=1, want_chain=True):
+        k = self.d if order == 1 else self.d * (self.d + 3) // 2
+        zv = np.empty((self.C, self.S, self.d)) if want_chain else None
+        a = np.empty((self.C, k, self.d))
+        check(lib().mcmcgpu_run_zv(self.h, order, dptr(zv), dptr(a)))
+        return zv, a
 
     def close(self):
         if self.h:

@@ -703,6 +703,27 @@ def acceptance(c, lags=None, reject=False):                                # sum
     return out if isinstance(c, MCMCChainBatch) else float(out[0])
 
 
+def linearZv(c, grad=None):
+    """zv.jl:8-29: (zvChain, a).  c: MCMCChain, MCMCChainBatch, or an (S, d) array with grad an (S, d) array."""
+    return _zv(c, grad, 1)
+
+
+def quadraticZv(c, grad=None):
+    """zv.jl:32-66"""
+    return _zv(c, grad, 2)
+
+
+def _zv(c, grad, order):
+    if isinstance(c, MCMCChainBatch):
+        return c._run.zv(order)
+    if isinstance(c, MCMCChain):
+        x, g = c._s, c.gradients.values
+    else:
+        x, g = np.asarray(c, dtype=np.float64), np.asarray(grad, dtype=np.float64)
+    zv, a = default_context().zv(x[None], g[None], order)
+    return zv[0], a[0]
+
+
 def describe(c, io=None):
     """summary.jl:24-55 for one chain: Min / Mean / Max / MC Error / ESS / AC Time per parameter."""
     import sys

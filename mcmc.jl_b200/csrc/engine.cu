@@ -14,6 +14,7 @@
 #include "population.h"
 #include "stats.h"
 #include "transition.h"
+#include "zv.h"
 
 using namespace mg;
 
@@ -841,6 +842,61 @@ int32_t mcmcgpu_stats(mcmcgpu_ctx* c, const double* samples, int64_t S, int64_t 
   cudaStreamSynchronize(st);
   cudaFree(tmp); cudaFree(dev);
   return rc;
+}
+
+static int zv_common(mcmcgpu_ctx* c, const double* samples, const double* grads, int64_t S, int64_t d, int64_t C, int64_t Cp,
+                     int32_t order, double* out_zv, double* out_a) {
+  cudaStream_t st = c->stream;
+  if (!out_a) return fail(MCMCGPU_E_ARG, "out_a is NULL");
+  if (S < 2) return fail(MCMCGPU_E_ARG, "need at least 2 kept draws");
+  if (!zv_supported(d, order)) return fail(MCMCGPU_E_ARG, "ZV: order must be 1 or 2 and the k x (k+d) covariance must fit in shared memory (order 1: d <= 110; order 2: d <= 13)");
+  const int64_t k = zv_features(d, order);
+  DevBufs B;
+  double *zv = nullptr, *a = nullptr, *tmp = nullptr;
+  int32_t* status = nullptr;
+  if (out_zv) CU(B.get(&zv, (size_t)(S * d * Cp), st, false));
+  CU(B.get(&a, (size_t)(k * d * Cp), st));
+  CU(B.get(&status, (size_t)Cp, st));
+  CU(launch_zv(samples, grads, S, d, C, Cp, order, zv, a, status, st));
+  CU(B.get(&tmp, (size_t)(C * k * d), st, false));
+  CU(transpose_to_chain_major(a, tmp, 0, C, k * d, Cp, st));
+  CU(cudaMemcpyAsync(out_a, tmp, sizeof(double) * (size_t)(C * k * d), cudaMemcpyDeviceToHost, st));
+  if (out_zv) {
+    double* t2 = nullptr;
+    CU(B.get(&t2, (size_t)(C * S * d), st, false));
+    CU(transpose_to_chain_major(zv, t2, 0, C, S * d, Cp, st));
+    CU(cudaMemcpyAsync(out_zv, t2, sizeof(double) * (size_t)(C * S * d), cudaMemcpyDeviceToHost, st));
+  }
+  std::vector<int32_t> stt((size_t)C);
+  CU(cudaMemcpyAsync(stt.data(), status, sizeof(int32_t) * (size_t)C, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int32_t v : stt) if (v) return fail(MCMCGPU_E_ARG, "ZV: singular feature covariance (SingularException in the reference's inv)");
+  return MCMCGPU_OK;
+}
+
+int32_t mcmcgpu_run_zv(mcmcgpu_run* R, int32_t order, double* out_zv, double* out_a) {
+  if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
+  if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
+  if (!R->grads) return fail(MCMCGPU_E_STATE, "ZV needs the stored gradients (store_grad = 1)");
+  CU(cudaSetDevice(R->m->ctx->device));
+  return zv_common(R->m->ctx, R->samples, R->grads, R->S, R->d, R->C, R->Cp, order, out_zv, out_a);
+}
+
+int32_t mcmcgpu_zv(mcmcgpu_ctx* c, const double* samples, const double* grads, int64_t S, int64_t d, int64_t C, int32_t order,
+                   double* out_zv, double* out_a) {
+  if (!c || !samples || !grads || S < 1 || d < 1 || C < 1) return fail(MCMCGPU_E_ARG, "bad arguments");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int64_t Cp = round_up(C, K1_CHAINS), K = S * d;
+  DevBufs B;
+  double *tmp = nullptr, *ds = nullptr, *dg = nullptr;
+  CU(B.get(&tmp, (size_t)(C * K), st, false));
+  CU(B.get(&ds, (size_t)(K * Cp), st)); CU(B.get(&dg, (size_t)(K * Cp), st));
+  CU(cudaMemcpyAsync(tmp, samples, sizeof(double) * (size_t)(C * K), cudaMemcpyHostToDevice, st));
+  CU(transpose_to_chain_minor(tmp, ds, C, K, Cp, st));
+  CU(cudaMemcpyAsync(tmp, grads, sizeof(double) * (size_t)(C * K), cudaMemcpyHostToDevice, st));
+  CU(transpose_to_chain_minor(tmp, dg, C, K, Cp, st));
+  return zv_common(c, ds, dg, S, d, C, Cp, order, out_zv, out_a);
 }
 
 int32_t mcmcgpu_run_chains(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r, const double* init,

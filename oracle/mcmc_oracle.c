@@ -789,6 +789,71 @@ static double geyer(const double* x, int64_t n, int64_t maxlag, int monotone) {
 double orc_mcvar_imse(const double* x, int64_t n, int64_t maxlag) { return geyer(x, n, maxlag, 1); }
 double orc_mcvar_ipse(const double* x, int64_t n, int64_t maxlag) { return geyer(x, n, maxlag, 0); }
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* zero-variance control variates (src/stats/zv.jl)                                            */
+/* ------------------------------------------------------------------------------------------ */
+static double zv_feature(int64_t p, int64_t d, const double* x, const double* g) {
+  /* zv.jl:16,48-56: z = -grad/2; zQuadratic = [z, 2*z.*x - 1, x_i*z_j + x_j*z_i (i<j)] */
+  if (p < d) return (-g[p]) / 2.0;
+  if (p < 2 * d) { int64_t j = p - d; return (2.0 * ((-g[j]) / 2.0)) * x[j] - 1.0; }
+  int64_t l = p - 2 * d, i = 0;
+  while (l >= d - 1 - i) { l -= d - 1 - i; i++; }
+  int64_t j = i + 1 + l;
+  return x[i] * ((-g[j]) / 2.0) + x[j] * ((-g[i]) / 2.0);
+}
+
+int32_t orc_zv(const double* x, const double* grad, int64_t S, int64_t d, int32_t order, double* zv, double* a) {
+  if (S < 2 || d < 1 || (order != 1 && order != 2)) return -2;
+  const int64_t k = (order == 1) ? d : d * (d + 3) / 2, w = k + d;
+  double* mean = (double*)calloc((size_t)w, sizeof(double));
+  double* M = (double*)calloc((size_t)(k * w), sizeof(double));
+  /* column means of [features x] */
+  for (int64_t p = 0; p < w; p++) {
+    double s = 0.0;
+    for (int64_t t = 0; t < S; t++) s += (p < k) ? zv_feature(p, d, x + t * d, grad + t * d) : x[t * d + (p - k)];
+    mean[p] = s / (double)S;
+  }
+  /* cov([features x_i]) (zv.jl:19,58): rows = features, columns = features then the d parameters */
+  for (int64_t p = 0; p < k; p++)
+    for (int64_t q = 0; q < w; q++) {
+      double s = 0.0;
+      for (int64_t t = 0; t < S; t++) {
+        double fp = zv_feature(p, d, x + t * d, grad + t * d) - mean[p];
+        double fq = ((q < k) ? zv_feature(q, d, x + t * d, grad + t * d) : x[t * d + (q - k)]) - mean[q];
+        s += fp * fq;
+      }
+      M[p * w + q] = s / (double)(S - 1);
+    }
+  /* Gauss-Jordan with partial pivoting on [C | Sigma] -> [I | inv(C) Sigma] (zv.jl:20-22,59-61) */
+  int32_t rc = 0;
+  for (int64_t c = 0; c < k && rc == 0; c++) {
+    int64_t piv = c; double best = fabs(M[c * w + c]);
+    for (int64_t r = c + 1; r < k; r++) if (fabs(M[r * w + c]) > best) { best = fabs(M[r * w + c]); piv = r; }
+    if (!(best > 0.0)) { rc = -3; break; }
+    if (piv != c) for (int64_t q = 0; q < w; q++) { double tmp = M[c * w + q]; M[c * w + q] = M[piv * w + q]; M[piv * w + q] = tmp; }
+    double pv = M[c * w + c];
+    for (int64_t q = 0; q < w; q++) M[c * w + q] = M[c * w + q] / pv;
+    for (int64_t r = 0; r < k; r++) {
+      if (r == c) continue;
+      double f = M[r * w + c];
+      for (int64_t q = 0; q < w; q++) M[r * w + q] = M[r * w + q] - f * M[c * w + q];
+    }
+  }
+  if (rc == 0) {
+    for (int64_t p = 0; p < k; p++) for (int64_t i = 0; i < d; i++) a[p * d + i] = -M[p * w + k + i];   /* a = -precision*sigma */
+    if (zv)                                                                                              /* zv.jl:25,63 */
+      for (int64_t t = 0; t < S; t++)
+        for (int64_t i = 0; i < d; i++) {
+          double s = 0.0;
+          for (int64_t p = 0; p < k; p++) s += zv_feature(p, d, x + t * d, grad + t * d) * a[p * d + i];
+          zv[t * d + i] = x[t * d + i] + s;
+        }
+  }
+  free(mean); free(M);
+  return rc;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3")    */
 /* ------------------------------------------------------------------------------------------ */

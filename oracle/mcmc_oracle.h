@@ -117,6 +117,14 @@ double orc_mcvar_imse(const double* x, int64_t n, int64_t maxlag); /* var.jl:45-
 double orc_mcvar_ipse(const double* x, int64_t n, int64_t maxlag); /* var.jl:95-116   */
 void orc_acov(const double* x, int64_t n, int64_t maxlag, double* acv); /* StatsBase.acf(x, 0:maxlag, correlation=false) */
 
+/* ---- zero-variance control variates (src/stats/zv.jl:8-66; Mira, Solgi, Imparato 2013) ----
+ * x, grad: S x d row-major (one chain).  order 1: linearZv (k = d features z = -grad/2); order 2: quadraticZv
+ * (k = d(d+3)/2 features: z, 2 z.*x - 1, x_i z_j + x_j z_i for i < j).  Outputs: zv S x d, a k x d (row-major).
+ * a[:, i] = -inv(cov(features)) * cov(features, x_i), computed as the Gauss-Jordan solution of [C | Sigma]
+ * with partial pivoting (the reference calls LAPACK inv; same value up to conditioning).  returns 0, -2 bad args,
+ * -3 singular covariance. */
+int32_t orc_zv(const double* x, const double* grad, int64_t S, int64_t d, int32_t order, double* zv, double* a);
+
 /* ---- Philox4x32-10 (Random123; Salmon et al. SC'11) and the draw conventions of the engine ---- */
 void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 /* engine conventions: key = (seed lo, seed hi); ctr = (chain lo, chain hi, step, block);

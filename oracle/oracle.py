@@ -235,6 +235,20 @@ def acov(x, maxlag):
     return out
 
 
+def zv(x, grad, order=1):
+    """x, grad: (S, d).  Returns (zvchain (S, d), a (k, d)) like linearZv / quadraticZv (zv.jl:8-66)."""
+    x = np.ascontiguousarray(x, dtype=np.float64); g = np.ascontiguousarray(grad, dtype=np.float64)
+    S, d = x.shape
+    k = d if order == 1 else d * (d + 3) // 2
+    out, a = np.empty((S, d)), np.empty((k, d))
+    L = lib()
+    L.orc_zv.restype = C.c_int32
+    rc = L.orc_zv(_dp(x), _dp(g), C.c_int64(S), C.c_int64(d), C.c_int32(order), _dp(out), _dp(a))
+    if rc != 0:
+        raise RuntimeError(f"orc_zv rc={rc}")
+    return out, a
+
+
 def philox(ctr, key):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)

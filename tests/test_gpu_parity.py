@@ -508,3 +508,39 @@ def test_ram_examples(O, capi, ctx):
     m = mj.model("linear", X=X, Y=y, vars=np.zeros(10))
     ch = mj.run(m * mj.RAM(1.0, 0.3) * mj.SerialMC(1000, 5000))
     assert 20 < mj.acceptance(ch) < 40                                       # linear_regression.jl:27 "~ 29.7%"
+
+
+@pytest.mark.parametrize("order", [1, 2])
+def test_zv_control_variates(O, capi, ctx, order):
+    """linearZv / quadraticZv (src/stats/zv.jl:8-66) on the device against the oracle (same elimination,
+    bit for bit) and against a numpy restatement that calls inv() like the reference"""
+    X, y, hy, _ = make_regression("logistic", 300, 4, 6)
+    dm = capi.DeviceModel(ctx, "logistic", 4, X, y, hy)
+    run = capi.DeviceRun(dm, capi.sampler_cfg("HMC", scale=0.05, nleaps=5), (201, 1, 1200), 70, np.zeros(4), seed=3, engine="wave")
+    run.execute()
+    out = run.fetch()
+    zv, a = run.zv(order)
+    zv2, a2 = ctx.zv(out["samples"], out["grads"], order)                      # host-array entry point
+    assert np.array_equal(zv, zv2) and np.array_equal(a, a2)
+    d = 4
+    k = d if order == 1 else d * (d + 3) // 2
+    assert a.shape == (70, k, d)
+    for c in range(0, 70, 9):
+        x, g = out["samples"][c], out["grads"][c]
+        ozv, oa = O.zv(x, g, order)
+        assert np.array_equal(a[c], oa) and np.allclose(zv[c], ozv, rtol=0, atol=1e-13)
+        z = -g / 2
+        feats = [z] if order == 1 else [z, 2 * z * x - 1] + [np.column_stack([x[:, i] * z[:, j] + x[:, j] * z[:, i] for i in range(d - 1) for j in range(i + 1, d)])]
+        F = np.column_stack(feats)
+        ar = np.empty((k, d))
+        for i in range(d):
+            cv = np.cov(np.column_stack([F, x[:, i]]), rowvar=False)
+            ar[:, i] = -np.linalg.inv(cv[:k, :k]) @ cv[:k, k]
+        assert np.allclose(a[c], ar, rtol=1e-7, atol=1e-9)
+        assert np.all(zv[c].var(0) < 0.35 * x.var(0))                          # the control variates do reduce variance
+        assert np.allclose(zv[c].mean(0), x.mean(0), atol=5 * x.std(0) / np.sqrt(30))
+    run.close(); dm.close()
+    import mcmc_jl_b200 as mj
+    ch = mj.run(mj.model("normal", init=np.ones(3)) * mj.HMC(0.75) * mj.SerialMC(steps=3000, burnin=300))
+    zvc, aa = (mj.linearZv if order == 1 else mj.quadraticZv)(ch)
+    assert zvc.shape == (2700, 3) and np.all(np.abs(zvc) < 1e-9)               # Gaussian target: z = x, the estimator is exact
