@@ -88,6 +88,9 @@ typedef struct {
   int32_t store_grad;        /* keep pgrads (SerialMC.jl:51-53)                                       */
   int32_t store_logtarget;   /* keep plogtarget of every kept sample                                   */
   int32_t engine;            /* MCMCGPU_ENGINE_*                                                       */
+  int32_t store_rb;          /* HMC storeLeaps (HMC.jl:145-150): keep, per kept step, the Rao-Blackwell sum of
+                                mean_rb_hmc (src/stats/mean.jl:11-35) accumulated over the leapfrog states on the fly
+                                (the leap states themselves are not stored); fetched with mcmcgpu_run_fetch_rb */
 } mcmcgpu_runner_cfg;
 
 typedef struct {
@@ -159,6 +162,8 @@ int32_t mcmcgpu_run_set_state(mcmcgpu_run* run, int64_t step0, const double* lea
 int32_t mcmcgpu_run_get_state(mcmcgpu_run* run, double* pars, double* leapstep, double* dual_leapstep, double* dualH);
 int32_t mcmcgpu_run_fetch(mcmcgpu_run* run, double* out_samples, double* out_grads, uint8_t* out_accept,
                           double* out_logtarget);
+/* Rao-Blackwellised draws (store_rb): out_rb d x S x nchains; their column means are mean_rb(chain) (mean.jl:37-41) */
+int32_t mcmcgpu_run_fetch_rb(mcmcgpu_run* run, double* out_rb);
 /* per-chain diagnostics: final leap step (HMCDA/tuned), kept-step leap steps (S x nchains) and leap counts */
 int32_t mcmcgpu_run_fetch_diag(mcmcgpu_run* run, double* out_eps, int64_t* out_nleaps);
 /* src/stats on the device-resident draws: outputs d x nchains each (NULL = skip).

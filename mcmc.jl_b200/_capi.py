@@ -36,7 +36,7 @@ class RunnerCfg(C.Structure):
     _fields_ = [("first", C.c_int64), ("step", C.c_int64), ("last", C.c_int64),
                 ("nchains", C.c_int64), ("chain_offset", C.c_int64), ("seed", C.c_uint64),
                 ("init_per_chain", C.c_int32), ("store_grad", C.c_int32),
-                ("store_logtarget", C.c_int32), ("engine", C.c_int32)]
+                ("store_logtarget", C.c_int32), ("engine", C.c_int32), ("store_rb", C.c_int32)]
 
 
 class RunInfo(C.Structure):
@@ -52,7 +52,7 @@ EXPORTS = [
     "mcmcgpu_set_option", "mcmcgpu_comm_unique_id", "mcmcgpu_comm_init", "mcmcgpu_model_create", "mcmcgpu_model_create_device",
     "mcmcgpu_model_destroy", "mcmcgpu_logtarget_grad", "mcmcgpu_run_chains", "mcmcgpu_run_create",
     "mcmcgpu_run_execute", "mcmcgpu_run_execute_steps", "mcmcgpu_run_set_state", "mcmcgpu_run_get_state",
-    "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
+    "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_rb", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
     "mcmcgpu_run_destroy", "mcmcgpu_stats", "mcmcgpu_philox_draws", "mcmcgpu_run_seqmc", "mcmcgpu_run_serialtemp", "mcmcgpu_run_zv", "mcmcgpu_zv",
 ]
 
@@ -91,6 +91,7 @@ def lib():
         L.mcmcgpu_run_set_state.argtypes = [vp, C.c_int64, dp, dp, dp]
         L.mcmcgpu_run_get_state.argtypes = [vp, dp, dp, dp, dp]
         L.mcmcgpu_run_fetch.argtypes = [vp, dp, dp, C.POINTER(C.c_uint8), dp]
+        L.mcmcgpu_run_fetch_rb.argtypes = [vp, dp]
         L.mcmcgpu_run_fetch_diag.argtypes = [vp, dp, C.POINTER(C.c_int64)]
         L.mcmcgpu_run_stats.argtypes = [vp, C.c_int32, C.c_int64, C.c_int64, dp, dp, dp, dp, dp, dp]
         L.mcmcgpu_run_destroy.argtypes = [vp]
@@ -275,7 +276,7 @@ class DeviceRun:
     """Split-form run: inputs resident in HBM after construction; execute() may be timed alone."""
 
     def __init__(self, model, scfg, rng, nchains, init, scale=None, seed=0, chain_offset=0, normals=None, uniforms=None,
-                 store_grad=True, store_logtarget=True, engine="auto"):
+                 store_grad=True, store_logtarget=True, engine="auto", store_rb=False):
         first, step, last = rng
         self.model, self.d = model, model.d
         r = RunnerCfg()
@@ -285,6 +286,7 @@ class DeviceRun:
         if init.ndim == 2 and init.shape != (nchains, self.d):
             raise MCMCGPUError(E_ARG, "init must be (d,) or (nchains, d)")
         r.store_grad, r.store_logtarget, r.engine = int(store_grad), int(store_logtarget), ENGINE[engine]
+        r.store_rb = int(store_rb)
         self.S = 0 if (step < 1 or last < first) else (last - first) // step + 1
         self.C = nchains
         self.store_grad, self.store_logtarget = store_grad, store_logtarget
@@ -338,6 +340,11 @@ class DeviceRun:
                                       None if acc is None else acc.ctypes.data_as(C.POINTER(C.c_uint8)),
                                       dptr(res["logtarget"])))
         return {k: v for k, v in res.items() if v is not None}
+
+    def fetch_rb(self):
+        rb = np.empty((self.C, self.S, self.d))
+        check(lib().mcmcgpu_run_fetch_rb(self.h, dptr(rb)))
+        return rb
 
     def fetch_diag(self):
         eps = np.empty((self.C, self.S))

@@ -258,9 +258,8 @@ class HMC(_Sampler):
             leapStep = float(scale)
         assert nLeaps > 0, "inner steps should be > 0"
         assert leapStep > 0, "inner steps scaling should be > 0"
-        if storeLeaps:
-            raise NotImplementedError("storeLeaps is outside the hot-path scope (SURVEY.md 8f.2)")
-        self.nLeaps, self.leapStep, self.storeLeaps, self.tuner = nLeaps, leapStep, False, tuner
+        # storeLeaps (HMC.jl:145-150): the GPU keeps the Rao-Blackwell sums mean_rb needs instead of the leap states
+        self.nLeaps, self.leapStep, self.storeLeaps, self.tuner = nLeaps, leapStep, bool(storeLeaps), tuner
 
     def _cfg(self):
         return capi.sampler_cfg("HMC", scale=self.leapStep, nleaps=self.nLeaps, tuner=self.tuner._cfg() if self.tuner else None)
@@ -466,6 +465,10 @@ class MCMCChainBatch:
     def stats(self, vtype="imse", **kw):
         return self._run.stats(vtype, kw.get("maxlag", -1), kw.get("batchlen", 100))
 
+    def rb(self):
+        """(C, S, d) Rao-Blackwellised draws of an HMC(storeLeaps=true) run"""
+        return self._run.fetch_rb()
+
     def close(self):
         self._run.close()
 
@@ -529,7 +532,8 @@ def _run_task(t, init=None, normals=None, uniforms=None, shard_over_ranks=False)
         ini = ini[offset:offset + nchains]
     drun = capi.DeviceRun(m.device_model(), s._cfg(), (r.r.start, r.r.step, r.r[-1]), nchains, ini, scale=m.scale,
                           seed=r.seed, chain_offset=offset, normals=normals, uniforms=uniforms,
-                          store_grad=bool(r.store_gradients), store_logtarget=True, engine=r.engine)
+                          store_grad=bool(r.store_gradients), store_logtarget=True, engine=r.engine,
+                          store_rb=bool(getattr(s, "storeLeaps", False)))
     try:
         info = drun.execute()
     except MCMCGPUError as e:
@@ -560,6 +564,8 @@ def run(*args, **kw):
     if isinstance(t.runner, GPUMC):
         return batch
     chain = batch[0]
+    if getattr(t.sampler, "storeLeaps", False):
+        chain.diagnostics["rb"] = batch.rb()[0]
     chain.runTime = batch.runTime
     batch.close()
     return chain
@@ -663,6 +669,16 @@ def _stats(c, vtype, pars=None, **kw):
 
 def mean(c, pars=None):                                                    # mean.jl:6
     return _stats(c, "iid", pars)["mean"]
+
+
+def mean_rb(c, pars=None, s="hmc"):
+    """mean.jl:37-41: mean of an HMC(storeLeaps=true) chain from the Rao-Blackwell samples (mean.jl:11-35)"""
+    assert s == "hmc"
+    rb = c.rb() if isinstance(c, MCMCChainBatch) else c.diagnostics["rb"][None]
+    out = rb.mean(axis=1)
+    if pars is not None:
+        out = out[:, [p - 1 for p in ([pars] if np.isscalar(pars) else list(pars))]]
+    return out if isinstance(c, MCMCChainBatch) else out[0]
 
 
 def var(c, pars=None, vtype="imse", **kw):                                 # var.jl:137-151

@@ -107,7 +107,7 @@ struct RunnerDev {
   int64_t C, Cp;          // chains, padded chain count (array pitch)
   int64_t chain_offset;
   uint64_t seed;
-  int32_t init_per_chain, store_grad, store_lt;
+  int32_t init_per_chain, store_grad, store_lt, store_rb;
 };
 
 }  // namespace mg

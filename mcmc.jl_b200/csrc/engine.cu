@@ -80,6 +80,7 @@ struct mcmcgpu_run {
   int32_t *nleaps = nullptr, *status = nullptr;
   unsigned long long* n_evals = nullptr;
   // wave state
+  double *rb = nullptr, *rb_acc = nullptr;
   double *ram_S = nullptr, *ram_al = nullptr;
   uint8_t* ram_pending = nullptr;
   double *q = nullptr, *part = nullptr, *red = nullptr, *cur_pars = nullptr, *cur_grad = nullptr, *cur_lt = nullptr,
@@ -458,6 +459,10 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   if (r->store_grad) RCU(R->alloc(&R->grads, (size_t)(S * d * Cp), false));
   RCU(R->alloc(&R->accept, (size_t)(S * Cp)));
   if (r->store_logtarget) RCU(R->alloc(&R->logtarget, (size_t)(S * Cp), false));
+  if (r->store_rb) {
+    if (s->kind != MCMCGPU_HMC && s->kind != MCMCGPU_HMCDA) { mcmcgpu_run_destroy(R); return fail(MCMCGPU_E_ARG, "storeLeaps applies to HMC / HMCDA"); }
+    RCU(R->alloc(&R->rb, (size_t)(S * d * Cp), false));
+  }
   if (R->has_diag) {
     RCU(R->alloc(&R->eps, (size_t)(S * Cp)));
     RCU(R->alloc(&R->nleaps, (size_t)(S * Cp)));
@@ -490,6 +495,7 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     RCU(R->alloc(&R->tn_acc, (size_t)Cp));
     RCU(R->alloc(&R->tn_prop, (size_t)Cp));
     RCU(R->alloc(&R->need_ll, (size_t)Cp));
+    if (r->store_rb) RCU(R->alloc(&R->rb_acc, (size_t)(d * Cp)));
     if (s->kind == MCMCGPU_RAM) {
       RCU(R->alloc(&R->ram_S, (size_t)(d * d * Cp)));
       RCU(R->alloc(&R->ram_al, (size_t)Cp));
@@ -505,7 +511,7 @@ static RunnerDev runner_dev(const mcmcgpu_run* R) {
   RunnerDev D;
   D.first = R->r.first; D.step = R->r.step; D.last = R->r.last; D.S = R->S; D.C = R->C; D.Cp = R->Cp;
   D.chain_offset = R->r.chain_offset; D.seed = R->r.seed; D.init_per_chain = R->r.init_per_chain;
-  D.store_grad = R->r.store_grad; D.store_lt = R->r.store_logtarget;
+  D.store_grad = R->r.store_grad; D.store_lt = R->r.store_logtarget; D.store_rb = R->r.store_rb;
   return D;
 }
 static SamplerDev sampler_dev(const mcmcgpu_run* R) {
@@ -549,7 +555,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     A.M = m->dev(); A.S = sampler_dev(R); A.R = runner_dev(R);
     A.init = R->init; A.scale = R->scale; A.inj_normals = R->inj_normals; A.inj_uniforms = R->inj_uniforms;
     A.samples = R->samples; A.grads = R->grads; A.accept = R->accept; A.logtarget = R->logtarget;
-    A.eps = R->eps; A.nleaps = R->nleaps; A.final_eps = R->final_eps; A.final_pars = nullptr;
+    A.eps = R->eps; A.nleaps = R->nleaps; A.final_eps = R->final_eps; A.final_pars = nullptr; A.rb = R->rb;
     A.status = R->status; A.n_evals = R->n_evals;
     CU(launch_fused(A, st));
     launches = 1;
@@ -567,7 +573,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     W.need_ll = R->need_ll; W.status = R->status; W.remaining = R->remaining; W.n_evals = R->n_evals;
     W.init = R->init; W.scale = R->scale; W.inj_normals = R->inj_normals; W.inj_uniforms = R->inj_uniforms;
     W.samples = R->samples; W.grads = R->grads; W.accept = R->accept; W.logtarget = R->logtarget;
-    W.eps = R->eps; W.nleaps = R->nleaps; W.final_eps = R->final_eps;
+    W.eps = R->eps; W.nleaps = R->nleaps; W.final_eps = R->final_eps; W.rb = R->rb; W.rb_acc = R->rb_acc;
     const int kind = R->s.kind;
     const bool need_grad = (kind != MCMCGPU_RWM && kind != MCMCGPU_RAM);
     const bool is_ram = (kind == MCMCGPU_RAM);
@@ -760,6 +766,14 @@ __global__ void i32_to_i64_kernel(const int32_t* in, int64_t* out, int64_t n) {
   if (i < n) out[i] = in[i];
 }
 
+int32_t mcmcgpu_run_fetch_rb(mcmcgpu_run* R, double* out_rb) {
+  if (!R || !out_rb) return fail(MCMCGPU_E_ARG, "NULL argument");
+  if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
+  if (!R->rb) return fail(MCMCGPU_E_STATE, "Rao-Blackwell sums were not stored (store_rb = 0)");
+  CU(cudaSetDevice(R->m->ctx->device));
+  return fetch_chunked(R, R->rb, R->S * R->d, out_rb);
+}
+
 int32_t mcmcgpu_run_fetch_diag(mcmcgpu_run* R, double* out_eps, int64_t* out_nleaps) {
   if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
@@ -906,6 +920,7 @@ int32_t mcmcgpu_run_chains(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   mcmcgpu_runner_cfg rr = *r;
   rr.store_grad = out_grads ? 1 : 0;
   rr.store_logtarget = out_logtarget ? 1 : 0;
+  rr.store_rb = 0;
   mcmcgpu_run* R = nullptr;
   int rc = mcmcgpu_run_create(m, s, &rr, init, scale, inj_normals, inj_uniforms, &R);
   if (rc != MCMCGPU_OK) return rc;

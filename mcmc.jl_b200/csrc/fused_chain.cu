@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
       double plt = Family<FAM, D>::evalallg(M, sh_series, d, prop, pg);         // :60 (eval; gradient unused)
       nev++;
       double ratio = plt - lt;                                                  // :62
-      bool acc = ratio > 0 || ratio > log(draw_uniform(i));                     // :63
+      bool acc = ratio > 0;                                                     // :63 `ratio > 0 || ratio > log(rand())`
+      if (!acc) acc = ratio > log(draw_uniform(i));
       if (acc) {
         store(i, prop, plt, pg, false, true, CUDART_NAN, 0);
 #pragma unroll
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
 #pragma unroll
       for (int j = 0; j < D; j++) if (j < d) { double t = mean[j] - pars[j]; qon += -(t * t) / (2.0 * h) - lc; }
       double ratio = plt + qon - lt - qno;                                      // :107
-      bool acc = ratio > 0 || ratio > log(draw_uniform(i));                     // :108
+      bool acc = ratio > 0;                                                     // :108
+      if (!acc) acc = ratio > log(draw_uniform(i));
       if (acc) {
         store(i, prop, plt, pg, true, true, h, 0);
 #pragma unroll
@@ -250,6 +252,9 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
       double plt = lt;
 #pragma unroll
       for (int j = 0; j < D; j++) { p[j] = pars[j]; g[j] = grad[j]; }
+      double rbacc[D];
+#pragma unroll
+      for (int j = 0; j < D; j++) rbacc[j] = 0.0;
       for (long long l = 0; l < nLeaps; l++) {                                  // leapfrog HMC.jl:93-102
 #pragma unroll
         for (int j = 0; j < D; j++) m[j] += (0.5 * g[j]) * eps;
@@ -259,6 +264,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
         nev++;
 #pragma unroll
         for (int j = 0; j < D; j++) m[j] += (0.5 * g[j]) * eps;
+        if (A.rb) {                                                             // storeLeaps: w = exp(H0 - H_leap) (mean.jl:19)
+          const double wl = exp(H0 - (-plt + 0.5 * dotd<D>(m, d)));
+#pragma unroll
+          for (int j = 0; j < D; j++) rbacc[j] += wl * p[j];                    // mean.jl:27
+        }
       }
       const double H = -plt + 0.5 * dotd<D>(m, d);
       const double e = exp(H0 - H);
@@ -266,6 +276,10 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
       bool acc; double pacc = 0.0;
       if (da) { pacc = isnan(e) ? 0.0 : (e < 1.0 ? e : 1.0); acc = u < pacc; }  // HMCDA.jl:120-121 (NaN => 0: documented)
       else acc = u < e;                                                          // HMC.jl:154
+      if (A.rb && in_range(i, R.first, R.step, R.last)) {                       // (sample + sum_k w_k pars_k)/(nleaps+1), mean.jl:24-30
+#pragma unroll
+        for (int j = 0; j < D; j++) if (j < d) A.rb[(kept * d + j) * Cp + c] = ((acc ? p[j] : pars[j]) + rbacc[j]) / (double)(nLeaps + 1);
+      }
       if (acc) {
         store(i, p, plt, g, true, true, eps, (int)nLeaps);
 #pragma unroll

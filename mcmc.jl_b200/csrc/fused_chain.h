@@ -15,6 +15,7 @@ struct FusedArgs {
   double* grads;               // [S][d][Cp] or null
   uint8_t* accept;             // [S][Cp]
   double* logtarget;           // [S][Cp] or null
+  double* rb;                  // [S][d][Cp] or null: Rao-Blackwell sums (mean.jl:11-35)
   double* eps;                 // [S][Cp] or null
   int32_t* nleaps;             // [S][Cp] or null
   double* final_eps;           // [Cp] or null

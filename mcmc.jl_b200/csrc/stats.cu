@@ -30,9 +30,11 @@ __global__ void __launch_bounds__(128) stats_kernel(const double* __restrict__ s
   const double n = (double)S;
   // mean (mean.jl:6) and variance (Base.var: two-pass, n-1)
   double s = 0.0;
-  for (int64_t t = 0; t < S; t++) s += x[t * st];
+#pragma unroll 8
+  for (int64_t t = 0; t < S; t++) s += x[t * st];            // loads are independent: 8 in flight per thread
   const double mu = s / n;
   double ss = 0.0;
+#pragma unroll 8
   for (int64_t t = 0; t < S; t++) { double v = x[t * st] - mu; ss += v * v; }
   const double viid = (ss / (double)(S - 1)) / n;   // var.jl:7-8
   double v = CUDART_NAN;

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
   int64_t i = W.istep[c];
   int leap = hmc_like ? W.leap[c] : 0;
   int nl_cur = hmc_like ? W.nleaps_cur[c] : 0;
-  const bool interior = (ph == PH_LEAP) && (leap + 1 < nl_cur);
+  const bool interior = (ph == PH_LEAP) && (leap + 1 < nl_cur) && (W.rb == nullptr);   // storeLeaps needs H at every leap
   EvalFin F; F.lt = CUDART_NAN; F.oos = false; F.ginv = 0.0; F.fam = M.family;
   if (ph != PH_PAUSE) F = finalize_eval(M, q, part, ns, Cp, c, !interior);
   const double lt_q = F.lt;
@@ -197,7 +197,17 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
   } else {  // PH_LEAP: HMC.jl:93-102 second half, then either the next leapfrog or the decision
     const double eps = W.eps_cur[c];
     leap += 1;
+    if (W.rb) {   // storeLeaps: weight of this leap state exp(H0 - H) and its contribution (mean.jl:19,27)
+      double mm2 = 0.0;
+      for (int64_t j = 0; j < d; j++) {
+        double m = W.mom[j * Cp + c] + (0.5 * fin_grad(F, M, q, part, ns, Cp, c, j)) * eps;
+        mm2 += m * m;
+      }
+      const double wl = exp(W.H0[c] - (-lt_q + 0.5 * mm2));
+      for (int64_t j = 0; j < d; j++) W.rb_acc[j * Cp + c] += wl * q[j * Cp + c];
+    }
     if (leap < nl_cur) {
+#pragma unroll 4
       for (int64_t j = 0; j < d; j++) {
         double gj = fin_grad(F, M, q, part, ns, Cp, c, j);
         double m = W.mom[j * Cp + c];
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
         q[j * Cp + c] = p;
       }
       W.leap[c] = leap;
-      W.need_ll[c] = (leap + 1 == nl_cur) ? 1 : 0;
+      W.need_ll[c] = (leap + 1 == nl_cur || W.rb) ? 1 : 0;
       atomicAdd(W.n_evals, nev);
       return;
     }
@@ -233,6 +243,10 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       }
       W.cur_lt[c] = lt_q;
       if (S.tuner_on) W.tn_acc[c] += 1;
+    }
+    if (W.rb && in_range(i, R.first, R.step, R.last)) {   // (sample + sum_k w_k pars_k) / (nleaps + 1), mean.jl:24-30
+      const int64_t k = W.kept[c];
+      for (int64_t j = 0; j < d; j++) W.rb[(k * d + j) * Cp + c] = (W.cur_pars[j * Cp + c] + W.rb_acc[j * Cp + c]) / (double)(nl_cur + 1);
     }
     store(i, true, acc, eps, nl_cur);
     if (kind == MCMCGPU_HMCDA) {
@@ -331,9 +345,10 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       }
     }
     if (hmc_like) {
+      if (W.rb) for (int64_t j = 0; j < d; j++) W.rb_acc[j * Cp + c] = 0.0;
       W.H0[c] = -W.cur_lt[c] + 0.5 * mm;                              // update! HMC.jl:91
       W.leap[c] = 0; W.nleaps_cur[c] = nl;
-      W.need_ll[c] = (nl == 1) ? 1 : 0;
+      W.need_ll[c] = (nl == 1 || W.rb) ? 1 : 0;
       W.phase[c] = PH_LEAP;
     } else {
       W.need_ll[c] = 1;

@@ -42,6 +42,8 @@ struct WaveArgs {
   // outputs
   double* samples; double* grads; uint8_t* accept; double* logtarget; double* eps; int32_t* nleaps;
   double* final_eps;
+  double* rb;                  // [S][d][Cp] Rao-Blackwell sums (store_rb) or null
+  double* rb_acc;              // [d][Cp] running sum_k w_k pars_k of the current trajectory
 };
 
 cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st);

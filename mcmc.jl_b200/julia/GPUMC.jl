@@ -66,7 +66,7 @@ type SamplerCfg   # mirrors mcmcgpu_sampler_cfg field for field
 end
 type RunnerCfg    # mirrors mcmcgpu_runner_cfg
   first::Int64; step::Int64; last::Int64; nchains::Int64; chain_offset::Int64; seed::Uint64
-  init_per_chain::Int32; store_grad::Int32; store_logtarget::Int32; engine::Int32
+  init_per_chain::Int32; store_grad::Int32; store_logtarget::Int32; engine::Int32; store_rb::Int32
 end
 
 tunercfg(t) = isa(t, EmpMCTuner) ? (int32(1), int32(t.adaptStep), int32(t.maxStep), t.targetPath, t.targetRate) :
@@ -75,6 +75,7 @@ samplercfg(s::RWM)   = SamplerCfg(0, 0, s.scale, 0., 0., 0., 0., 0., 0, 0, 0, 0,
 samplercfg(s::MALA)  = SamplerCfg(1, 0, s.driftStep, 0., 0., 0., 0., 0., 0, tunercfg(s.tuner)...)
 samplercfg(s::HMC)   = SamplerCfg(2, s.nLeaps, s.leapStep, 0., 0., 0., 0., 0., 0, tunercfg(s.tuner)...)
 samplercfg(s::HMCDA) = SamplerCfg(3, 0, 0., s.rate, s.len, s.shrinkage, s.t0, s.step, 0, 0, 0, 0, 0., 0.)
+samplercfg(s::RAM)   = SamplerCfg(4, 0, s.scale, s.rate, 0., 0., 0., 0., 0, 0, 0, 0, 0., 0.)
 
 function run_gpumc(t::MCMCTask)
   tic()
@@ -90,7 +91,7 @@ function run_gpumc(t::MCMCTask)
   samples = Array(Float64, d, S, C); grads = Array(Float64, d, S, C)
   accept = Array(Uint8, S, C); logtarget = Array(Float64, S, C)
   scfg = samplercfg(t.sampler)
-  rcfg = RunnerCfg(first(r.r), r.r.step, last(r.r), C, 0, r.seed, 0, r.storegradients, 1, 0)
+  rcfg = RunnerCfg(first(r.r), r.r.step, last(r.r), C, 0, r.seed, 0, r.storegradients, 1, 0, 0)
   info = Array(Float64, 5)
   rc = ccall((:mcmcgpu_run_chains, libmcmcgpu), Int32,
              (Ptr{Void}, Ptr{SamplerCfg}, Ptr{RunnerCfg}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},

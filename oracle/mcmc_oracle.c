@@ -416,7 +416,22 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
       memcpy(st0.m, normals + i * d, sizeof(double) * (size_t)d); /* :136 */
       hs_update(&st0, d);                                         /* :137 */
       hs_copy(&st, &st0, d);                                      /* :138 */
-      for (int64_t j = 0; j < nLeaps; j++) hs_leapfrog(&st, leapStep, m, &nev); /* :141-143 */
+      double* leapP = NULL; double* leapH = NULL;                 /* leapStates[2..nLeaps+1] (:145-150) */
+      if (s->rb_out) { leapP = (double*)malloc(sizeof(double) * (size_t)(nLeaps * d)); leapH = (double*)malloc(sizeof(double) * (size_t)nLeaps); }
+      for (int64_t j = 0; j < nLeaps; j++) {                      /* :141-143 */
+        hs_leapfrog(&st, leapStep, m, &nev);
+        if (s->rb_out) { memcpy(leapP + j * d, st.pars, sizeof(double) * (size_t)d); leapH[j] = st.H; }
+      }
+      if (s->rb_out && in_range(i, r)) {                          /* mean_rb_hmc, src/stats/mean.jl:17-31 */
+        int accn = uniforms[i] < exp(st0.H - st.H);
+        const double* smp = accn ? st.pars : st0.pars;            /* c.samples[i, :] */
+        for (int64_t jj = 0; jj < d; jj++) {
+          double sm = smp[jj];
+          for (int64_t k = 0; k < nLeaps; k++) sm += exp(st0.H - leapH[k]) * leapP[k * d + jj];
+          s->rb_out[kept * d + jj] = sm / (double)(nLeaps + 1);
+        }
+      }
+      if (leapP) { free(leapP); free(leapH); }
       if (uniforms[i] < exp(st0.H - st.H)) {                      /* :154 */
         STORE(st.pars, st.logTarget, st.grad, 1, leapStep, nLeaps);
         hs_copy(&st0, &st, d);                                    /* :158 */

@@ -32,7 +32,7 @@ class _Sampler(C.Structure):
                 ("rate", C.c_double), ("len", C.c_double), ("shrinkage", C.c_double),
                 ("t0", C.c_double), ("step", C.c_double), ("max_leaps", C.c_int64),
                 ("tuner_on", C.c_int32), ("adapt_step", C.c_int32), ("max_step", C.c_int32),
-                ("target_path", C.c_double), ("target_rate", C.c_double), ("force_eps", C.c_void_p)]
+                ("target_path", C.c_double), ("target_rate", C.c_double), ("force_eps", C.c_void_p), ("rb_out", C.c_void_p)]
 
 
 class _Range(C.Structure):
@@ -110,8 +110,12 @@ class Model:
 
 
 def sampler(kind, scale=1.0, nleaps=10, rate=0.65, len=2.0, shrinkage=0.05, t0=10.0, step=0.75, max_leaps=0,
-            tuner=None, force_eps=None):
+            tuner=None, force_eps=None, rb_out=None):
     s = _Sampler()
+    if rb_out is not None:
+        assert rb_out.flags["C_CONTIGUOUS"] and rb_out.dtype == np.float64
+        s._rb = rb_out
+        s.rb_out = rb_out.ctypes.data
     if force_eps is not None:
         s._keep = np.ascontiguousarray(force_eps, dtype=np.float64)  # keep alive
         s.force_eps = s._keep.ctypes.data

@@ -544,3 +544,27 @@ def test_zv_control_variates(O, capi, ctx, order):
     ch = mj.run(mj.model("normal", init=np.ones(3)) * mj.HMC(0.75) * mj.SerialMC(steps=3000, burnin=300))
     zvc, aa = (mj.linearZv if order == 1 else mj.quadraticZv)(ch)
     assert zvc.shape == (2700, 3) and np.all(np.abs(zvc) < 1e-9)               # Gaussian target: z = x, the estimator is exact
+
+
+@pytest.mark.parametrize("engine", ["fused", "wave"])
+def test_store_leaps_rao_blackwell(O, capi, ctx, engine):
+    """HMC storeLeaps + mean_rb (HMC.jl:145-150, src/stats/mean.jl:11-41): the Rao-Blackwell sums are
+    accumulated over the leap states on the device; the oracle keeps the leap states and applies mean.jl literally"""
+    d, C, rngt = 3, 50, (21, 1, 300)
+    rng = np.random.default_rng(12)
+    zn = rng.standard_normal((C, rngt[2] + 1, d)); un = rng.random((C, rngt[2] + 1))
+    dm = capi.DeviceModel(ctx, "normal_fn", d)
+    run = capi.DeviceRun(dm, capi.sampler_cfg("HMC", scale=0.4, nleaps=6), rngt, C, np.ones(d), normals=zn, uniforms=un, engine=engine, store_rb=True)
+    run.execute(); out = run.fetch(); rb = run.fetch_rb()
+    om = O.Model("normal_fn", d)
+    S = out["samples"].shape[1]
+    for c in range(C):
+        orb = np.full((S, d), np.nan)
+        ref = O.run_chain(om, O.sampler("HMC", scale=0.4, nleaps=6, rb_out=orb), rngt, np.ones(d), None, zn[c], un[c])
+        assert np.array_equal(ref["samples"], out["samples"][c]) and np.array_equal(ref["accept"], out["accept"][c])
+        assert np.allclose(rb[c], orb, rtol=1e-13, atol=1e-15)
+    run.close(); dm.close()
+    import mcmc_jl_b200 as mj
+    ch = mj.run(mj.model("normal", init=np.ones(3)) * mj.HMC(0.3, storeLeaps=True) * mj.SerialMC(steps=4000, burnin=500))
+    m_rb, m = mj.mean_rb(ch), mj.mean(ch)
+    assert m_rb.shape == (3,) and np.all(np.abs(m_rb) < 0.1) and np.all(np.abs(m) < 0.1)
