@@ -105,14 +105,23 @@ __device__ __forceinline__ LinkOut link(double eta, double y, const double* hy, 
       const double u = fabs(z) * MG_SQRT1_2;
       const double ex = erfcx(u);
       double l, w;
-      if (z < 0.0) {
-        l = -(u * u) + log(0.5 * ex);
-        w = 0.79788456080286535588 / ex;                 // sqrt(2/pi)
-      } else {
+      if (u < 26.0) {
+        // branch-free for |z| < 36.8: c = exp(-u^2) erfcx(u) / 2 is the tail mass; no lane of a warp diverges on the
+        // sign of z (the signs are mixed in practically every warp)
         const double e2 = exp(-(u * u));
         const double c = 0.5 * e2 * ex;
-        l = log1p(-c);
-        w = (0.39894228040143267794 * e2) / (1.0 - c);   // 1/sqrt(2 pi)
+        const bool neg = z < 0.0;
+        const double omc = 1.0 - c;
+        l = log(neg ? c : omc);                                    // log Phi(z)
+        w = neg ? 0.79788456080286535588 / ex                      // sqrt(2/pi) / erfcx(u)
+                : (0.39894228040143267794 * e2) / omc;             // phi(z) / Phi(z)
+      } else if (z < 0.0) {
+        l = -(u * u) + log(0.5 * ex);                              // far lower tail: exp(-u^2) would underflow
+        w = 0.79788456080286535588 / ex;
+      } else {
+        const double e2 = exp(-(u * u));                           // far upper tail: Phi(z) = 1 - (denormal or 0)
+        l = log1p(-0.5 * e2 * ex);
+        w = 0.39894228040143267794 * e2;
       }
       (void)base;
       o.ll1 = y1 ? l : 0.0;
@@ -133,7 +142,7 @@ __device__ __forceinline__ LinkOut link(double eta, double y, const double* hy, 
 // 256 threads, <= 128 registers, two CTAs per SM: 16 warps keep the DMMA pipe fed while other warps
 // are in the (latency-bound) link-function epilogue.
 template <int FAM, int DK, int NR>
-__global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_2CTA) ? 2 : 1) k1_kernel(const K1Args a) {
+__global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1)) k1_kernel(const K1Args a) {
   constexpr int S = 8 * DK + 4;
   constexpr int TILE_D = K1_ROWS * S + K1_ROWS;
   constexpr int NG = K1_ROWS / (8 * NR);      // row groups per tile
@@ -340,7 +349,7 @@ int k1_choose_splits(const K1Pack& P, int64_t Cp) {
   const int64_t ctiles = Cp / K1_CHAINS;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  const int64_t slots = (P.DK <= K1_MAX_DK_2CTA ? 2LL : 1LL) * sms;
+  const int64_t slots = (P.DK <= K1_MAX_DK_3CTA ? 3LL : (P.DK <= K1_MAX_DK_2CTA ? 2LL : 1LL)) * sms;
   int64_t maxs = P.ntiles / 8;
   if (maxs < 1) maxs = 1;
   if (maxs > 512) maxs = 512;

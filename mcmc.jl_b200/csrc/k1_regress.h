@@ -6,6 +6,7 @@ namespace mg {
 constexpr int K1_ROWS = 32;      // rows of X per shared-memory tile
 constexpr int K1_WARPS = 8;      // consumer warps per CTA; each owns 8 chains
 constexpr int K1_CHAINS = 8 * K1_WARPS;  // chains per CTA (64)
+constexpr int K1_MAX_DK_3CTA = 4;   // d <= 32: small accumulators, three CTAs per SM hide the epilogue latency
 constexpr int K1_MAX_DK_2CTA = 13;  // d <= 104: 128 registers per thread, two CTAs per SM
 constexpr int K1_MAX_D = 200;
 
