@@ -18,6 +18,7 @@
 //
 // Algorithmic work per (row, chain): 4*d flop (2d for eta, 2d for X'r); bound: FP64 tensor pipe.
 #include "k1_regress.h"
+#include "erfcx_table.h"
 #include <cmath>
 #include <cstdio>
 
@@ -62,6 +63,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// ---- erfcx(u), 0 <= u < 26: degree-9 piecewise polynomial (tools/gen_erfcx_table.py, 2e-16 relative) ----------
+// CUDA's erfcx costs ~100 FP64 instructions; the table costs 10 fused multiply-adds and 10 cached loads (the
+// coefficient-major layout keeps a warp's gathers on one or two cache lines because |z| clusters around 0..3).
+__device__ const double erfcx_tab[(ERFCX_DEG + 1) * ERFCX_NINT] = {ERFCX_TABLE_VALUES};
+__device__ __forceinline__ double erfcx_fast(double u) {
+  const int k = (int)(u * (double)ERFCX_INV_W);
+  const double t = u - ((double)k + 0.5) * (1.0 / ERFCX_INV_W);
+  const double* c = erfcx_tab + k;
+  double p = __ldg(c + ERFCX_DEG * ERFCX_NINT);
+#pragma unroll
+  for (int j = ERFCX_DEG - 1; j >= 0; j--) p = fma(p, t, __ldg(c + j * ERFCX_NINT));
+  return p;
+}
+
 // ---- link functions: (eta, y) -> loglik term(s) and r = d loglik / d eta ----------------------
 struct LinkOut { double ll1, ll2, r; bool bad; };
 
@@ -103,24 +118,25 @@ __device__ __forceinline__ LinkOut link(double eta, double y, const double* hy, 
       bool y1 = (y == 1.0);
       const double z = y1 ? eta : -eta;
       const double u = fabs(z) * MG_SQRT1_2;
-      const double ex = erfcx(u);
       double l, w;
-      if (u < 26.0) {
+      if (u < (double)ERFCX_UMAX) {
         // branch-free for |z| < 36.8: c = exp(-u^2) erfcx(u) / 2 is the tail mass; no lane of a warp diverges on the
         // sign of z (the signs are mixed in practically every warp)
+        const double ex = erfcx_fast(u);
         const double e2 = exp(-(u * u));
         const double c = 0.5 * e2 * ex;
         const bool neg = z < 0.0;
         const double omc = 1.0 - c;
         l = log(neg ? c : omc);                                    // log Phi(z)
-        w = neg ? 0.79788456080286535588 / ex                      // sqrt(2/pi) / erfcx(u)
-                : (0.39894228040143267794 * e2) / omc;             // phi(z) / Phi(z)
+        // phi(z)/Phi(z): sqrt(2/pi)/erfcx(u) for z < 0, phi(z)/(1 - c) otherwise -- one division either way
+        w = (neg ? 0.79788456080286535588 : 0.39894228040143267794 * e2) / (neg ? ex : omc);
       } else if (z < 0.0) {
+        const double ex = erfcx(u);
         l = -(u * u) + log(0.5 * ex);                              // far lower tail: exp(-u^2) would underflow
         w = 0.79788456080286535588 / ex;
       } else {
         const double e2 = exp(-(u * u));                           // far upper tail: Phi(z) = 1 - (denormal or 0)
-        l = log1p(-0.5 * e2 * ex);
+        l = log1p(-0.5 * e2 * erfcx(u));
         w = 0.39894228040143267794 * e2;
       }
       (void)base;
