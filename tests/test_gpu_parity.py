@@ -568,3 +568,51 @@ def test_store_leaps_rao_blackwell(O, capi, ctx, engine):
     ch = mj.run(mj.model("normal", init=np.ones(3)) * mj.HMC(0.3, storeLeaps=True) * mj.SerialMC(steps=4000, burnin=500))
     m_rb, m = mj.mean_rb(ch), mj.mean(ch)
     assert m_rb.shape == (3,) and np.all(np.abs(m_rb) < 0.1) and np.all(np.abs(m) < 0.1)
+
+
+def test_edge_shapes(O, capi, ctx):
+    """smallest and most ragged shapes: one observation, one parameter, one chain, one kept step, thinning past the end,
+    a single leapfrog, the HMCDA leap cap"""
+    rng = np.random.default_rng(21)
+    # N = 1, d = 1, C = 1 regression
+    X = np.array([[1.0]]); y = np.array([1.0])
+    for fam, hy in (("linear", (1.0, 1.0)), ("logistic", (1.0, -1.0)), ("probit", (10.0,))):
+        dm = capi.DeviceModel(ctx, fam, 1, X, y, hy)
+        om = O.Model(fam, 1, X, y, hy)
+        lt, g = dm.logtarget_grad(np.array([[0.3]]))
+        olt, og = om.evalallg(np.array([0.3]))
+        assert abs(lt[0] - olt) <= 1e-13 * abs(olt) and abs(g[0, 0] - og[0]) <= 1e-13
+        zn = rng.standard_normal((1, 6, 1)); un = rng.random((1, 6))
+        for rngt in ((5, 1, 5), (2, 7, 5), (1, 1, 1)):                       # one kept step; thinning past the end; one step in all
+            zz, uu = zn[:, :rngt[2] + 1], un[:, :rngt[2] + 1]
+            run = capi.DeviceRun(dm, capi.sampler_cfg("HMC", scale=0.3, nleaps=1), rngt, 1, np.zeros(1), normals=zz, uniforms=uu, engine="wave")
+            run.execute(); out = run.fetch()
+            ref = O.run_chain(om, O.sampler("HMC", scale=0.3, nleaps=1), rngt, np.zeros(1), None, zz[0], uu[0])
+            assert out["samples"].shape == (1, 1, 1) and np.array_equal(out["accept"][0], ref["accept"])
+            assert np.allclose(out["samples"][0], ref["samples"], rtol=1e-12, atol=1e-15)
+            run.close()
+        dm.close()
+    # HMCDA with a tiny leap cap: nLeaps = min(round(len/eps), max_leaps)
+    dm = capi.DeviceModel(ctx, "normal_fn", 2)
+    zn = rng.standard_normal((3, 41, 2)); un = rng.random((3, 41))
+    for engine in ("fused", "wave"):
+        run = capi.DeviceRun(dm, capi.sampler_cfg("HMCDA", len=50.0, max_leaps=7), (1, 1, 40), 3, np.ones(2), normals=zn, uniforms=un, engine=engine)
+        run.execute(); out = run.fetch(); eps, nl = run.fetch_diag()
+        assert np.all(nl == 7) and np.all(eps == 1.0)                         # burn-in 0: eps stays 1, round(50/1) = 50 capped at 7
+        for c in range(3):
+            ref = O.run_chain(O.Model("normal_fn", 2), O.sampler("HMCDA", len=50.0, max_leaps=7), (1, 1, 40), np.ones(2), None, zn[c], un[c])
+            assert np.array_equal(out["samples"][c], ref["samples"]) and np.array_equal(out["accept"][c], ref["accept"])
+        run.close()
+    dm.close()
+    # per-chain initial values (d x nchains init), RWM with model.scale
+    dm = capi.DeviceModel(ctx, "normal_dsl", 3, hyper=(1.0, 0.5))
+    init = rng.standard_normal((5, 3)); sc = np.array([0.5, 1.0, 2.0])
+    zn = rng.standard_normal((5, 31, 3)); un = rng.random((5, 31))
+    for engine in ("fused", "wave"):
+        run = capi.DeviceRun(dm, capi.sampler_cfg("RWM", scale=0.3), (1, 1, 30), 5, init, scale=sc, normals=zn, uniforms=un, engine=engine)
+        run.execute(); out = run.fetch()
+        for c in range(5):
+            ref = O.run_chain(O.Model("normal_dsl", 3, hyper=(1.0, 0.5)), O.sampler("RWM", scale=0.3), (1, 1, 30), init[c], sc, zn[c], un[c])
+            assert np.array_equal(out["samples"][c], ref["samples"])
+        run.close()
+    dm.close()
