@@ -430,15 +430,27 @@ def main():
                                     store_grad=False, store_logtarget=False)
                 rr.execute()
             else:
-                ce, se = 256, 300
-                rr = capi.DeviceRun(dm, scfg, (step0 + 51, 1, step0 + se), ce, init_state[:ce], seed=wl["seed"] + 7, engine="wave",
+                ce, se, skip = 256, 300, 50
+                # `skip` steps from the synthetic start are run first and discarded through a state hand-over, so that the kept
+                # range starts right after step0' = step0 + skip (a kept range starting later would turn HMCDA's burn-in
+                # adaptation back on: it runs while i < first - 1, HMCDA.jl:133)
+                r0 = capi.DeviceRun(dm, scfg, (step0 + 1, 1, step0 + skip), ce, init_state[:ce], seed=wl["seed"] + 7, engine="wave",
                                     store_grad=False, store_logtarget=False)
                 if set_state:
-                    rr.set_state(set_state[0], *(a[:ce] for a in set_state[1:]))
+                    r0.set_state(set_state[0], *(a[:ce] for a in set_state[1:]))
+                r0.execute()
+                st0 = r0.get_state()
+                r0.close()
+                rr = capi.DeviceRun(dm, scfg, (step0 + skip + 1, 1, step0 + se), ce, st0["pars"], seed=wl["seed"] + 7, engine="wave",
+                                    store_grad=False, store_logtarget=False)
+                if set_state:
+                    rr.set_state(step0 + skip, st0["leapstep"], st0["dual_leapstep"], st0["dualH"])
+                else:
+                    rr.set_state(step0 + skip)
                 rr.execute()
             st = rr.stats("imse")
             kept = rr.S
-            ess_per_step = float(np.median(st["ess"].min(axis=1)) / kept)
+            ess_per_step = float(np.nanmedian(np.nanmin(st["ess"], axis=1)) / kept)
             rr.close()
             line["min_ess_per_s"] = dict(value=ess_per_step * value, unit="min-ESS/s (min over parameters, summed over chains)",
                                          ess_per_chain_step=ess_per_step, sample=f"{ce} chains x {kept} kept steps, Geyer IMSE on the device")

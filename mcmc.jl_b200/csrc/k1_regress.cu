@@ -67,9 +67,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // CUDA's erfcx costs ~100 FP64 instructions; the table costs 10 fused multiply-adds and 10 cached loads (the
 // coefficient-major layout keeps a warp's gathers on one or two cache lines because |z| clusters around 0..3).
 __device__ const double erfcx_tab[(ERFCX_DEG + 1) * ERFCX_NINT] = {ERFCX_TABLE_VALUES};
-__device__ __forceinline__ double erfcx_fast(double u) {
-  const int k = (int)(u * (double)ERFCX_INV_W);
-  const double t = u - ((double)k + 0.5) * (1.0 / ERFCX_INV_W);
+__device__ __forceinline__ double erfcx_fast(double u) {       // requires 0 <= u < ERFCX_UMAX
+  // nearest grid point k/8 by the magic-number add (no double<->int conversion instructions on the FP64 pipe)
+  const double m = fma(u, (double)ERFCX_INV_W, 6755399441055744.0);
+  const int k = __double2loint(m);
+  const double t = fma(m - 6755399441055744.0, -1.0 / ERFCX_INV_W, u);
   const double* c = erfcx_tab + k;
   double p = __ldg(c + ERFCX_DEG * ERFCX_NINT);
 #pragma unroll
