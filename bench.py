@@ -450,10 +450,14 @@ def main():
                 rr.execute()
             st = rr.stats("imse")
             kept = rr.S
-            ess_per_step = float(np.nanmedian(np.nanmin(st["ess"], axis=1)) / kept)
+            # ess.jl:9 is n*var_iid/var_imse; for antithetic chains (HMC overshooting: lag-1 autocorrelation < -0.5) Geyer's
+            # estimate is <= 0 or tiny and the ratio is negative or above n: such parameters are counted as ESS = n
+            # (at least as good as independent draws), i.e. ESS is clipped to (0, n]
+            ess = np.where((st["ess"] > 0) & (st["ess"] < kept), st["ess"], float(kept))
+            ess_per_step = float(np.median(ess.min(axis=1)) / kept)
             rr.close()
             line["min_ess_per_s"] = dict(value=ess_per_step * value, unit="min-ESS/s (min over parameters, summed over chains)",
-                                         ess_per_chain_step=ess_per_step, sample=f"{ce} chains x {kept} kept steps, Geyer IMSE on the device")
+                                         ess_per_chain_step=ess_per_step, sample=f"{ce} chains x {kept} kept steps, Geyer IMSE on the device, ESS clipped to (0, n]")
         if not args.no_cpu_baseline and not row_sharded:
             cores = os.cpu_count() or 1
             cs = args.cpu_steps if args.workload != "cfg2" else 2000
