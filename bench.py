@@ -260,6 +260,10 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args, wl, args.workload)
 
+    # keep stdout clean for the one JSON line: libraries (NCCL prints its version banner to stdout) write to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import mcmc_jl_b200  # noqa: F401
@@ -464,7 +468,10 @@ def main():
             cb = cpu_baseline(wl, cs, 1 if args.workload != "cfg2" else 200, cores, problem)
             line["cpu_baseline"] = dict(value=cb["value"], unit="chain-steps/s", cores=cores, kind="port", sample=cb["sample"],
                                         grad_evals_per_s=cb["grad_evals_per_s"])
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     dm.close()
     ctx.close()
     if world > 1:
