@@ -34,8 +34,9 @@ struct mcmcgpu_ctx {
   NcclComm comm = nullptr;
   int rank = 0, nranks = 1;
   int64_t time_eval = 0;      // option: time every likelihood launch with events
-  int64_t poll_every = 8;     // option: waves between completion polls (HMCDA / tuned HMC)
+  int64_t poll_every = 0;     // option: waves between completion polls (HMCDA / tuned HMC); 0 = automatic
   int64_t force_splits = 0;   // option: override K1 row splits
+  int64_t k1_debug = 0;       // option (experiments): see K1Args::debug
   int32_t* h_remaining = nullptr;  // pinned
 };
 
@@ -165,8 +166,9 @@ int32_t mcmcgpu_set_option(mcmcgpu_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return fail(MCMCGPU_E_ARG, "ctx/key is NULL");
   std::string k(key);
   if (k == "time_eval") c->time_eval = value;
-  else if (k == "poll_every") c->poll_every = value < 1 ? 1 : value;
+  else if (k == "poll_every") c->poll_every = value < 0 ? 0 : value;
   else if (k == "force_splits") c->force_splits = value;
+  else if (k == "k1_debug") c->k1_debug = value;
   else return fail(MCMCGPU_E_ARG, "unknown option " + k);
   return MCMCGPU_OK;
 }
@@ -296,7 +298,7 @@ static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* re
     a.P = m->pack; a.family = m->family;
     for (int i = 0; i < 4; i++) a.hyper[i] = m->k1_hyper[i];
     a.q = q; a.part = part; a.Cp = Cp; a.nsplit = nsplit; a.need_grad = need_grad ? 1 : 0;
-    a.need_ll = need_ll; a.phase = phase; a.remaining = remaining;
+    a.need_ll = need_ll; a.phase = phase; a.remaining = remaining; a.debug = (int32_t)m->ctx->k1_debug;
     CU(k1_launch(a, st));
     if (m->row_sharded) {
       const NcclApi* api = nccl_api(nullptr);
@@ -599,6 +601,10 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       launches++;
       if (is_ram) { CU(launch_ram(W, false, st)); launches++; }
     }
+    // completion polls: when one wave is long (>= ~0.5 ms of likelihood work) poll after every wave, so that no empty
+    // wave is ever launched (and none is counted in n_waves / eval_ms); for tiny waves poll every 8
+    int64_t poll = c->poll_every;
+    if (poll <= 0) poll = (m->is_regression && (double)m->N * (double)m->d * (double)R->Cp >= 5e9) ? 1 : 8;
     std::vector<cudaEvent_t> evs;
     for (;;) {
       const double* pp; int ns;
@@ -615,7 +621,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       waves++;
       first = false;
       if (known >= 0) { if (waves >= known) break; }
-      else if (waves % c->poll_every == 0) {
+      else if (waves % poll == 0) {
         CU(cudaMemcpyAsync(c->h_remaining, R->remaining, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (*c->h_remaining == 0) break;

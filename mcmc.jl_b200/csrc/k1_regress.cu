@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   double* betas = reinterpret_cast<double*>(smem_raw);
   double* tiles = betas + K1_CHAINS * S;
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)K1_STAGES * TILE_D);
-  uint64_t* empty = full + K1_STAGES;
+  unsigned int* released = reinterpret_cast<unsigned int*>(full + K1_STAGES);   // warps that have finished with a slot
 
   if (a.remaining && *a.remaining == 0) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   const uint32_t tile_bytes = (uint32_t)(TILE_D * sizeof(double));
 
   if (tid == 0) {
-    for (int s = 0; s < K1_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], K1_WARPS); }
+    for (int s = 0; s < K1_STAGES; s++) { mbar_init(&full[s], 1); released[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // beta tile: betas[c][j] = q[j][chain0 + c] (zero-padded features)
@@ -229,6 +229,12 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   const int row2a = pi8(2 * t), row2b = pi8(2 * t + 1);
   const int off2a = row2a * S + g, off2b = row2b * S + g;
 
+  // de-phase the two warps that share a scheduler partition (warps w and w+4): the second half of the CTA starts half a
+  // tile late, so that one of them is in its DMMA phases while the other is in the (latency-bound) link epilogue
+  if (a.debug >= 100 && warp >= K1_WARPS / 2) {
+    const long long t_end = clock64() + (long long)a.debug;
+    while (clock64() < t_end) { }
+  }
   for (int64_t it = 0; it < nt; it++) {
     const int slot = (int)(it % K1_STAGES);
     const uint32_t par = (uint32_t)((it / K1_STAGES) & 1);
@@ -260,14 +266,16 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
         for (int s = 0; s < 2; s++) {
           const int lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);   // local row of accumulator column 2t+s
           const double y = ys[lr];
-          LinkOut o = link<FAM>(acc[n][s], y, hy, need_ll);
+          LinkOut o;
+          if (a.debug == 1) { o.ll1 = 0.0; o.ll2 = 0.0; o.bad = false; o.r = acc[n][s] * y; }
+          else o = link<FAM>(acc[n][s], y, hy, need_ll);
           const bool valid = (rowbase + lr) < N;
           if (valid) { ll1 += o.ll1; ll2 += o.ll2; nbad += o.bad ? 1 : 0; }
           acc[n][s] = o.r;    // rows >= N have X == 0, so their r never reaches G
         }
       }
       // ---- phase 2: G += r^T X ----
-      if (a.need_grad) {
+      if (a.need_grad && a.debug != 2) {
         // consecutive DMMAs go to different accumulators (DK independent chains)
 #pragma unroll
         for (int n = 0; n < NR; n++) {
@@ -284,14 +292,20 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
         }
       }
     }
-    // release the slot; thread 0 refills it with tile it + STAGES once every warp has released
+    // release the slot: the LAST warp to finish with it issues the refill (tile it + STAGES), so no warp ever waits
+    // for the slowest one just to start a copy
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[slot]);
-    if (tid == 0 && it + K1_STAGES < nt) {
-      mbar_wait(&empty[slot], par);
-      mbar_expect_tx(&full[slot], tile_bytes);
-      bulk_g2s(tiles + (size_t)slot * TILE_D, a.P.tiles + (t0 + it + K1_STAGES) * a.P.tile_doubles, tile_bytes,
-               &full[slot]);
+    if (lane == 0) {
+      const unsigned int prev = atomicAdd(&released[slot], 1u);
+      if (prev == K1_WARPS - 1) {
+        released[slot] = 0;
+        if (it + K1_STAGES < nt) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy overwrite
+          mbar_expect_tx(&full[slot], tile_bytes);
+          bulk_g2s(tiles + (size_t)slot * TILE_D, a.P.tiles + (t0 + it + K1_STAGES) * a.P.tile_doubles, tile_bytes,
+                   &full[slot]);
+        }
+      }
     }
   }
 

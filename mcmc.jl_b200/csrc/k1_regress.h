@@ -35,6 +35,7 @@ struct K1Args {
   const uint8_t* need_ll;  // [Cp] per-chain flag, or null = all chains need the log-likelihood
   const int32_t* phase;    // [Cp] per-chain phase (PH_DONE chains are skipped), or null
   const int32_t* remaining; // device counter of unfinished chains, or null
+  int32_t debug;           // experiments only: 1 = skip the link function (r = eta), 2 = skip phase 2
 };
 
 cudaError_t k1_pack(K1Pack& P, const double* dX /* N x d col-major, device */, const double* dy, int64_t N, int64_t d,

@@ -12,6 +12,7 @@ splits = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 ctx = capi.Context(0)
 ctx.set_option("time_eval", 1)
 if splits: ctx.set_option("force_splits", splits)
+if os.environ.get("K1_DEBUG"): ctx.set_option("k1_debug", int(os.environ["K1_DEBUG"]))
 r = np.random.default_rng(4)
 t0 = time.time()
 X = r.standard_normal((d, N)).T  # F-ordered view
