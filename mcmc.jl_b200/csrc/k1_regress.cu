@@ -229,12 +229,6 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   const int row2a = pi8(2 * t), row2b = pi8(2 * t + 1);
   const int off2a = row2a * S + g, off2b = row2b * S + g;
 
-  // de-phase the two warps that share a scheduler partition (warps w and w+4): the second half of the CTA starts half a
-  // tile late, so that one of them is in its DMMA phases while the other is in the (latency-bound) link epilogue
-  if (a.debug >= 100 && warp >= K1_WARPS / 2) {
-    const long long t_end = clock64() + (long long)a.debug;
-    while (clock64() < t_end) { }
-  }
   for (int64_t it = 0; it < nt; it++) {
     const int slot = (int)(it % K1_STAGES);
     const uint32_t par = (uint32_t)((it / K1_STAGES) & 1);
