@@ -79,6 +79,42 @@ __device__ __forceinline__ double erfcx_fast(double u) {       // requires 0 <= 
   return p;
 }
 
+// ---- lean, branch-free exp and reciprocal for the logistic link (|x| < 700) --------------------------------------
+// The link epilogue shares the FP64 pipe with DMMA, so every FP64 instruction counts; libm's exp and the IEEE division
+// also carry slow-path branches that keep the compiler from interleaving the independent elements of a thread.
+//   exp(x) = 2^k * (e^(r/2))^2,  k = rint(x*log2 e) (magic-number add), r = x - k*ln2 (hi/lo), degree-11 Taylor in r/2
+//   (truncation 2e-18; measured against mpmath: 3.3e-16 relative);  1/d by rcp.approx + two Newton steps (<= 2e-16).
+__device__ __forceinline__ double exp_lean(double x) {
+  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+  const int k = __double2loint(t);
+  const double kf = t - 6755399441055744.0;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  const double h = 0.5 * r;
+  double p = 2.50521083854417187751e-08;            // 1/11!
+  p = fma(p, h, 2.75573192239858906526e-07);        // 1/10!
+  p = fma(p, h, 2.75573192239858906526e-06);        // 1/9!
+  p = fma(p, h, 2.48015873015873015873e-05);        // 1/8!
+  p = fma(p, h, 1.98412698412698412698e-04);        // 1/7!
+  p = fma(p, h, 1.38888888888888888889e-03);        // 1/6!
+  p = fma(p, h, 8.33333333333333333333e-03);        // 1/5!
+  p = fma(p, h, 4.16666666666666666667e-02);        // 1/4!
+  p = fma(p, h, 1.66666666666666666667e-01);        // 1/3!
+  p = fma(p, h, 0.5);
+  p = fma(p, h, 1.0);
+  p = fma(p, h, 1.0);
+  const double e = p * p;
+  return __hiloint2double(__double2hiint(e) + (k << 20), __double2loint(e));   // * 2^k, |k| <= 1010: stays normal
+}
+__device__ __forceinline__ double rcp_lean(double d) {     // d in [1, 1e305]
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  double e = fma(-d, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-d, y, 1.0);
+  return fma(y, e, y);
+}
+
 // ---- link functions: (eta, y) -> loglik term(s) and r = d loglik / d eta ----------------------
 struct LinkOut { double ll1, ll2, r; bool bad; };
 
@@ -254,18 +290,62 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
         }
       }
       // ---- epilogue: link function on this lane's 2*NR (row, chain) elements ----
+      bool done = false;
+      if (FAM == MCMCGPU_FAM_LOGISTIC && a.debug == 0) {
+        // all 2*NR elements stage by stage, so their dependency chains interleave.  The same arithmetic is used whether
+        // or not the log-likelihood is wanted (need_ll is a per-WARP flag: a chain's numbers must not depend on the
+        // phase of its neighbours, or sharding / stepwise execution would change the draws)
+        double xv[2 * NR], yv[2 * NR];
+        bool fast = true;
 #pragma unroll
-      for (int n = 0; n < NR; n++) {
+        for (int n = 0; n < NR; n++)
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
-          const int lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);   // local row of accumulator column 2t+s
-          const double y = ys[lr];
-          LinkOut o;
-          if (a.debug == 1) { o.ll1 = 0.0; o.ll2 = 0.0; o.bad = false; o.r = acc[n][s] * y; }
-          else o = link<FAM>(acc[n][s], y, hy, need_ll);
-          const bool valid = (rowbase + lr) < N;
-          if (valid) { ll1 += o.ll1; ll2 += o.ll2; nbad += o.bad ? 1 : 0; }
-          acc[n][s] = o.r;    // rows >= N have X == 0, so their r never reaches G
+          for (int s = 0; s < 2; s++) {
+            const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+            xv[i] = hy[1] * acc[n][s];
+            yv[i] = ys[lr];
+            fast = fast && ((__double2hiint(xv[i]) & 0x7fffffff) < 0x4085E000);   // |x| < 700 and not NaN (integer compare)
+          }
+        if (fast) {
+          double ev[2 * NR], pv[2 * NR];
+#pragma unroll
+          for (int i = 0; i < 2 * NR; i++) ev[i] = exp_lean(xv[i]);
+#pragma unroll
+          for (int i = 0; i < 2 * NR; i++) pv[i] = rcp_lean(1.0 + ev[i]);
+#pragma unroll
+          for (int n = 0; n < NR; n++)
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+              const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+              const bool y1 = (yv[i] != 0.0);
+              // support: log(p) is finite for |x| < 700; log(1 - p) is finite unless 1 + e rounds to 1 (x <= ln 2^-53)
+              const bool bad = !y1 && (xv[i] <= -36.736800569677101);
+              const bool valid = (rowbase + lr) < N;
+              if (valid) nbad += bad ? 1 : 0;
+              acc[n][s] = y1 ? (-hy[1]) * (ev[i] * pv[i]) : hy[1] * pv[i];
+              ev[i] = valid ? (y1 ? pv[i] : 1.0 - pv[i]) : 1.0;                // Bernoulli: p1, or p0 = 1 - p1 by subtraction
+            }
+          if (need_ll) {                                                        // warp-uniform; kept out of the straight-line code above
+#pragma unroll
+            for (int i = 0; i < 2 * NR; i++) ll1 += log(ev[i]);                 // padded rows contribute log(1) = 0
+          }
+          done = true;
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int n = 0; n < NR; n++) {
+#pragma unroll
+          for (int s = 0; s < 2; s++) {
+            const int lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);   // local row of accumulator column 2t+s
+            const double y = ys[lr];
+            LinkOut o;
+            if (a.debug == 1) { o.ll1 = 0.0; o.ll2 = 0.0; o.bad = false; o.r = acc[n][s] * y; }
+            else o = link<FAM>(acc[n][s], y, hy, need_ll);
+            const bool valid = (rowbase + lr) < N;
+            if (valid) { ll1 += o.ll1; ll2 += o.ll2; nbad += o.bad ? 1 : 0; }
+            acc[n][s] = o.r;    // rows >= N have X == 0, so their r never reaches G
+          }
         }
       }
       // ---- phase 2: G += r^T X ----
