@@ -332,6 +332,48 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
           done = true;
         }
       }
+      if (FAM == MCMCGPU_FAM_PROBIT && a.debug == 0) {
+        // binary responses with |eta| < 36.7 (the only case met in practice): stage by stage over the 2*NR elements, with the
+        // table-driven erfcx, the lean exp and reciprocal; the log is skipped when no chain of the warp needs the value
+        double zv[2 * NR], uv[2 * NR];
+        bool fast = true;
+#pragma unroll
+        for (int n = 0; n < NR; n++)
+#pragma unroll
+          for (int s = 0; s < 2; s++) {
+            const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+            const double y = ys[lr];
+            zv[i] = (y == 1.0) ? acc[n][s] : -acc[n][s];
+            uv[i] = fabs(zv[i]) * MG_SQRT1_2;
+            fast = fast && (y == 1.0 || y == 0.0) && (uv[i] < (double)ERFCX_UMAX);   // NaN fails the comparison
+          }
+        if (fast) {
+          double exv[2 * NR], e2v[2 * NR];
+#pragma unroll
+          for (int i = 0; i < 2 * NR; i++) exv[i] = erfcx_fast(uv[i]);
+#pragma unroll
+          for (int i = 0; i < 2 * NR; i++) e2v[i] = exp_lean(-(uv[i] * uv[i]));      // -u^2 > -676
+#pragma unroll
+          for (int n = 0; n < NR; n++)
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+              const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+              const bool neg = zv[i] < 0.0, y1 = (ys[lr] == 1.0), valid = (rowbase + lr) < N;
+              const double c = 0.5 * e2v[i] * exv[i];                               // tail mass
+              const double omc = 1.0 - c;
+              // phi(z)/Phi(z): sqrt(2/pi)/erfcx(u) for z < 0, phi(z)/(1 - c) otherwise
+              const double w = (neg ? 0.79788456080286535588 : 0.39894228040143267794 * e2v[i]) * rcp_lean(neg ? exv[i] : omc);
+              acc[n][s] = y1 ? w : -w;
+              e2v[i] = valid ? (neg ? c : omc) : 1.0;                               // Phi(z); padded rows give log(1) = 0
+              uv[i] = y1 ? 1.0 : 0.0;
+            }
+          if (need_ll) {
+#pragma unroll
+            for (int i = 0; i < 2 * NR; i++) { const double l = log(e2v[i]); ll1 += (uv[i] != 0.0) ? l : 0.0; ll2 += (uv[i] != 0.0) ? 0.0 : l; }
+          }
+          done = true;
+        }
+      }
       if (!done) {
 #pragma unroll
         for (int n = 0; n < NR; n++) {
