@@ -27,3 +27,21 @@ def test_seqmc_population_sharded_over_two_gpus():
            "--master-port", "29613", os.path.join(ROOT, "tests", "multigpu_seqmc.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "SEQMC_SHARDED_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+def test_bench_native_arm_small():
+    """bench.py end to end on a reduced cfg4 (the JSON contract keys of the native arm)"""
+    import json
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--N", "40000", "--chains", "512", "--steps", "2", "--warmup", "3",
+                        "--cpu-steps", "1"], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stderr[-3000:]
+    lines = [l for l in p.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and p.stdout.strip() == lines[0], "stdout must carry exactly the JSON line"
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline", "min_ess_per_s"):
+        assert key in line, key
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0 and line["gpu_launches"] > 0
+    rf = line["roofline"]
+    assert rf["bound"] == "tensor" and 0 < rf["frac"] < 1.2 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
