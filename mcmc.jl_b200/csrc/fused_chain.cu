@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
       nev++;
       double ratio = plt - lt;                                                  // :62
       bool acc = ratio > 0;                                                     // :63 `ratio > 0 || ratio > log(rand())`
-      if (!acc) acc = ratio > log(draw_uniform(i));
+      if (!acc) acc = ratio > log_lean_normal(draw_uniform(i));
       if (acc) {
         store(i, prop, plt, pg, false, true, CUDART_NAN, 0);
 #pragma unroll
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
       for (int j = 0; j < D; j++) if (j < d) { double t = mean[j] - pars[j]; qon += -(t * t) / (2.0 * h) - lc; }
       double ratio = plt + qon - lt - qno;                                      // :107
       bool acc = ratio > 0;                                                     // :108
-      if (!acc) acc = ratio > log(draw_uniform(i));
+      if (!acc) acc = ratio > log_lean_normal(draw_uniform(i));
       if (acc) {
         store(i, prop, plt, pg, true, true, h, 0);
 #pragma unroll
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
       double tr = 0.0;
 #pragma unroll
       for (int a = 0; a < D; a++) if (a < d) tr += Sm[a][a];                    // "scale" => trace(S)
-      bool acc = ratio > 0 || ratio > log(draw_uniform(i));                     // :64
+      bool acc = ratio > 0 || ratio > log_lean_normal(draw_uniform(i));                // :64
       if (acc) {
         store(i, prop, plt, pg, false, true, tr, 0);
 #pragma unroll

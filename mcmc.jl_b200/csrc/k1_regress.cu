@@ -80,64 +80,6 @@ __device__ __forceinline__ double erfcx_fast(double u) {       // requires 0 <= 
   return p;
 }
 
-// ---- lean, branch-free exp and reciprocal for the logistic link (|x| < 700) --------------------------------------
-// The link epilogue shares the FP64 pipe with DMMA, so every FP64 instruction counts; libm's exp and the IEEE division
-// also carry slow-path branches that keep the compiler from interleaving the independent elements of a thread.
-//   exp(x) = 2^k * (e^(r/2))^2,  k = rint(x*log2 e) (magic-number add), r = x - k*ln2 (hi/lo), degree-11 Taylor in r/2
-//   (truncation 2e-18; measured against mpmath: 3.3e-16 relative);  1/d by rcp.approx + two Newton steps (<= 2e-16).
-__device__ __forceinline__ double exp_lean(double x) {
-  const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
-  const int k = __double2loint(t);
-  const double kf = t - 6755399441055744.0;
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
-  const double h = 0.5 * r;
-  double p = 2.50521083854417187751e-08;            // 1/11!
-  p = fma(p, h, 2.75573192239858906526e-07);        // 1/10!
-  p = fma(p, h, 2.75573192239858906526e-06);        // 1/9!
-  p = fma(p, h, 2.48015873015873015873e-05);        // 1/8!
-  p = fma(p, h, 1.98412698412698412698e-04);        // 1/7!
-  p = fma(p, h, 1.38888888888888888889e-03);        // 1/6!
-  p = fma(p, h, 8.33333333333333333333e-03);        // 1/5!
-  p = fma(p, h, 4.16666666666666666667e-02);        // 1/4!
-  p = fma(p, h, 1.66666666666666666667e-01);        // 1/3!
-  p = fma(p, h, 0.5);
-  p = fma(p, h, 1.0);
-  p = fma(p, h, 1.0);
-  const double e = p * p;
-  return __hiloint2double(__double2hiint(e) + (k << 20), __double2loint(e));   // * 2^k, |k| <= 1010: stays normal
-}
-__device__ __forceinline__ double rcp_lean(double d) {     // d in [1, 1e305]
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-  double e = fma(-d, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-d, y, 1.0);
-  return fma(y, e, y);
-}
-
-// log(x) for x in the normal positive range, after fdlibm's e_log.c (argument reduction to sqrt(2)/2 < m < sqrt(2),
-// s = f/(2+f), degree-7 even/odd polynomial in s^2; 1.4e-16 relative against mpmath), the division replaced by
-// rcp_lean; zero, denormal, negative, infinite and NaN arguments go to libm's log (they decide the support test).
-__device__ __forceinline__ double log_lean(double x) {
-  int hx = __double2hiint(x);
-  if ((unsigned)(hx - 0x00100000) >= (unsigned)(0x7ff00000 - 0x00100000)) return log(x);
-  int k = (hx >> 20) - 1023;
-  hx &= 0x000fffff;
-  const int i = (hx + 0x95f64) & 0x100000;
-  k += i >> 20;
-  const double m = __hiloint2double(hx | (i ^ 0x3ff00000), __double2loint(x));
-  const double f = m - 1.0;
-  const double sq = f * rcp_lean(2.0 + f);
-  const double dk = (double)k;
-  const double z = sq * sq, w = z * z;
-  const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
-  const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
-  const double R = t2 + t1;
-  const double hfsq = 0.5 * f * f;
-  return dk * 6.93147180369123816490e-01 - ((hfsq - fma(sq, hfsq + R, dk * 1.90821492927058770002e-10)) - f);
-}
-
 // ---- probit link from tables: F(z) = log Phi(z), W(z) = phi(z)/Phi(z), |z| < 36.9 (tools/gen_probit_table.py) ----
 // one round-to-nearest index (magic-number add, no conversions) and a degree-9 Horner per function: ~13 FP64
 // instructions each instead of erfcx + exp + reciprocal + log (~70); relative error 2e-16 for z < 0, absolute 1e-16 for z >= 0

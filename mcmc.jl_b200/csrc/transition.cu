@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
   } else if (ph == PH_RWM) {
     // RWM.jl:62-70 (and RAM.jl:63-71, the same Metropolis test)
     double ratio = lt_q - W.cur_lt[c];
-    bool acc = ratio > 0 || ratio > log(uniform(i));
+    bool acc = ratio > 0 || ratio > log_lean_normal(uniform(i));
     if (acc) {
       for (int64_t j = 0; j < d; j++) W.cur_pars[j * Cp + c] = q[j * Cp + c];
       W.cur_lt[c] = lt_q;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       double t2 = mean2 - pj;   qon += -(t2 * t2) / (2.0 * h) - lc;   // :105
     }
     double ratio = lt_q + qon - W.cur_lt[c] - qno;                    // :107
-    bool acc = ratio > 0 || ratio > log(uniform(i));                  // :108
+    bool acc = ratio > 0 || ratio > log_lean_normal(uniform(i));                  // :108
     if (acc) {
       for (int64_t j = 0; j < d; j++) {
         W.cur_pars[j * Cp + c] = q[j * Cp + c];
