@@ -616,3 +616,39 @@ def test_edge_shapes(O, capi, ctx):
             assert np.array_equal(out["samples"][c], ref["samples"])
         run.close()
     dm.close()
+
+
+@pytest.mark.parametrize("fam", ["logistic", "probit"])
+def test_link_functions_over_wide_range(O, capi, ctx, fam):
+    """the kernel's own exp / reciprocal / log / table-driven log Phi and phi/Phi over the whole range of eta, incl. the
+    libm fall-back paths (|eta| >= 36.9 probit, >= 700 logistic).  For the logistic model the reference forms 1 - p by
+    subtraction, so its log-likelihood is ill-conditioned where p -> 1: the tolerance carries that conditioning."""
+    from scipy.special import log_ndtr, expit
+    rng = np.random.default_rng(5)
+    N, d = 4000, 2
+    X = np.column_stack([np.ones(N), np.linspace(-1, 1, N)])
+    y = (rng.random(N) < 0.5).astype(float)
+    hy = (1.0, -1.0) if fam == "logistic" else (10.0,)
+    om, dm = O.Model(fam, d, X, y, hy), capi.DeviceModel(ctx, fam, d, X, y, hy)
+    scales = [0.5, 3.0, 10.0, 25.0, 34.0] + ([36.0, 40.0, 300.0] if fam == "probit" else [])
+    B = np.array([[rng.normal(0, 0.3), s] for s in scales])            # eta spans [-s, s]
+    lt, g = dm.logtarget_grad(B)
+    for c, b in enumerate(B):
+        olt, og = om.evalallg(b)
+        eta = X @ b
+        if fam == "logistic":
+            p = expit(eta)
+            cond = np.sum(np.finfo(float).eps / np.minimum(np.where(y == 1, p, 1 - p), 1.0))   # |d log(1-p)| for a last-bit change of p
+            assert abs(lt[c] - olt) <= 1e-12 * abs(olt) + 4 * cond, (c, lt[c], olt)
+            assert np.all(np.abs(g[c] - og) <= 1e-11 * np.abs(X).sum(0) + 4 * cond), c
+        else:
+            truth = np.sum(np.where(y == 1, log_ndtr(eta), log_ndtr(-eta))) - 0.5 * (d * np.log(2 * np.pi) + d * np.log(100.0)) - 0.5 * (b @ b) / 100.0
+            assert abs(lt[c] - olt) <= 1e-12 * abs(olt) and abs(lt[c] - truth) <= 1e-11 * abs(truth), (c, lt[c], olt, truth)
+            assert np.all(np.abs(g[c] - og) <= 1e-11 * (np.abs(X) * np.maximum(1.0, np.abs(eta))[:, None]).sum(0)), c
+    # far beyond every fast path: logistic saturates to the support boundary, the sampler must see (-Inf, zeros)
+    if fam == "logistic":
+        lt2, g2 = dm.logtarget_grad(np.array([[0.0, 800.0], [0.0, 40.0]]))
+        o0, o1 = om.evalallg(np.array([0.0, 800.0])), om.evalallg(np.array([0.0, 40.0]))
+        assert lt2[0] == o0[0] == -np.inf and np.all(g2[0] == 0)
+        assert (lt2[1] == -np.inf) == (o1[0] == -np.inf)
+    dm.close()
