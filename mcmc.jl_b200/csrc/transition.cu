@@ -35,16 +35,24 @@ __device__ __forceinline__ EvalFin finalize_eval(const ModelDev& M, const double
   const int64_t d = M.d;
   if (M.family == MCMCGPU_FAM_LINEAR || M.family == MCMCGPU_FAM_LOGISTIC) {
     const double psd = M.hyper[0];
-    const double lsd = log(psd);
-    double s = 0.0;
-    for (int64_t j = 0; j < d; j++) {   // vars ~ Normal(0, prior_sd)
-      double z = (q[j * Cp + c] - 0.0) / psd;
-      s += -(MG_LN_SQRT_2PI + 0.5 * z * z + lsd);
-    }
-    double acc = 0.0 + s;
-    f.oos = !isfinite(acc);
     double bad = sum_part(part, nsplit, d + 1, d, Cp, c);
-    if (bad > 0.0) f.oos = true;
+    f.oos = bad > 0.0;
+    double acc = 0.0;
+    if (want_lt) {
+      // vars ~ Normal(0, prior_sd).  On interior leapfrogs the prior value is not needed and its only other role -- a
+      // non-finite prior puts the point out of support -- is covered by the likelihood's support count: a non-finite
+      // beta makes every eta NaN.  (A finite |beta_j| > 1e154, whose square overflows, is the one case left to the
+      // trajectory's last evaluation.)
+      const double lsd = log(psd);
+      double s = 0.0;
+#pragma unroll 4
+      for (int64_t j = 0; j < d; j++) {
+        double z = (q[j * Cp + c] - 0.0) / psd;
+        s += -(MG_LN_SQRT_2PI + 0.5 * z * z + lsd);
+      }
+      acc = 0.0 + s;
+      if (!isfinite(acc)) f.oos = true;
+    }
     if (want_lt) {
       double ll = sum_part(part, nsplit, d, d, Cp, c);
       double acc2 = acc + ll;
