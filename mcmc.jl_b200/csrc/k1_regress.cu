@@ -490,6 +490,14 @@ int k1_choose_splits(const K1Pack& P, int64_t Cp) {
     if (waves < 1.0) eff = waves;              // not enough CTAs to fill the machine once
     if (eff > beste + 0.02) { beste = eff; best = (int)s; }   // prefer fewer splits unless clearly better
   }
+  // small problems: when even the best choice leaves SMs idle, latency matters more than amortising the prologue --
+  // spread the rows over as many CTAs as there are free slots (down to one tile per CTA)
+  if (ctiles * best < slots) {
+    int64_t s = slots / ctiles;
+    if (s > P.ntiles) s = P.ntiles;
+    if (s > 512) s = 512;
+    if (s > best) best = (int)s;
+  }
   return best;
 }
 

@@ -152,3 +152,26 @@ def test_dsl_recogniser():
         recognise("y = abs(x)\n y ~ Gamma(2, 3)", dict(x=0.0))
     with pytest.raises(ValueError):
         recognise(lin, dict(vars=np.zeros(3), X=X))                                # Y missing
+
+
+def _build_c_demo(tmp_path):
+    import subprocess
+    exe = os.path.join(str(tmp_path), "c_abi_demo")
+    pkg = os.path.join(ROOT, "mcmc.jl_b200")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_demo.c"),
+                           "-L" + pkg, "-lmcmcgpu", "-Wl,-rpath," + pkg, "-lm", "-o", exe])
+    return exe
+
+
+def test_struct_layouts_match_the_header(capi, tmp_path):
+    """the ctypes Structures of the binding have exactly the C layout of include/mcmcgpu.h (sizes and field offsets)"""
+    import subprocess
+    out = subprocess.check_output([_build_c_demo(tmp_path), "layout"], text=True).strip().splitlines()
+    for line, st in zip(out, (capi.SamplerCfg, capi.RunnerCfg, capi.RunInfo)):
+        toks = line.split()
+        import ctypes
+        assert int(toks[1]) == ctypes.sizeof(st), line
+        fields = dict(zip(toks[2::2], map(int, toks[3::2])))
+        assert set(fields) == {n for n, _ in st._fields_}, line
+        for name, off in fields.items():
+            assert getattr(st, name).offset == off, (st.__name__, name)

@@ -45,3 +45,11 @@ def test_bench_native_arm_small():
     rf = line["roofline"]
     assert rf["bound"] == "tensor" and 0 < rf["frac"] < 1.2 and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] > 0
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """examples/c_abi_demo.c: the library driven from C exactly as a Julia ccall would (no Python in the loop)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_capi_and_host import _build_c_demo
+    p = subprocess.run([_build_c_demo(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "C_ABI_DEMO ok" in p.stdout, p.stdout + p.stderr
