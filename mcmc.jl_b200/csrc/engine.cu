@@ -37,6 +37,7 @@ struct mcmcgpu_ctx {
   int64_t poll_every = 0;     // option: waves between completion polls (HMCDA / tuned HMC); 0 = automatic
   int64_t force_splits = 0;   // option: override K1 row splits
   int64_t k1_debug = 0;       // option (experiments): see K1Args::debug
+  int64_t use_graphs = 1;     // option: replay fixed-length wave loops from a CUDA graph
   int32_t* h_remaining = nullptr;  // pinned
 };
 
@@ -169,6 +170,7 @@ int32_t mcmcgpu_set_option(mcmcgpu_ctx* c, const char* key, int64_t value) {
   else if (k == "poll_every") c->poll_every = value < 0 ? 0 : value;
   else if (k == "force_splits") c->force_splits = value;
   else if (k == "k1_debug") c->k1_debug = value;
+  else if (k == "use_graphs") c->use_graphs = value;
   else return fail(MCMCGPU_E_ARG, "unknown option " + k);
   return MCMCGPU_OK;
 }
@@ -300,6 +302,12 @@ static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* re
     a.q = q; a.part = part; a.Cp = Cp; a.nsplit = nsplit; a.need_grad = need_grad ? 1 : 0;
     a.need_ll = need_ll; a.phase = phase; a.remaining = remaining; a.debug = (int32_t)m->ctx->k1_debug;
     CU(k1_launch(a, st));
+    if (!m->row_sharded && nsplit > 4 && red) {
+      // many row splits (small problems spread over the whole machine): fold them with a parallel pass, in split order,
+      // so the per-chain transition thread does not walk nsplit partial buffers serially
+      CU(launch_reduce_splits(part, nsplit, m->d + 2, Cp, red, st));
+      *part_out = red; *nsplit_out = 1;
+    }
     if (m->row_sharded) {
       const NcclApi* api = nccl_api(nullptr);
       if (!api || !m->ctx->comm) return fail(MCMCGPU_E_COMM, "communicator not initialised");
@@ -476,7 +484,7 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     R->nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp)) : 1;
     RCU(R->alloc(&R->q, (size_t)(d * Cp)));
     RCU(R->alloc(&R->part, (size_t)(R->nsplit * (d + 2) * Cp)));
-    if (m->row_sharded) RCU(R->alloc(&R->red, (size_t)((d + 2) * Cp)));
+    if (m->row_sharded || R->nsplit > 4) RCU(R->alloc(&R->red, (size_t)((d + 2) * Cp)));
     RCU(R->alloc(&R->cur_pars, (size_t)(d * Cp)));
     RCU(R->alloc(&R->cur_grad, (size_t)(d * Cp)));
     RCU(R->alloc(&R->cur_lt, (size_t)Cp));
@@ -606,7 +614,38 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     int64_t poll = c->poll_every;
     if (poll <= 0) poll = (m->is_regression && (double)m->N * (double)m->d * (double)R->Cp >= 5e9) ? 1 : 8;
     std::vector<cudaEvent_t> evs;
+    bool graph_done = false;
     for (;;) {
+      if (known >= 0 && waves >= known) break;
+      // launch-bound regime (small N x C): when the number of waves is known, replay them from a CUDA graph
+      // (captured once: GRAPH_WAVES x [likelihood, transition]) instead of 2+ stream launches per wave
+      if (!graph_done && !first && known >= 0 && !c->time_eval && !m->row_sharded && c->use_graphs) {
+        graph_done = true;
+        const int64_t GW = 32;
+        const int64_t todo = known - waves;
+        if (todo >= 2 * GW) {
+          cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
+          CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+          int crc = MCMCGPU_OK;
+          for (int64_t g = 0; g < GW && crc == MCMCGPU_OK; g++) {
+            const double* pp; int ns;
+            crc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad, R->need_ll, R->phase, R->remaining, &pp, &ns);
+            W.part = pp; W.nsplit = ns;
+            if (crc == MCMCGPU_OK && launch_transition(W, st) != cudaSuccess) crc = MCMCGPU_E_CUDA;
+            if (crc == MCMCGPU_OK && is_ram && launch_ram(W, false, st) != cudaSuccess) crc = MCMCGPU_E_CUDA;
+          }
+          cudaError_t ce = cudaStreamEndCapture(st, &graph);
+          if (crc != MCMCGPU_OK || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(MCMCGPU_E_CUDA, "CUDA graph capture of the wave loop failed"); }
+          CU(cudaGraphInstantiate(&gexec, graph, 0));
+          const int64_t reps = todo / GW;
+          for (int64_t rp = 0; rp < reps; rp++) CU(cudaGraphLaunch(gexec, st));
+          waves += reps * GW;
+          launches += reps * GW * (2 + (is_ram ? 1 : 0));
+          CU(cudaStreamSynchronize(st));
+          cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph);
+        }
+      }
+      if (known >= 0 && waves >= known) break;
       const double* pp; int ns;
       cudaEvent_t a0 = nullptr, a1 = nullptr;
       if (c->time_eval) { CU(cudaEventCreate(&a0)); CU(cudaEventCreate(&a1)); CU(cudaEventRecord(a0, st)); }
