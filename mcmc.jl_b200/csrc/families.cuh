@@ -21,12 +21,21 @@ struct Family<MCMCGPU_FAM_NORMAL_FN, D> {
     for (int j = 0; j < D; j++) g[j] = -2.0 * v[j];
     return -s;
   }
+  // interior leapfrogs: only the gradient is used (HMC.jl:97 evaluates both; the value is never read)
+  static __device__ __forceinline__ double gradonly(const ModelDev&, const double*, int, const double (&v)[D], double (&g)[D]) {
+#pragma unroll
+    for (int j = 0; j < D; j++) g[j] = -2.0 * v[j];
+    return CUDART_NAN;
+  }
 };
 
 // README.md:67-72 `v ~ Normal(mu, sigma)`; gradient rule MCMCDerivRules.jl:57; LLAcc check
 // AccumulatorDerivRules.jl:10-20 => (-Inf, zeros) (modelparser.jl:64-72)
 template <int D>
 struct Family<MCMCGPU_FAM_NORMAL_DSL, D> {
+  static __device__ __forceinline__ double gradonly(const ModelDev& M, const double* x, int d, const double (&v)[D], double (&g)[D]) {
+    return evalallg(M, x, d, v, g);   // the LLAcc support test needs the value
+  }
   static __device__ __forceinline__ double evalallg(const ModelDev& M, const double*, int d, const double (&v)[D],
                                                     double (&g)[D]) {
     const double mu = M.hyper[0], sigma = M.hyper[1];
@@ -48,6 +57,9 @@ struct Family<MCMCGPU_FAM_NORMAL_DSL, D> {
 // README.md:253-259 `y = abs(x); y ~ Normal(mu, sigma)`: abs rule dx += sign(x)*ds, Normal rule MCMCDerivRules.jl:57
 template <int D>
 struct Family<MCMCGPU_FAM_ABS_NORMAL, D> {
+  static __device__ __forceinline__ double gradonly(const ModelDev& M, const double* x, int d, const double (&v)[D], double (&g)[D]) {
+    return evalallg(M, x, d, v, g);   // the LLAcc support test needs the value
+  }
   static __device__ __forceinline__ double evalallg(const ModelDev& M, const double*, int d, const double (&v)[D],
                                                     double (&g)[D]) {
     const double mu = M.hyper[0], sigma = M.hyper[1];
@@ -72,6 +84,9 @@ struct Family<MCMCGPU_FAM_ABS_NORMAL, D> {
 // examples/ornstein.jl:19-27; parameter vector (tau, sigma, mu); series staged in shared memory
 template <int D>
 struct Family<MCMCGPU_FAM_OU, D> {
+  static __device__ __forceinline__ double gradonly(const ModelDev& M, const double* x, int d, const double (&v)[D], double (&g)[D]) {
+    return evalallg(M, x, d, v, g);   // the LLAcc support test needs the value
+  }
   static __device__ __forceinline__ double evalallg(const ModelDev& M, const double* x, int, const double (&v)[D],
                                                     double (&g)[D]) {
     static_assert(D >= 3, "OU has 3 parameters");

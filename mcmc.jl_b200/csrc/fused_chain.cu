@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
         for (int j = 0; j < D; j++) m[j] += (0.5 * g[j]) * eps;
 #pragma unroll
         for (int j = 0; j < D; j++) p[j] += eps * m[j];
-        plt = Family<FAM, D>::evalallg(M, sh_series, d, p, g);
+        if (l + 1 == nLeaps || A.rb) plt = Family<FAM, D>::evalallg(M, sh_series, d, p, g);
+        else Family<FAM, D>::gradonly(M, sh_series, d, p, g);
         nev++;
 #pragma unroll
         for (int j = 0; j < D; j++) m[j] += (0.5 * g[j]) * eps;
