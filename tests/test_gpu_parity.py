@@ -652,3 +652,21 @@ def test_link_functions_over_wide_range(O, capi, ctx, fam):
         assert lt2[0] == o0[0] == -np.inf and np.all(g2[0] == 0)
         assert (lt2[1] == -np.inf) == (o1[0] == -np.inf)
     dm.close()
+
+
+def test_readme_snippet():
+    """the usage example of README.md runs as written"""
+    import mcmc_jl_b200 as mj
+    rng = np.random.default_rng(2)
+    X = np.concatenate([np.ones((1000, 1)), rng.standard_normal((1000, 9))], axis=1)
+    Y = (rng.random(1000) < 1 / (1 + np.exp(-X @ rng.standard_normal(10)))).astype(float)
+    m = mj.model("""vars ~ Normal(0, 1.0)
+                   prob = 1 / (1. + exp(- X * vars))
+                   Y ~ Bernoulli(prob)""", vars=np.zeros(10), gradient=True, X=X, Y=Y)
+    chain = mj.run(m * mj.HMC(2, 0.1) * mj.SerialMC(1000, 10000))
+    batch = mj.run(m * mj.HMCDA(len=0.2) * mj.GPUMC(steps=2000, burnin=1000, nchains=4096, seed=1))
+    acc, ess_min, vbm, (zv, a) = mj.acceptance(chain), mj.ess(batch).min(axis=1), mj.var(chain, vtype="bm"), mj.linearZv(chain)
+    assert 20 < acc <= 100 and ess_min.shape == (4096,) and vbm.shape == (10,) and zv.shape == (9001, 10) and a.shape == (10, 10)
+    assert np.median(mj.acceptance(batch)) > 40 and np.isfinite(batch[7].samples.values).all()
+    assert np.all(zv.var(0) < chain.samples.values.var(0))
+    batch.close()
