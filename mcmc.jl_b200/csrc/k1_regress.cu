@@ -85,6 +85,16 @@ __device__ __forceinline__ double erfcx_fast(double u) {       // requires 0 <= 
 // instructions each instead of erfcx + exp + reciprocal + log (~70); relative error 2e-16 for z < 0, absolute 1e-16 for z >= 0
 __device__ const double probit_F_tab[(PROBIT_DEG + 1) * PROBIT_NINT] = {PROBIT_F_VALUES};
 __device__ const double probit_W_tab[(PROBIT_DEG + 1) * PROBIT_NINT] = {PROBIT_W_VALUES};
+// joint table: one degree-10 polynomial J per interval with J' = the W interpolant and J(0) = F(centre); the simultaneous
+// Horner scheme gives log Phi and phi/Phi from ONE set of coefficient loads (the kernel is load/store-unit bound at small d)
+__device__ const double probit_J_tab[(PROBIT_DEG + 2) * PROBIT_NINT] = {PROBIT_J_VALUES};
+__device__ __forceinline__ void probit_eval_joint(int k, double t, double& f, double& w) {
+  const double* c = probit_J_tab + k;
+  double p = __ldg(c + (PROBIT_DEG + 1) * PROBIT_NINT), dp = 0.0;
+#pragma unroll
+  for (int j = PROBIT_DEG; j >= 0; j--) { dp = fma(dp, t, p); p = fma(p, t, __ldg(c + j * PROBIT_NINT)); }
+  f = p; w = dp;
+}
 __device__ __forceinline__ void probit_index(double z, int& k, double& t) {
   const double m = fma(z, (double)PROBIT_INV_W, 6755399441055744.0 + (double)(PROBIT_ZMAX * PROBIT_INV_W));
   k = __double2loint(m);
@@ -333,25 +343,45 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
         if (fast) {
 #pragma unroll
           for (int i = 0; i < 2 * NR; i++) probit_index(zv[i], kv[i], tv[i]);
-#pragma unroll
-          for (int n = 0; n < NR; n++)
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-              const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-              const double w = probit_eval(probit_W_tab, kv[i], tv[i]);
-              acc[n][s] = (ys[lr] == 1.0) ? w : -w;
-            }
-          if (need_ll) {
+          if (a.need_ll == nullptr && a.need_grad) {
+            // every chain needs value and gradient on every wave of this run (MALA; the first wave of any run):
+            // both from the joint table, one set of coefficient loads
 #pragma unroll
             for (int n = 0; n < NR; n++)
 #pragma unroll
               for (int s = 0; s < 2; s++) {
                 const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-                const double l = ((rowbase + lr) < N) ? probit_eval(probit_F_tab, kv[i], tv[i]) : 0.0;
+                double l, w;
+                probit_eval_joint(kv[i], tv[i], l, w);
                 const bool y1 = (ys[lr] == 1.0);
+                acc[n][s] = y1 ? w : -w;
+                if ((rowbase + lr) >= N) l = 0.0;
                 ll1 += y1 ? l : 0.0;
                 ll2 += y1 ? 0.0 : l;
               }
+          } else {
+            if (a.need_grad) {
+#pragma unroll
+              for (int n = 0; n < NR; n++)
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                  const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+                  const double w = probit_eval(probit_W_tab, kv[i], tv[i]);
+                  acc[n][s] = (ys[lr] == 1.0) ? w : -w;
+                }
+            }
+            if (need_ll) {
+#pragma unroll
+              for (int n = 0; n < NR; n++)
+#pragma unroll
+                for (int s = 0; s < 2; s++) {
+                  const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+                  const double l = ((rowbase + lr) < N) ? probit_eval(probit_F_tab, kv[i], tv[i]) : 0.0;
+                  const bool y1 = (ys[lr] == 1.0);
+                  ll1 += y1 ? l : 0.0;
+                  ll2 += y1 ? 0.0 : l;
+                }
+            }
           }
           done = true;
         }

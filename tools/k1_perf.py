@@ -23,7 +23,7 @@ y = (r.random(N) < 1 / (1 + np.exp(-eta))).astype(float)
 print("gen", time.time() - t0)
 hy = {"logistic": (1.0, -1.0), "probit": (10.0,), "linear": (1.0, 1.0)}[fam]
 t0 = time.time(); dm = capi.DeviceModel(ctx, fam, d, X, y, hy); print("model create", time.time() - t0)
-for kind, kw, last in [("HMC", dict(scale=1e-3, nleaps=8), 3), ("RWM", dict(scale=1e-3), 6)]:
+for kind, kw, last in [("HMC", dict(scale=1e-3, nleaps=8), 3), ("RWM", dict(scale=1e-3), 6), ("MALA", dict(scale=1e-6), 6)]:
     init = np.tile(b0, (C, 1)) + 1e-3 * r.standard_normal((C, d))
     run = capi.DeviceRun(dm, capi.sampler_cfg(kind, **kw), (1, 1, last), C, init, seed=1, engine="wave", store_grad=False, store_logtarget=False)
     info = run.execute()
