@@ -587,6 +587,8 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     const int kind = R->s.kind;
     const bool need_grad = (kind != MCMCGPU_RWM && kind != MCMCGPU_RAM);
     const bool is_ram = (kind == MCMCGPU_RAM);
+    // RWM / MALA / RAM: every chain needs the log-target on every wave -- tell the likelihood kernel so (null flag array)
+    const uint8_t* need_ll_flags = (kind == MCMCGPU_HMC || kind == MCMCGPU_HMCDA) ? R->need_ll : nullptr;
     // number of waves when it is known in advance; otherwise poll the device counter
     int64_t known = -1;
     if (kind == MCMCGPU_RWM || kind == MCMCGPU_MALA || kind == MCMCGPU_RAM) known = seg;
@@ -629,7 +631,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
           int crc = MCMCGPU_OK;
           for (int64_t g = 0; g < GW && crc == MCMCGPU_OK; g++) {
             const double* pp; int ns;
-            crc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad, R->need_ll, R->phase, R->remaining, &pp, &ns);
+            crc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad, need_ll_flags, R->phase, R->remaining, &pp, &ns);
             W.part = pp; W.nsplit = ns;
             if (crc == MCMCGPU_OK && launch_transition(W, st) != cudaSuccess) crc = MCMCGPU_E_CUDA;
             if (crc == MCMCGPU_OK && is_ram && launch_ram(W, false, st) != cudaSuccess) crc = MCMCGPU_E_CUDA;
@@ -650,7 +652,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       cudaEvent_t a0 = nullptr, a1 = nullptr;
       if (c->time_eval) { CU(cudaEventCreate(&a0)); CU(cudaEventCreate(&a1)); CU(cudaEventRecord(a0, st)); }
       int rc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad || first,
-                         first ? nullptr : R->need_ll, R->phase, R->remaining, &pp, &ns);
+                         first ? nullptr : need_ll_flags, R->phase, R->remaining, &pp, &ns);
       if (rc != MCMCGPU_OK) return rc;
       if (c->time_eval) { CU(cudaEventRecord(a1, st)); evs.push_back(a0); evs.push_back(a1); }
       W.part = pp; W.nsplit = ns;
