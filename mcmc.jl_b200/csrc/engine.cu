@@ -225,6 +225,9 @@ static int model_create_impl(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
     case MCMCGPU_FAM_LOGISTIC:
       if (nhyper < 1) m->hyper[0] = 1.0;
       if (nhyper < 2) m->hyper[1] = -1.0;
+      // the two conventions of the reference: exp(-X*vars) (examples/logistic_regression.jl:18) and exp(X*vars)
+      // (test/test_syntax.jl:18); K1 folds this sign into beta, which is exact only for +-1
+      if (m->hyper[1] != 1.0 && m->hyper[1] != -1.0) { delete m; return fail(MCMCGPU_E_ARG, "logistic sign must be +1 or -1"); }
       m->is_regression = true; break;
     case MCMCGPU_FAM_PROBIT:
       if (nhyper < 1) m->hyper[0] = 10.0;

@@ -20,6 +20,7 @@
 #include "k1_regress.h"
 #include "erfcx_table.h"
 #include "probit_table.h"
+#include "exp_table.h"
 #include <cmath>
 #include <cstdio>
 
@@ -106,6 +107,34 @@ __device__ __forceinline__ double probit_eval(const double* tab, int k, double t
 #pragma unroll
   for (int j = PROBIT_DEG - 1; j >= 0; j--) p = fma(p, t, __ldg(c + j * PROBIT_NINT));
   return p;
+}
+
+// ---- logistic link: exp from a 64-entry table of 2^(j/64) held in shared memory (tools/gen_exp_table.py) ---------------
+// DMMA and the scalar FP64 instructions share one pipe, so the link is written for the fewest FP64 instructions:
+//   exp(x) = 2^k T[j] (1 + q(r)), n = rint(64 x / ln 2) = 64 k + j, |r| <= ln2/128, q of degree 5: 10 FP64 instructions
+//   (exp_lean: 17), 2.2e-16 relative against mpmath; the table read is one LDS.64 (the load/store pipe has room).
+__device__ const double exp_tab_g[EXP_NTAB] = {EXP_TABLE_VALUES};
+__device__ __forceinline__ double exp_tab64(double x, const double* T) {      // |x| < 700
+  const double t = fma(x, 64.0 * 1.4426950408889634, 6755399441055744.0);
+  const int n = __double2loint(t);
+  const double nf = t - 6755399441055744.0;
+  double r = fma(nf, -6.93147180369123816490e-01 / 64.0, x);
+  r = fma(nf, -1.90821492927058770002e-10 / 64.0, r);
+  double p = fma(8.33333333333333333333e-03, r, 4.16666666666666666667e-02);
+  p = fma(p, r, 1.66666666666666666667e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  const double tj = T[n & (EXP_NTAB - 1)];
+  const double e = fma(tj, p * r, tj);
+  return __hiloint2double(__double2hiint(e) + ((n >> 6) << 20), __double2loint(e));   // * 2^k, |k| <= 1010: stays normal
+}
+// 1/d, d in [1, 1e305]: rcp.approx.ftz.f64 (relative error <= 2^-23) and one cubic step y (1 + e + e^2), e = 1 - d y
+// (remaining error e^3 = 2^-69): 3 FP64 instructions instead of the 4 of two Newton steps
+__device__ __forceinline__ double rcp_cubic(double d) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-d, y, 1.0);
+  return fma(y, fma(e, e, e), y);
 }
 
 // ---- link functions: (eta, y) -> loglik term(s) and r = d loglik / d eta ----------------------
@@ -198,6 +227,7 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   double* tiles = betas + K1_CHAINS * S;
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)K1_STAGES * TILE_D);
   unsigned int* released = reinterpret_cast<unsigned int*>(full + K1_STAGES);   // warps that have finished with a slot
+  double* etab = reinterpret_cast<double*>(full + 2 * K1_STAGES);               // 2^(j/64) (logistic link)
 
   if (a.remaining && *a.remaining == 0) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -224,11 +254,15 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
     for (int s = 0; s < K1_STAGES; s++) { mbar_init(&full[s], 1); released[s] = 0; }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // beta tile: betas[c][j] = q[j][chain0 + c] (zero-padded features)
+  // beta tile: betas[c][j] = q[j][chain0 + c] (zero-padded features).  Logistic: the sign convention of the link
+  // (hyper[1] = +-1, checked at model_create) is folded into beta, so phase 1 yields x = sign * eta directly; a sign
+  // flip commutes with every rounding, so x is bit-identical to sign * (X beta)
+  const double bsign = (FAM == MCMCGPU_FAM_LOGISTIC) ? a.hyper[1] : 1.0;
   for (int idx = tid; idx < K1_CHAINS * 8 * DK; idx += K1_THREADS) {
     const int j = idx / K1_CHAINS, c = idx % K1_CHAINS;
-    betas[c * S + j] = (j < d) ? a.q[(int64_t)j * Cp + chain0 + c] : 0.0;
+    betas[c * S + j] = (j < d) ? bsign * a.q[(int64_t)j * Cp + chain0 + c] : 0.0;
   }
+  if (FAM == MCMCGPU_FAM_LOGISTIC && tid < EXP_NTAB) etab[tid] = exp_tab_g[tid];
   __syncthreads();
   if (tid == 0) {
     for (int s = 0; s < K1_STAGES && s < nt; s++) {
@@ -287,40 +321,53 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
       if (FAM == MCMCGPU_FAM_LOGISTIC && a.debug == 0) {
         // all 2*NR elements stage by stage, so their dependency chains interleave.  The same arithmetic is used whether
         // or not the log-likelihood is wanted (need_ll is a per-WARP flag: a chain's numbers must not depend on the
-        // phase of its neighbours, or sharding / stepwise execution would change the draws)
-        double xv[2 * NR], yv[2 * NR];
+        // phase of its neighbours, or sharding / stepwise execution would change the draws).  acc holds x = sign * eta
+        // (sign folded into beta).  15 FP64 instructions per element on a gradient wave: exp 10, 1 + e, reciprocal 3,
+        // e * p; the response test, the support test and the sign of r are integer work on the bit patterns.
         bool fast = true;
 #pragma unroll
         for (int n = 0; n < NR; n++)
 #pragma unroll
-          for (int s = 0; s < 2; s++) {
-            const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-            xv[i] = hy[1] * acc[n][s];
-            yv[i] = ys[lr];
-            fast = fast && ((__double2hiint(xv[i]) & 0x7fffffff) < 0x4085E000);   // |x| < 700 and not NaN (integer compare)
-          }
+          for (int s = 0; s < 2; s++)
+            fast = fast && ((__double2hiint(acc[n][s]) & 0x7fffffff) < 0x4085E000);   // |x| < 700 and not NaN
         if (fast) {
           double ev[2 * NR], pv[2 * NR];
 #pragma unroll
-          for (int i = 0; i < 2 * NR; i++) ev[i] = exp_lean(xv[i]);
+          for (int n = 0; n < NR; n++)
 #pragma unroll
-          for (int i = 0; i < 2 * NR; i++) pv[i] = rcp_lean(1.0 + ev[i]);
+            for (int s = 0; s < 2; s++) ev[2 * n + s] = exp_tab64(acc[n][s], etab);
+#pragma unroll
+          for (int i = 0; i < 2 * NR; i++) pv[i] = rcp_cubic(1.0 + ev[i]);
+          const int sbit = __double2hiint(hy[1]) & 0x80000000;      // sign bit of the link's sign convention
+          unsigned y1mask = 0u;
 #pragma unroll
           for (int n = 0; n < NR; n++)
 #pragma unroll
             for (int s = 0; s < 2; s++) {
               const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-              const bool y1 = (yv[i] != 0.0);
-              // support: log(p) is finite for |x| < 700; log(1 - p) is finite unless 1 + e rounds to 1 (x <= ln 2^-53)
-              const bool bad = !y1 && (xv[i] <= -36.736800569677101);
-              const bool valid = (rowbase + lr) < N;
-              if (valid) nbad += bad ? 1 : 0;
-              acc[n][s] = y1 ? (-hy[1]) * (ev[i] * pv[i]) : hy[1] * pv[i];
-              ev[i] = valid ? (y1 ? pv[i] : 1.0 - pv[i]) : 1.0;                // Bernoulli: p1, or p0 = 1 - p1 by subtraction
+              const long long yb = __double_as_longlong(ys[lr]);
+              const bool y1 = (yb << 1) != 0;                        // y != 0.0 (NaN counts as a success, as != does)
+              // support: log(p) is finite for |x| < 700; log(1 - p) is finite unless 1 + e rounds to 1, i.e.
+              // x <= ln 2^-53 = -36.736800569677101 (padded rows have x = 0)
+              nbad += (!y1 && (unsigned long long)__double_as_longlong(acc[n][s]) >= 0xC0425E4F7B2737FAull) ? 1 : 0;
+              y1mask |= y1 ? (1u << i) : 0u;
+              // r = y ? (-sign) (e p) : sign p  (the reference's AD chain in closed form, see link<>): magnitude, then sign bit
+              const double ep = ev[i] * pv[i];
+              const double mag = y1 ? ep : pv[i];
+              const int flip = (y1 ? (int)0x80000000 : 0) ^ sbit;
+              acc[n][s] = __hiloint2double(__double2hiint(mag) ^ flip, __double2loint(mag));
             }
           if (need_ll) {                                                        // warp-uniform; kept out of the straight-line code above
 #pragma unroll
-            for (int i = 0; i < 2 * NR; i++) ll1 += log_lean(ev[i]);            // padded rows contribute log(1) = 0
+            for (int n = 0; n < NR; n++)
+#pragma unroll
+              for (int s = 0; s < 2; s++) {
+                const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+                const bool y1 = (y1mask >> i) & 1u;
+                double arg = y1 ? pv[i] : 1.0 - pv[i];                          // Bernoulli: p1, or p0 = 1 - p1 by subtraction
+                if ((rowbase + lr) >= N) arg = 1.0;                             // padded rows contribute log(1) = 0
+                ll1 += log_lean(arg);
+              }
           }
           done = true;
         }
@@ -395,7 +442,12 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
             const double y = ys[lr];
             LinkOut o;
             if (a.debug == 1) { o.ll1 = 0.0; o.ll2 = 0.0; o.bad = false; o.r = acc[n][s] * y; }
-            else o = link<FAM>(acc[n][s], y, hy, need_ll);
+            else if (FAM == MCMCGPU_FAM_LOGISTIC) {
+              // acc = sign * eta (sign folded into beta): the link with sign 1, then d/d eta = sign * d/d x
+              const double h1[4] = {hy[0], 1.0, hy[2], hy[3]};
+              o = link<FAM>(acc[n][s], y, h1, need_ll);
+              o.r *= hy[1];
+            } else o = link<FAM>(acc[n][s], y, hy, need_ll);
             const bool valid = (rowbase + lr) < N;
             if (valid) { ll1 += o.ll1; ll2 += o.ll2; nbad += o.bad ? 1 : 0; }
             acc[n][s] = o.r;    // rows >= N have X == 0, so their r never reaches G
@@ -536,7 +588,7 @@ static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
   constexpr int S = 8 * DK + 4;
   constexpr int NR = K1_NR;
   constexpr size_t smem = sizeof(double) * ((size_t)K1_CHAINS * S + (size_t)K1_STAGES * (K1_ROWS * S + K1_ROWS)) +
-                          2 * K1_STAGES * sizeof(uint64_t);
+                          2 * K1_STAGES * sizeof(uint64_t) + EXP_NTAB * sizeof(double);
   static bool attr_done[64] = {false};      // the attribute is per device
   int dev = 0;
   cudaGetDevice(&dev);

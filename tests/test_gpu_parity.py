@@ -654,6 +654,35 @@ def test_link_functions_over_wide_range(O, capi, ctx, fam):
     dm.close()
 
 
+@pytest.mark.parametrize("sign", [-1.0, 1.0])
+def test_logistic_link_elementwise(capi, ctx, sign):
+    """r = d loglik / d eta of the logistic link, element by element (N = 1, X = [1], one chain per eta), against mpmath:
+    the table-driven exp (tools/gen_exp_table.py), the cubic reciprocal step and the sign handling on bit patterns of
+    K1's fast path must keep ~1e-15 relative accuracy over the whole fast range, for both sign conventions
+    (examples/logistic_regression.jl:18, test/test_syntax.jl:18) and both responses."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(11)
+    eta = np.concatenate([np.linspace(-36.5, 36.5, 1500), rng.uniform(-5, 5, 1500), rng.uniform(-690, 690, 200), [0.0, 1e-300, -1e-17]])
+    sd = 1e6
+    for yval in (1.0, 0.0):
+        dm = capi.DeviceModel(ctx, "logistic", 1, np.ones((1, 1)), np.array([yval]), (sd, sign))
+        lt, g = dm.logtarget_grad(eta.reshape(-1, 1))
+        for c, b in enumerate(eta):
+            x = mp.mpf(sign) * mp.mpf(float(b))
+            pr = 1 / (1 + mp.exp(x))                                   # prob = 1/(1 + exp(sign * eta))
+            r = (-mp.mpf(sign) * (1 - pr)) if yval == 1.0 else mp.mpf(sign) * pr
+            truth = r - mp.mpf(float(b)) / (sd * sd)
+            if yval == 0.0 and sign * b <= -36.736800569677101:        # 1 - p == 0 in binary64: out of support, (-Inf, zeros)
+                assert lt[c] == -np.inf and g[c, 0] == 0.0
+                continue
+            assert abs(mp.mpf(float(g[c, 0])) - truth) <= mp.mpf(1e-15) * (abs(r) + abs(mp.mpf(float(b))) / (sd * sd)), (sign, yval, b, g[c, 0], truth)
+            assert np.isfinite(lt[c])
+        dm.close()
+    with pytest.raises(capi.MCMCGPUError):
+        capi.DeviceModel(ctx, "logistic", 1, np.ones((1, 1)), np.array([1.0]), (1.0, -2.0))     # sign must be +-1
+
+
 def test_readme_snippet():
     """the usage example of README.md runs as written"""
     import mcmc_jl_b200 as mj
