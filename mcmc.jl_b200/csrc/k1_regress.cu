@@ -24,6 +24,7 @@
 #include "log_table.h"
 #include <cmath>
 #include <cstdio>
+#include <type_traits>
 
 namespace mg {
 
@@ -90,11 +91,30 @@ __device__ const double probit_W_tab[(PROBIT_DEG + 1) * PROBIT_NINT] = {PROBIT_W
 // joint table: one degree-10 polynomial J per interval with J' = the W interpolant and J(0) = F(centre); the simultaneous
 // Horner scheme gives log Phi and phi/Phi from ONE set of coefficient loads (the kernel is load/store-unit bound at small d)
 __device__ const double probit_J_tab[(PROBIT_DEG + 2) * PROBIT_NINT] = {PROBIT_J_VALUES};
-__device__ __forceinline__ void probit_eval_joint(int k, double t, double& f, double& w) {
-  const double* c = probit_J_tab + k;
-  double p = __ldg(c + (PROBIT_DEG + 1) * PROBIT_NINT), dp = 0.0;
+// The tables sit in global memory (L1-resident).  At small d the kernel is bound by the load/store unit (ncu on the MALA
+// wave of cfg3: LSU wavefronts 83 % of peak, one wavefront per distinct 32-byte sector of every gather), so when the CTA has
+// room the central part |z| < 8 -- where practically every element falls -- is copied to shared memory, where a gather costs
+// one wavefront per group of lanes that hit one bank at different addresses.  The copies hold the same coefficients and the
+// arithmetic is the same, so which copy a warp reads never changes a number.
+constexpr int PS_K0 = (PROBIT_ZMAX - 8) * PROBIT_INV_W - 1;      // first interval of the shared-memory copy
+constexpr int PS_N = 16 * PROBIT_INV_W + 3;                       // intervals -8 - 1/8 .. 8 + 1/8
+constexpr int PS_DOUBLES = PS_N * (3 * PROBIT_DEG + 4);           // J (DEG+2 rows), W and F (DEG+1 rows each)
+// shared-memory bytes of a CTA without the probit tables, and whether the resident CTA count of the DK class survives them
+__host__ __device__ constexpr size_t k1_smem_base(int DK) {
+  return sizeof(double) * ((size_t)K1_CHAINS * (8 * DK + 4) + (size_t)K1_STAGES * (K1_ROWS * (8 * DK + 4) + K1_ROWS)) +
+         2 * K1_STAGES * sizeof(uint64_t) + (EXP_NTAB + 2 * LOG_NINT) * sizeof(double);
+}
+__host__ __device__ constexpr bool k1_probit_smem(int DK) {
+  const size_t ctas = (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1);
+  return ctas * (k1_smem_base(DK) + PS_DOUBLES * sizeof(double) + 1024) <= 233472;   // 228 KB per SM
+}
+template <bool SM>
+__device__ __forceinline__ double tab_ld(const double* p) { return SM ? *p : __ldg(p); }
+template <bool SM>
+__device__ __forceinline__ void probit_eval_joint(const double* c, int stride, double t, double& f, double& w) {
+  double p = tab_ld<SM>(c + (PROBIT_DEG + 1) * stride), dp = 0.0;
 #pragma unroll
-  for (int j = PROBIT_DEG; j >= 0; j--) { dp = fma(dp, t, p); p = fma(p, t, __ldg(c + j * PROBIT_NINT)); }
+  for (int j = PROBIT_DEG; j >= 0; j--) { dp = fma(dp, t, p); p = fma(p, t, tab_ld<SM>(c + j * stride)); }
   f = p; w = dp;
 }
 __device__ __forceinline__ void probit_index(double z, int& k, double& t) {
@@ -102,11 +122,11 @@ __device__ __forceinline__ void probit_index(double z, int& k, double& t) {
   k = __double2loint(m);
   t = fma(m - (6755399441055744.0 + (double)(PROBIT_ZMAX * PROBIT_INV_W)), -1.0 / PROBIT_INV_W, z);
 }
-__device__ __forceinline__ double probit_eval(const double* tab, int k, double t) {
-  const double* c = tab + k;
-  double p = __ldg(c + PROBIT_DEG * PROBIT_NINT);
+template <bool SM>
+__device__ __forceinline__ double probit_eval(const double* c, int stride, double t) {
+  double p = tab_ld<SM>(c + PROBIT_DEG * stride);
 #pragma unroll
-  for (int j = PROBIT_DEG - 1; j >= 0; j--) p = fma(p, t, __ldg(c + j * PROBIT_NINT));
+  for (int j = PROBIT_DEG - 1; j >= 0; j--) p = fma(p, t, tab_ld<SM>(c + j * stride));
   return p;
 }
 
@@ -255,6 +275,8 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   unsigned int* released = reinterpret_cast<unsigned int*>(full + K1_STAGES);   // warps that have finished with a slot
   double* etab = reinterpret_cast<double*>(full + 2 * K1_STAGES);               // 2^(j/64) (logistic link)
   double2* ltab = reinterpret_cast<double2*>(etab + EXP_NTAB);                  // (1/c_j, log c_j) (logistic link)
+  constexpr bool PSM = (FAM == MCMCGPU_FAM_PROBIT) && k1_probit_smem(DK);
+  double* ptab = reinterpret_cast<double*>(ltab + LOG_NINT);                    // central part of the probit tables
 
   if (a.remaining && *a.remaining == 0) return;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -288,6 +310,15 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   for (int idx = tid; idx < K1_CHAINS * 8 * DK; idx += K1_THREADS) {
     const int j = idx / K1_CHAINS, c = idx % K1_CHAINS;
     betas[c * S + j] = (j < d) ? bsign * a.q[(int64_t)j * Cp + chain0 + c] : 0.0;
+  }
+  if (PSM) {
+    for (int idx = tid; idx < PS_DOUBLES; idx += K1_THREADS) {
+      const int row = idx / PS_N, i = idx - row * PS_N;       // rows: J[0..DEG+1], W[0..DEG], F[0..DEG]
+      const double* src = (row < PROBIT_DEG + 2) ? probit_J_tab + row * PROBIT_NINT
+                        : (row < 2 * PROBIT_DEG + 3) ? probit_W_tab + (row - (PROBIT_DEG + 2)) * PROBIT_NINT
+                                                     : probit_F_tab + (row - (2 * PROBIT_DEG + 3)) * PROBIT_NINT;
+      ptab[idx] = src[PS_K0 + i];
+    }
   }
   if (FAM == MCMCGPU_FAM_LOGISTIC) {
     if (tid < EXP_NTAB) etab[tid] = exp_tab_g[tid];
@@ -404,62 +435,82 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
       }
       if (FAM == MCMCGPU_FAM_PROBIT && a.debug == 0) {
         // binary responses with |eta| < 36.9 (the only case met in practice): log Phi(z) and phi(z)/Phi(z), z = +-eta, from
-        // the tables, stage by stage over the 2*NR elements; log Phi is skipped when no chain of the warp needs the value
+        // the tables, stage by stage over the 2*NR elements; log Phi is skipped when no chain of the warp needs the value.
+        // Response tests, range tests and sign flips are integer work on the bit patterns (the FP64 pipe is DMMA's).
         double zv[2 * NR], tv[2 * NR];
         int kv[2 * NR];
-        bool fast = true;
+        unsigned y1mask = 0u;
+        bool fast = true, central = true;
 #pragma unroll
         for (int n = 0; n < NR; n++)
 #pragma unroll
           for (int s = 0; s < 2; s++) {
             const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-            const double y = ys[lr];
-            zv[i] = (y == 1.0) ? acc[n][s] : -acc[n][s];
-            fast = fast && (y == 1.0 || y == 0.0) && (fabs(zv[i]) < (double)PROBIT_ZMAX - 0.1);   // NaN fails the comparison
+            const long long yb = __double_as_longlong(ys[lr]);
+            const bool y1 = (yb == 0x3FF0000000000000ll);
+            y1mask |= y1 ? (1u << i) : 0u;
+            const int zh = __double2hiint(acc[n][s]) ^ (y1 ? 0 : (int)0x80000000);          // z = y ? eta : -eta
+            zv[i] = __hiloint2double(zh, __double2loint(acc[n][s]));
+            fast = fast && (y1 || yb == 0ll) && ((zh & 0x7fffffff) < 0x40427333);            // |z| < 36.9 and not NaN
+            central = central && ((zh & 0x7fffffff) < 0x40200000);                           // |z| < 8
           }
+        // the shared-memory copies only when every element of the warp is central (warp-uniform choice of the code path;
+        // same coefficients, same arithmetic: the choice never changes a number)
+        const bool insm = PSM && __all_sync(0xffffffffu, fast && central);
         if (fast) {
 #pragma unroll
           for (int i = 0; i < 2 * NR; i++) probit_index(zv[i], kv[i], tv[i]);
-          if (a.need_ll == nullptr && a.need_grad) {
-            // every chain needs value and gradient on every wave of this run (MALA; the first wave of any run):
-            // both from the joint table, one set of coefficient loads
+          auto stages = [&](auto sm_tag) {
+            constexpr bool SM = decltype(sm_tag)::value;
+            constexpr int stride = SM ? PS_N : PROBIT_NINT;
+            const double* TJ = SM ? ptab : probit_J_tab;
+            const double* TW = SM ? ptab + (PROBIT_DEG + 2) * PS_N : probit_W_tab;
+            const double* TF = SM ? ptab + (2 * PROBIT_DEG + 3) * PS_N : probit_F_tab;
+            constexpr int k0 = SM ? PS_K0 : 0;
+            if (a.need_ll == nullptr && a.need_grad) {
+              // every chain needs value and gradient on every wave of this run (MALA; the first wave of any run):
+              // both from the joint table, one set of coefficient loads
 #pragma unroll
-            for (int n = 0; n < NR; n++)
+              for (int n = 0; n < NR; n++)
 #pragma unroll
-              for (int s = 0; s < 2; s++) {
-                const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-                double l, w;
-                probit_eval_joint(kv[i], tv[i], l, w);
-                const bool y1 = (ys[lr] == 1.0);
-                acc[n][s] = y1 ? w : -w;
-                if ((rowbase + lr) >= N) l = 0.0;
-                ll1 += y1 ? l : 0.0;
-                ll2 += y1 ? 0.0 : l;
+                for (int s = 0; s < 2; s++) {
+                  const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+                  double l, w;
+                  probit_eval_joint<SM>(TJ + (kv[i] - k0), stride, tv[i], l, w);
+                  const bool y1 = (y1mask >> i) & 1u;
+                  acc[n][s] = __hiloint2double(__double2hiint(w) ^ (y1 ? 0 : (int)0x80000000), __double2loint(w));   // r = y ? w : -w
+                  if ((rowbase + lr) >= N) l = 0.0;
+                  const double sum = (y1 ? ll1 : ll2) + l;      // dot(log Phi(eta), y) and dot(log Phi(-eta), 1 - y) kept apart
+                  ll1 = y1 ? sum : ll1;
+                  ll2 = y1 ? ll2 : sum;
+                }
+            } else {
+              if (a.need_grad) {
+#pragma unroll
+                for (int n = 0; n < NR; n++)
+#pragma unroll
+                  for (int s = 0; s < 2; s++) {
+                    const int i = 2 * n + s;
+                    const double w = probit_eval<SM>(TW + (kv[i] - k0), stride, tv[i]);
+                    acc[n][s] = __hiloint2double(__double2hiint(w) ^ (((y1mask >> i) & 1u) ? 0 : (int)0x80000000), __double2loint(w));
+                  }
               }
-          } else {
-            if (a.need_grad) {
+              if (need_ll) {
 #pragma unroll
-              for (int n = 0; n < NR; n++)
+                for (int n = 0; n < NR; n++)
 #pragma unroll
-                for (int s = 0; s < 2; s++) {
-                  const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-                  const double w = probit_eval(probit_W_tab, kv[i], tv[i]);
-                  acc[n][s] = (ys[lr] == 1.0) ? w : -w;
-                }
+                  for (int s = 0; s < 2; s++) {
+                    const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+                    const double l = ((rowbase + lr) < N) ? probit_eval<SM>(TF + (kv[i] - k0), stride, tv[i]) : 0.0;
+                    const bool y1 = (y1mask >> i) & 1u;
+                    const double sum = (y1 ? ll1 : ll2) + l;
+                    ll1 = y1 ? sum : ll1;
+                    ll2 = y1 ? ll2 : sum;
+                  }
+              }
             }
-            if (need_ll) {
-#pragma unroll
-              for (int n = 0; n < NR; n++)
-#pragma unroll
-                for (int s = 0; s < 2; s++) {
-                  const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-                  const double l = ((rowbase + lr) < N) ? probit_eval(probit_F_tab, kv[i], tv[i]) : 0.0;
-                  const bool y1 = (ys[lr] == 1.0);
-                  ll1 += y1 ? l : 0.0;
-                  ll2 += y1 ? 0.0 : l;
-                }
-            }
-          }
+          };
+          if (insm) stages(std::true_type{}); else stages(std::false_type{});
           done = true;
         }
       }
@@ -615,10 +666,8 @@ int k1_choose_splits(const K1Pack& P, int64_t Cp) {
 
 template <int FAM, int DK>
 static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
-  constexpr int S = 8 * DK + 4;
   constexpr int NR = K1_NR;
-  constexpr size_t smem = sizeof(double) * ((size_t)K1_CHAINS * S + (size_t)K1_STAGES * (K1_ROWS * S + K1_ROWS)) +
-                          2 * K1_STAGES * sizeof(uint64_t) + (EXP_NTAB + 2 * LOG_NINT) * sizeof(double);
+  constexpr size_t smem = k1_smem_base(DK) + ((FAM == MCMCGPU_FAM_PROBIT && k1_probit_smem(DK)) ? PS_DOUBLES * sizeof(double) : 0);
   static bool attr_done[64] = {false};      // the attribute is per device
   int dev = 0;
   cudaGetDevice(&dev);
