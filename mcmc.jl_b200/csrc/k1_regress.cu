@@ -29,7 +29,6 @@
 namespace mg {
 
 constexpr int K1_STAGES = 2;
-constexpr int K1_THREADS = K1_WARPS * 32;
 constexpr int K1_NR = 4;          // 8-row groups per phase-1 pass (independent DMMA accumulator chains)
 constexpr int PH_IDLE_K1 = 98;  // phases >= PH_PAUSE (98) have no pending evaluation (transition.h)
 
@@ -100,13 +99,12 @@ constexpr int PS_K0 = (PROBIT_ZMAX - 8) * PROBIT_INV_W - 1;      // first interv
 constexpr int PS_N = 16 * PROBIT_INV_W + 3;                       // intervals -8 - 1/8 .. 8 + 1/8
 constexpr int PS_DOUBLES = PS_N * (3 * PROBIT_DEG + 4);           // J (DEG+2 rows), W and F (DEG+1 rows each)
 // shared-memory bytes of a CTA without the probit tables, and whether the resident CTA count of the DK class survives them
-__host__ __device__ constexpr size_t k1_smem_base(int DK) {
-  return sizeof(double) * ((size_t)K1_CHAINS * (8 * DK + 4) + (size_t)K1_STAGES * (K1_ROWS * (8 * DK + 4) + K1_ROWS)) +
-         2 * K1_STAGES * sizeof(uint64_t) + (EXP_NTAB + 2 * LOG_NINT) * sizeof(double);
+__host__ __device__ constexpr size_t k1_smem_base(int DK, int WARPS, int STAGES) {
+  return sizeof(double) * ((size_t)(8 * WARPS) * (8 * DK + 4) + (size_t)STAGES * (K1_ROWS * (8 * DK + 4) + K1_ROWS)) +
+         2 * STAGES * sizeof(uint64_t) + (EXP_NTAB + 2 * LOG_NINT) * sizeof(double);
 }
-__host__ __device__ constexpr bool k1_probit_smem(int DK) {
-  const size_t ctas = (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1);
-  return ctas * (k1_smem_base(DK) + PS_DOUBLES * sizeof(double) + 1024) <= 233472;   // 228 KB per SM
+__host__ __device__ constexpr bool k1_probit_smem(int DK, int WARPS, int STAGES, int CTAS) {
+  return (size_t)CTAS * (k1_smem_base(DK, WARPS, STAGES) + PS_DOUBLES * sizeof(double) + 1024) <= 233472;   // 228 KB per SM
 }
 template <bool SM>
 __device__ __forceinline__ double tab_ld(const double* p) { return SM ? *p : __ldg(p); }
@@ -263,8 +261,10 @@ __device__ __forceinline__ LinkOut link(double eta, double y, const double* hy, 
 // Shared memory per CTA: beta tile [64 chains][S] (A fragments of phase 1), STAGES X tiles, barriers.
 // 256 threads, <= 128 registers, two CTAs per SM: 16 warps keep the DMMA pipe fed while other warps
 // are in the (latency-bound) link-function epilogue.
-template <int FAM, int DK, int NR>
-__global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1)) k1_kernel(const K1Args a) {
+// CTA shape: WARPS consumer warps (8 chains each), a STAGES-deep tile ring, CTAS resident CTAs per SM.
+template <int FAM, int DK, int NR, int WARPS, int STAGES, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
+  constexpr int K1_WARPS = WARPS, K1_CHAINS = 8 * WARPS, K1_THREADS = 32 * WARPS, K1_STAGES = STAGES;   // shadow the defaults
   constexpr int S = 8 * DK + 4;
   constexpr int TILE_D = K1_ROWS * S + K1_ROWS;
   constexpr int NG = K1_ROWS / (8 * NR);      // row groups per tile
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   unsigned int* released = reinterpret_cast<unsigned int*>(full + K1_STAGES);   // warps that have finished with a slot
   double* etab = reinterpret_cast<double*>(full + 2 * K1_STAGES);               // 2^(j/64) (logistic link)
   double2* ltab = reinterpret_cast<double2*>(etab + EXP_NTAB);                  // (1/c_j, log c_j) (logistic link)
-  constexpr bool PSM = (FAM == MCMCGPU_FAM_PROBIT) && k1_probit_smem(DK);
+  constexpr bool PSM = (FAM == MCMCGPU_FAM_PROBIT) && k1_probit_smem(DK, WARPS, STAGES, CTAS);
   double* ptab = reinterpret_cast<double*>(ltab + LOG_NINT);                    // central part of the probit tables
 
   if (a.remaining && *a.remaining == 0) return;
@@ -289,7 +289,10 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
 
   // skip chain tiles whose chains have no pending evaluation (asynchronous HMCDA trajectories)
   int alive = 1;
-  if (a.phase) alive = (a.phase[chain0 + (tid & (K1_CHAINS - 1))] < PH_IDLE_K1);
+  if (a.phase) {
+    const int64_t pc = chain0 + (tid & (K1_CHAINS - 1));
+    alive = (pc < Cp) && (a.phase[pc] < PH_IDLE_K1);
+  }
   if (!__syncthreads_or(alive)) return;
 
   // tile range of this split
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   const double bsign = (FAM == MCMCGPU_FAM_LOGISTIC) ? a.hyper[1] : 1.0;
   for (int idx = tid; idx < K1_CHAINS * 8 * DK; idx += K1_THREADS) {
     const int j = idx / K1_CHAINS, c = idx % K1_CHAINS;
-    betas[c * S + j] = (j < d) ? bsign * a.q[(int64_t)j * Cp + chain0 + c] : 0.0;
+    betas[c * S + j] = (j < d && chain0 + c < Cp) ? bsign * a.q[(int64_t)j * Cp + chain0 + c] : 0.0;
   }
   if (PSM) {
     for (int idx = tid; idx < PS_DOUBLES; idx += K1_THREADS) {
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   }
   // per-warp flag: does any of this warp's chains need the log-likelihood value this wave?
   bool need_ll = true;
-  if (a.need_ll) need_ll = __any_sync(0xffffffffu, a.need_ll[mychain] != 0);
+  if (a.need_ll) need_ll = __any_sync(0xffffffffu, mychain < Cp && a.need_ll[mychain] != 0);
 
   double G[DK][2];
 #pragma unroll
@@ -576,6 +579,7 @@ __global__ void __launch_bounds__(K1_THREADS, (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK 
   ll2 += __shfl_xor_sync(0xffffffffu, ll2, 1); ll2 += __shfl_xor_sync(0xffffffffu, ll2, 2);
   nbad += __shfl_xor_sync(0xffffffffu, nbad, 1); nbad += __shfl_xor_sync(0xffffffffu, nbad, 2);
   double* part = a.part + (int64_t)split * (d + 2) * Cp;
+  if (mychain >= Cp) return;          // overhang of the last (wide) chain tile
   if (t == 0) {
     part[(int64_t)d * Cp + mychain] = ll1 + ll2;
     part[(int64_t)(d + 1) * Cp + mychain] = (double)nbad;
@@ -664,21 +668,32 @@ int k1_choose_splits(const K1Pack& P, int64_t Cp) {
   return best;
 }
 
-template <int FAM, int DK>
-static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
+template <int FAM, int DK, int WARPS, int STAGES, int CTAS>
+static cudaError_t launch_shape(const K1Args& a, cudaStream_t st) {
   constexpr int NR = K1_NR;
-  constexpr size_t smem = k1_smem_base(DK) + ((FAM == MCMCGPU_FAM_PROBIT && k1_probit_smem(DK)) ? PS_DOUBLES * sizeof(double) : 0);
+  constexpr size_t smem = k1_smem_base(DK, WARPS, STAGES) +
+                          ((FAM == MCMCGPU_FAM_PROBIT && k1_probit_smem(DK, WARPS, STAGES, CTAS)) ? PS_DOUBLES * sizeof(double) : 0);
+  static_assert(smem <= 232448, "one CTA must fit the 227 KB of dynamic shared memory");
   static bool attr_done[64] = {false};      // the attribute is per device
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k1_kernel<FAM, DK, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k1_kernel<FAM, DK, NR, WARPS, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  dim3 grid((unsigned)(a.Cp / K1_CHAINS), (unsigned)a.nsplit);
-  k1_kernel<FAM, DK, NR><<<grid, K1_THREADS, smem, st>>>(a);
+  dim3 grid((unsigned)((a.Cp + 8 * WARPS - 1) / (8 * WARPS)), (unsigned)a.nsplit);
+  k1_kernel<FAM, DK, NR, WARPS, STAGES, CTAS><<<grid, 32 * WARPS, smem, st>>>(a);
   return cudaGetLastError();
+}
+
+template <int FAM, int DK>
+static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
+  // 8 warps x 64 chains, 2-deep ring; 3 / 2 / 1 resident CTAs by register and shared-memory budget.  (Measured and dropped:
+  // one 16-warp x 128-chain CTA per SM with a 4-deep ring for 32 < d <= 104 -- same warps per SM, half the X-tile traffic,
+  // three tiles of slack between the fastest and the slowest warp -- 35.0 vs 35.1 ms per wave: the ring is not the limiter.)
+  constexpr int CTAS = (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1);
+  return launch_shape<FAM, DK, K1_WARPS, K1_STAGES, CTAS>(a, st);
 }
 
 template <int FAM>
