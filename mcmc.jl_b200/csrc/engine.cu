@@ -104,6 +104,15 @@ struct mcmcgpu_run {
 };
 
 // ------------------------------------------------------------------------------------------------
+struct Events {    // CUDA events destroyed on scope exit (every return path of the CU() macro included)
+  std::vector<cudaEvent_t> v;
+  ~Events() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+  cudaError_t make(cudaEvent_t* e) {
+    cudaError_t rc = cudaEventCreate(e);
+    if (rc == cudaSuccess) v.push_back(*e);
+    return rc;
+  }
+};
 struct DevBufs {   // frees everything on scope exit
   std::vector<void*> v;
   ~DevBufs() { for (void* p : v) cudaFree(p); }
@@ -126,6 +135,7 @@ extern "C" {
 int32_t mcmcgpu_abi_version(void) { return MCMCGPU_ABI_VERSION; }
 const char* mcmcgpu_last_error(void) { return g_err.c_str(); }
 
+int32_t mcmcgpu_destroy(mcmcgpu_ctx* c);
 int32_t mcmcgpu_init(int32_t device_id, mcmcgpu_ctx** out) {
   if (!out) return fail(MCMCGPU_E_ARG, "out is NULL");
   int n = 0;
@@ -138,8 +148,12 @@ int32_t mcmcgpu_init(int32_t device_id, mcmcgpu_ctx** out) {
   CU(cudaSetDevice(device_id));
   mcmcgpu_ctx* c = new mcmcgpu_ctx();
   c->device = device_id;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CU(cudaMallocHost((void**)&c->h_remaining, sizeof(int32_t)));
+  cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e2 == cudaSuccess) e2 = cudaMallocHost((void**)&c->h_remaining, sizeof(int32_t));
+  if (e2 != cudaSuccess) {
+    mcmcgpu_destroy(c);
+    return fail(MCMCGPU_E_CUDA, std::string("CUDA: ") + cudaGetErrorString(e2) + " in mcmcgpu_init");
+  }
   *out = c;
   return MCMCGPU_OK;
 }
@@ -176,6 +190,7 @@ int32_t mcmcgpu_set_option(mcmcgpu_ctx* c, const char* key, int64_t value) {
 }
 
 int32_t mcmcgpu_comm_unique_id(void* out128) {
+  if (!out128) return fail(MCMCGPU_E_ARG, "out128 is NULL");
   const char* err = nullptr;
   const NcclApi* api = nccl_api(&err);
   if (!api) return fail(MCMCGPU_E_COMM, err ? err : "NCCL unavailable");
@@ -208,6 +223,8 @@ static int model_create_impl(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
   if (nhyper < 0 || nhyper > 4 || (nhyper > 0 && !hyper)) return fail(MCMCGPU_E_ARG, "bad hyper");
   CU(cudaSetDevice(c->device));
   mcmcgpu_model* m = new mcmcgpu_model();
+  // released on every failing return below (validation errors and failing CUDA calls alike)
+  struct Guard { mcmcgpu_model* m; ~Guard() { if (m) { k1_free(m->pack); if (m->d_series) cudaFree(m->d_series); delete m; } } } guard{m};
   m->ctx = c; m->family = family; m->N = N; m->d = d;
   for (int i = 0; i < nhyper; i++) m->hyper[i] = hyper[i];
   switch (family) {
@@ -216,7 +233,7 @@ static int model_create_impl(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
     case MCMCGPU_FAM_NORMAL_DSL:
       m->N = 0;
       if (nhyper < 2) { m->hyper[0] = 0.0; m->hyper[1] = 1.0; }
-      if (!(m->hyper[1] > 0)) { delete m; return fail(MCMCGPU_E_ARG, "Normal sigma must be > 0"); }
+      if (!(m->hyper[1] > 0)) { return fail(MCMCGPU_E_ARG, "Normal sigma must be > 0"); }
       break;
     case MCMCGPU_FAM_LINEAR:
       if (nhyper < 1) m->hyper[0] = 1.0;
@@ -227,36 +244,34 @@ static int model_create_impl(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
       if (nhyper < 2) m->hyper[1] = -1.0;
       // the two conventions of the reference: exp(-X*vars) (examples/logistic_regression.jl:18) and exp(X*vars)
       // (test/test_syntax.jl:18); K1 folds this sign into beta, which is exact only for +-1
-      if (m->hyper[1] != 1.0 && m->hyper[1] != -1.0) { delete m; return fail(MCMCGPU_E_ARG, "logistic sign must be +1 or -1"); }
+      if (m->hyper[1] != 1.0 && m->hyper[1] != -1.0) { return fail(MCMCGPU_E_ARG, "logistic sign must be +1 or -1"); }
       m->is_regression = true; break;
     case MCMCGPU_FAM_PROBIT:
       if (nhyper < 1) m->hyper[0] = 10.0;
       m->is_regression = true; break;
     case MCMCGPU_FAM_OU:
-      if (d != 3) { delete m; return fail(MCMCGPU_E_ARG, "Ornstein-Uhlenbeck has 3 parameters (tau, sigma, mu)"); }
+      if (d != 3) { return fail(MCMCGPU_E_ARG, "Ornstein-Uhlenbeck has 3 parameters (tau, sigma, mu)"); }
       if (nhyper < 3) { m->hyper[0] = 100.0; m->hyper[1] = 2.0; m->hyper[2] = 20.0; }
-      if (!y || N < 2) { delete m; return fail(MCMCGPU_E_ARG, "OU needs a series of length >= 2 in y"); }
+      if (!y || N < 2) { return fail(MCMCGPU_E_ARG, "OU needs a series of length >= 2 in y"); }
       break;
-    default: delete m; return fail(MCMCGPU_E_ARG, "unknown family");
+    default: return fail(MCMCGPU_E_ARG, "unknown family");
   }
   if (m->is_regression) {
-    if (!X || !y || N < 1) { delete m; return fail(MCMCGPU_E_ARG, "regression families need X (N x d) and y (N)"); }
-    if (!(m->hyper[0] > 0)) { delete m; return fail(MCMCGPU_E_ARG, "prior sd must be > 0"); }
-    if (!k1_supported(d)) { delete m; return fail(MCMCGPU_E_ARG, "regression families support 1 <= d <= 200 in this build"); }
-    if (row_sharded && !c->comm) { delete m; return fail(MCMCGPU_E_COMM, "row_sharded model needs mcmcgpu_comm_init first"); }
+    if (!X || !y || N < 1) { return fail(MCMCGPU_E_ARG, "regression families need X (N x d) and y (N)"); }
+    if (!(m->hyper[0] > 0)) { return fail(MCMCGPU_E_ARG, "prior sd must be > 0"); }
+    if (!k1_supported(d)) { return fail(MCMCGPU_E_ARG, "regression families support 1 <= d <= 200 in this build"); }
+    if (row_sharded && !c->comm) { return fail(MCMCGPU_E_COMM, "row_sharded model needs mcmcgpu_comm_init first"); }
     m->row_sharded = row_sharded != 0;
     if (on_device) {
       CU(k1_pack(m->pack, X, y, N, d, c->stream));
       CU(cudaStreamSynchronize(c->stream));
     } else {
       double *dX = nullptr, *dy = nullptr;
-      CU(dalloc(&dX, (size_t)(N * d)));
-      CU(dalloc(&dy, (size_t)N));
-      CU(cudaMemcpyAsync(dX, X, sizeof(double) * (size_t)(N * d), cudaMemcpyHostToDevice, c->stream));
-      CU(cudaMemcpyAsync(dy, y, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, c->stream));
+      DevBufs staging;                       // the column-major upload lives only until the tile images are packed
+      CU(staging.up(&dX, X, (size_t)(N * d), c->stream));
+      CU(staging.up(&dy, y, (size_t)N, c->stream));
       CU(k1_pack(m->pack, dX, dy, N, d, c->stream));
       CU(cudaStreamSynchronize(c->stream));
-      cudaFree(dX); cudaFree(dy);
     }
     for (int i = 0; i < 4; i++) m->k1_hyper[i] = m->hyper[i];
     if (family == MCMCGPU_FAM_LINEAR) m->k1_hyper[3] = std::log(m->hyper[1]);
@@ -266,6 +281,7 @@ static int model_create_impl(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
     CU(cudaMemcpyAsync(m->d_series, y, sizeof(double) * (size_t)N, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
   }
+  guard.m = nullptr;
   *out = m;
   return MCMCGPU_OK;
 }
@@ -555,8 +571,9 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
   int64_t upto = (nsteps < 0 || from + nsteps > R->r.last) ? R->r.last : from + nsteps;
   const int64_t seg = upto - from;
   if (seg <= 0) return fail(MCMCGPU_E_ARG, "nsteps must be >= 1");
+  Events events;
   cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(events.make(&e0)); CU(events.make(&e1));
   int64_t launches = 0, waves = 0;
   double eval_ms = 0.0;
   CU(cudaMemsetAsync(R->n_evals, 0, sizeof(unsigned long long), st));
@@ -653,7 +670,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       if (known >= 0 && waves >= known) break;
       const double* pp; int ns;
       cudaEvent_t a0 = nullptr, a1 = nullptr;
-      if (c->time_eval) { CU(cudaEventCreate(&a0)); CU(cudaEventCreate(&a1)); CU(cudaEventRecord(a0, st)); }
+      if (c->time_eval) { CU(events.make(&a0)); CU(events.make(&a1)); CU(cudaEventRecord(a0, st)); }
       int rc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad || first,
                          first ? nullptr : need_ll_flags, R->phase, R->remaining, &pp, &ns);
       if (rc != MCMCGPU_OK) return rc;
@@ -675,7 +692,6 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       CU(cudaStreamSynchronize(st));
       for (size_t k = 0; k + 1 < evs.size(); k += 2) {
         float ms = 0; cudaEventElapsedTime(&ms, evs[k], evs[k + 1]); eval_ms += ms;
-        cudaEventDestroy(evs[k]); cudaEventDestroy(evs[k + 1]);
       }
     }
   }
@@ -683,7 +699,6 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
   CU(cudaStreamSynchronize(st));
   float ms = 0;
   CU(cudaEventElapsedTime(&ms, e0, e1));
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   R->executed = true;
   R->step_limit = upto;
   unsigned long long nev = 0;
@@ -767,9 +782,10 @@ static int fetch_chunked(mcmcgpu_run* R, const double* dev, int64_t K, double* h
   if (chunk > C) chunk = C;
   double* stage[2] = {nullptr, nullptr};
   cudaEvent_t done[2];
-  CU(dalloc(&stage[0], (size_t)(chunk * K)));
-  CU(dalloc(&stage[1], (size_t)(chunk * K)));
-  CU(cudaEventCreate(&done[0])); CU(cudaEventCreate(&done[1]));
+  DevBufs bufs; Events events;
+  CU(bufs.get(&stage[0], (size_t)(chunk * K), st, false));
+  CU(bufs.get(&stage[1], (size_t)(chunk * K), st, false));
+  CU(events.make(&done[0])); CU(events.make(&done[1]));
   int b = 0; bool used[2] = {false, false};
   for (int64_t c0 = 0; c0 < C; c0 += chunk, b ^= 1) {
     int64_t nc = (C - c0 < chunk) ? C - c0 : chunk;
@@ -780,8 +796,6 @@ static int fetch_chunked(mcmcgpu_run* R, const double* dev, int64_t K, double* h
     used[b] = true;
   }
   CU(cudaStreamSynchronize(st));
-  cudaFree(stage[0]); cudaFree(stage[1]);
-  cudaEventDestroy(done[0]); cudaEventDestroy(done[1]);
   return MCMCGPU_OK;
 }
 
@@ -1066,8 +1080,9 @@ int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt,
     CU(B.up(&a, inj_normals, (size_t)(K * d), st)); CU(B.up(&b, inj_uniforms, (size_t)K, st)); CU(B.up(&r, inj_res_uniforms, (size_t)K, st));
     A.inj_normals = a; A.inj_uniforms = b; A.inj_res = r;
   }
+  Events events;
   cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(events.make(&e0)); CU(events.make(&e1));
   CU(cudaEventRecord(e0, st));
   int64_t launches = 0;
   for (int64_t i = 1; i <= steps; i++) {                                                        // SeqMC.jl:62
@@ -1095,7 +1110,6 @@ int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt,
   CU(cudaMemcpyAsync(&nev, A.nevals, sizeof(nev), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (out_nresamples) *out_nresamples = (int64_t)nres;
   if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = steps * nt; info->n_launches = launches; info->eval_ms = 0; }
   return MCMCGPU_OK;
@@ -1135,8 +1149,9 @@ int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_
   A.at = nullptr;
   if (out_at) CU(B.get(&A.at, (size_t)(nrep * S), st));
   CU(B.get(&A.status, (size_t)nrep, st)); CU(B.get(&A.nevals, 1, st));
+  Events events;
   cudaEvent_t e0, e1;
-  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  CU(events.make(&e0)); CU(events.make(&e1));
   CU(cudaEventRecord(e0, st));
   CU(launch_serialtemp(A, st));
   CU(cudaEventRecord(e1, st));
@@ -1148,7 +1163,6 @@ int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_
   CU(cudaMemcpyAsync(&nev, A.nevals, sizeof(nev), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = 0; info->n_launches = 1; info->eval_ms = 0; }
   for (int32_t v : stt) if (v) return fail(MCMCGPU_E_SUPPORT, "Initial values out of model support, try other values");
   return MCMCGPU_OK;
