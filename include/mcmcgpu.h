@@ -39,7 +39,7 @@ extern "C" {
 #define MCMCGPU_FAM_NORMAL_FN 0  /* README.md:60,63  v -> -dot(v,v), grad -2v                          */
 #define MCMCGPU_FAM_NORMAL_DSL 1 /* README.md:67-72  v ~ Normal(mu, sigma)     hyper = {mu, sigma}     */
 #define MCMCGPU_FAM_LINEAR 2     /* examples/linear_regression.jl:14-18        hyper = {prior_sd, noise_sd} */
-#define MCMCGPU_FAM_LOGISTIC 3   /* examples/logistic_regression.jl:16-20      hyper = {prior_sd, sign}  (sign -1: exp(-X*b); +1: test/test_syntax.jl:18) */
+#define MCMCGPU_FAM_LOGISTIC 3   /* examples/logistic_regression.jl:16-20      hyper = {prior_sd, sign}  (sign -1: exp(-X*b); +1: test/test_syntax.jl:18; any other value is MCMCGPU_E_ARG) */
 #define MCMCGPU_FAM_PROBIT 4     /* examples/probit_regression.jl:18-41        hyper = {prior_sd}        */
 #define MCMCGPU_FAM_OU 5         /* examples/ornstein.jl:19-27                 hyper = {tau_hi, sigma_hi, mu_hi}; y = series, d = 3 */
 #define MCMCGPU_FAM_ABS_NORMAL 6 /* README.md:253-259  y = abs(x); y ~ Normal(mu, sigma)   hyper = {mu, sigma} (the SeqMC ladder) */
