@@ -371,6 +371,8 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
       double acc[NR][2];
 #pragma unroll
       for (int n = 0; n < NR; n++) { acc[n][0] = 0.0; acc[n][1] = 0.0; }
+      // (measured and dropped: splitting the feature range into two halves for 2*NR independent accumulator chains:
+      //  43.8 instead of 35.4 ms per wave)
 #pragma unroll 4
       for (int ks = 0; ks < ksn; ks++) {
         const double av = bfrag[4 * ks];
@@ -428,9 +430,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
               for (int s = 0; s < 2; s++) {
                 const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
                 const bool y1 = (y1mask >> i) & 1u;
-                double arg = y1 ? pv[i] : 1.0 - pv[i];                          // Bernoulli: p1, or p0 = 1 - p1 by subtraction
-                if ((rowbase + lr) >= N) arg = 1.0;                             // padded rows contribute log(1) = 0
-                ll1 += log_tab129(arg, ltab);
+                const double arg = y1 ? pv[i] : 1.0 - pv[i];                    // Bernoulli: p1, or p0 = 1 - p1 by subtraction
+                const double lg = log_tab129(arg, ltab);
+                ll1 += ((rowbase + lr) < N) ? lg : 0.0;                         // padded rows contribute an exact zero
               }
           }
           done = true;
