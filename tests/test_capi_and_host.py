@@ -175,3 +175,34 @@ def test_struct_layouts_match_the_header(capi, tmp_path):
         assert set(fields) == {n for n, _ in st._fields_}, line
         for name, off in fields.items():
             assert getattr(st, name).offset == off, (st.__name__, name)
+
+
+def test_generated_link_tables_are_reproducible():
+    """csrc/exp_table.h and csrc/log_table.h hold exactly what tools/gen_exp_table.py / gen_log_table.py compute (mpmath),
+    and the replayed device arithmetic built on them is accurate to a few 1e-16 (the same replay the generators print)."""
+    import importlib.util
+    import re
+    import mpmath as mp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def load(name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, "tools", name + ".py"))
+        mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+        return mod
+
+    def header_values(fn):
+        txt = open(os.path.join(root, "mcmc.jl_b200", "csrc", fn)).read()
+        return [float.fromhex(v) for v in re.findall(r"-?0x[0-9a-f.]+p[+-]\d+", txt)]
+
+    ge, gl = load("gen_exp_table"), load("gen_log_table")
+    T = ge.table()
+    assert header_values("exp_table.h") == T
+    R, L = gl.table()
+    assert header_values("log_table.h") == [v for pair in zip(R, L) for v in pair]
+    rng = np.random.default_rng(7)
+    for x in np.concatenate([rng.uniform(-40, 40, 300), rng.uniform(-700, 700, 100)]):
+        ref = mp.exp(mp.mpf(float(x)))
+        assert abs(mp.mpf(ge.exp_dev(float(x), T)) - ref) <= mp.mpf(3e-16) * ref
+    for x in np.concatenate([rng.uniform(1e-12, 1, 300), 1 - 10 ** rng.uniform(-15, -2, 100)]):
+        ref = mp.log(mp.mpf(float(x)))
+        assert abs(mp.mpf(gl.log_dev(float(x), R, L)) - ref) <= mp.mpf(3e-16) * abs(ref) + mp.mpf(3e-18)
