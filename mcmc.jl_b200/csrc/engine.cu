@@ -59,8 +59,15 @@ struct mcmcgpu_model {
   }
 };
 
+// Run and temporary buffers come from the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync on the
+// context's stream): with a release threshold the pool keeps freed blocks, so creating, fetching and destroying a run costs
+// no cudaMalloc / cudaFree round trips to the driver (measured on a 5-step cfg3 run: fetch 6..400 ms -> a few ms).
+// t_stream is the stream of the context the current API call works on (set by use_ctx at every entry point).
+static thread_local cudaStream_t t_stream = nullptr;
+static cudaError_t use_ctx(const mcmcgpu_ctx* c);
 template <typename T>
-static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)); }
+static cudaError_t dalloc(T** p, size_t n) { return cudaMallocAsync((void**)p, sizeof(T) * (n ? n : 1), t_stream); }
+static void dfree(void* p) { if (p) cudaFreeAsync(p, t_stream); }
 
 struct mcmcgpu_run {
   mcmcgpu_model* m = nullptr;
@@ -103,6 +110,8 @@ struct mcmcgpu_run {
   }
 };
 
+static cudaError_t use_ctx(const mcmcgpu_ctx* c) { t_stream = c->stream; return cudaSetDevice(c->device); }
+
 // ------------------------------------------------------------------------------------------------
 struct Events {    // CUDA events destroyed on scope exit (every return path of the CU() macro included)
   std::vector<cudaEvent_t> v;
@@ -115,7 +124,7 @@ struct Events {    // CUDA events destroyed on scope exit (every return path of 
 };
 struct DevBufs {   // frees everything on scope exit
   std::vector<void*> v;
-  ~DevBufs() { for (void* p : v) cudaFree(p); }
+  ~DevBufs() { for (void* p : v) dfree(p); }
   template <typename T> cudaError_t get(T** p, size_t n, cudaStream_t st, bool zero = true) {
     cudaError_t e = dalloc(p, n);
     if (e != cudaSuccess) return e;
@@ -150,6 +159,13 @@ int32_t mcmcgpu_init(int32_t device_id, mcmcgpu_ctx** out) {
   c->device = device_id;
   cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaMallocHost((void**)&c->h_remaining, sizeof(int32_t));
+  if (e2 == cudaSuccess) {
+    // keep up to 2 GB of freed run / temporary buffers in the device's default memory pool (dalloc / dfree above)
+    cudaMemPool_t pool = nullptr;
+    e2 = cudaDeviceGetDefaultMemPool(&pool, device_id);
+    uint64_t keep = 2ull << 30;
+    if (e2 == cudaSuccess) e2 = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   if (e2 != cudaSuccess) {
     mcmcgpu_destroy(c);
     return fail(MCMCGPU_E_CUDA, std::string("CUDA: ") + cudaGetErrorString(e2) + " in mcmcgpu_init");
@@ -160,8 +176,11 @@ int32_t mcmcgpu_init(int32_t device_id, mcmcgpu_ctx** out) {
 
 int32_t mcmcgpu_destroy(mcmcgpu_ctx* c) {
   if (!c) return MCMCGPU_OK;
-  cudaSetDevice(c->device);
+  use_ctx(c);
   if (c->comm) { const NcclApi* api = nccl_api(nullptr); if (api) api->CommDestroy(c->comm); }
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  cudaMemPool_t pool = nullptr;
+  if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);   // cached blocks back to the driver
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->h_remaining) cudaFreeHost(c->h_remaining);
   delete c;
@@ -170,10 +189,12 @@ int32_t mcmcgpu_destroy(mcmcgpu_ctx* c) {
 
 int32_t mcmcgpu_set_stream(mcmcgpu_ctx* c, void* cuda_stream) {
   if (!c) return fail(MCMCGPU_E_ARG, "ctx is NULL");
-  CU(cudaSetDevice(c->device));
-  if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  CU(use_ctx(c));
+  if (c->stream) cudaStreamSynchronize(c->stream);      // everything allocated / queued in the old stream's order is complete
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
   else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  t_stream = c->stream;
   return MCMCGPU_OK;
 }
 
@@ -206,7 +227,7 @@ int32_t mcmcgpu_comm_init(mcmcgpu_ctx* c, int32_t rank, int32_t nranks, const vo
   const char* err = nullptr;
   const NcclApi* api = nccl_api(&err);
   if (!api) return fail(MCMCGPU_E_COMM, err ? err : "NCCL unavailable");
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   NcclUniqueId id;
   memcpy(&id, unique_id128, sizeof(id));
   int rc = api->CommInitRank(&c->comm, nranks, id, rank);
@@ -221,10 +242,10 @@ static int model_create_impl(mcmcgpu_ctx* c, int32_t family, int64_t N, int64_t 
   if (!c || !out) return fail(MCMCGPU_E_ARG, "ctx/out is NULL");
   if (d < 1) return fail(MCMCGPU_E_ARG, "d must be >= 1");
   if (nhyper < 0 || nhyper > 4 || (nhyper > 0 && !hyper)) return fail(MCMCGPU_E_ARG, "bad hyper");
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   mcmcgpu_model* m = new mcmcgpu_model();
   // released on every failing return below (validation errors and failing CUDA calls alike)
-  struct Guard { mcmcgpu_model* m; ~Guard() { if (m) { k1_free(m->pack); if (m->d_series) cudaFree(m->d_series); delete m; } } } guard{m};
+  struct Guard { mcmcgpu_model* m; ~Guard() { if (m) { k1_free(m->pack); if (m->d_series) dfree(m->d_series); delete m; } } } guard{m};
   m->ctx = c; m->family = family; m->N = N; m->d = d;
   for (int i = 0; i < nhyper; i++) m->hyper[i] = hyper[i];
   switch (family) {
@@ -299,9 +320,9 @@ int32_t mcmcgpu_model_create_device(mcmcgpu_ctx* c, int32_t family, int64_t N, i
 
 int32_t mcmcgpu_model_destroy(mcmcgpu_model* m) {
   if (!m) return MCMCGPU_OK;
-  cudaSetDevice(m->ctx->device);
+  use_ctx(m->ctx);
   k1_free(m->pack);
-  if (m->d_series) cudaFree(m->d_series);
+  if (m->d_series) dfree(m->d_series);
   delete m;
   return MCMCGPU_OK;
 }
@@ -349,12 +370,12 @@ extern "C" {
 int32_t mcmcgpu_logtarget_grad(mcmcgpu_model* m, const double* B, int64_t C, double* out_lt, double* out_grad) {
   if (!m || !B || !out_lt || C < 1) return fail(MCMCGPU_E_ARG, "bad arguments");
   mcmcgpu_ctx* c = m->ctx;
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   cudaStream_t st = c->stream;
   const int64_t d = m->d, Cp = round_up(C, K1_CHAINS);
   int nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp)) : 1;
   double *hB = nullptr, *q = nullptr, *part = nullptr, *red = nullptr, *lt = nullptr, *grad = nullptr, *gout = nullptr;
-  struct Freer { double** p[7]; ~Freer() { for (auto pp : p) if (*pp) { cudaFree(*pp); *pp = nullptr; } } } freer{{&hB, &q, &part, &red, &lt, &grad, &gout}};
+  struct Freer { double** p[7]; ~Freer() { for (auto pp : p) if (*pp) { dfree(*pp); *pp = nullptr; } } } freer{{&hB, &q, &part, &red, &lt, &grad, &gout}};
   CU(dalloc(&hB, (size_t)(C * d)));
   CU(dalloc(&q, (size_t)(d * Cp)));
   CU(dalloc(&part, (size_t)(nsplit * (d + 2) * Cp)));
@@ -416,9 +437,9 @@ static int check_cfg(const mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
 
 int32_t mcmcgpu_run_destroy(mcmcgpu_run* run) {
   if (!run) return MCMCGPU_OK;
-  cudaSetDevice(run->m->ctx->device);
+  use_ctx(run->m->ctx);
   cudaStreamSynchronize(run->m->ctx->stream);
-  for (void* p : run->owned) cudaFree(p);
+  for (void* p : run->owned) dfree(p);
   delete run;
   return MCMCGPU_OK;
 }
@@ -430,7 +451,7 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   if (rc != MCMCGPU_OK) return rc;
   if ((inj_normals == nullptr) != (inj_uniforms == nullptr)) return fail(MCMCGPU_E_ARG, "inject both normals and uniforms or neither");
   mcmcgpu_ctx* c = m->ctx;
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   cudaStream_t st = c->stream;
   mcmcgpu_run* R = new mcmcgpu_run();
   R->m = m; R->s = *s; R->r = *r;
@@ -455,7 +476,7 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     RCU(R->alloc(&R->init, (size_t)(d * Cp)));
     RCU(transpose_to_chain_minor(tmp, R->init, C, d, Cp, st));
     RCU(cudaStreamSynchronize(st));
-    cudaFree(tmp);
+    dfree(tmp);
   } else {
     RCU(R->alloc(&R->init, (size_t)d));
     RCU(cudaMemcpyAsync(R->init, init, sizeof(double) * (size_t)d, cudaMemcpyHostToDevice, st));
@@ -475,13 +496,13 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     RCU(R->alloc(&R->inj_normals, (size_t)(K * Cp)));
     RCU(transpose_to_chain_minor(tmp, R->inj_normals, C, K, Cp, st));
     RCU(cudaStreamSynchronize(st));
-    cudaFree(tmp);
+    dfree(tmp);
     RCU(dalloc(&tmp, (size_t)(C * Ku)));
     RCU(cudaMemcpyAsync(tmp, inj_uniforms, sizeof(double) * (size_t)(C * Ku), cudaMemcpyHostToDevice, st));
     RCU(R->alloc(&R->inj_uniforms, (size_t)(Ku * Cp)));
     RCU(transpose_to_chain_minor(tmp, R->inj_uniforms, C, Ku, Cp, st));
     RCU(cudaStreamSynchronize(st));
-    cudaFree(tmp);
+    dfree(tmp);
   }
   // outputs
   RCU(R->alloc(&R->samples, (size_t)(S * d * Cp), false));
@@ -564,7 +585,7 @@ __global__ void wave_init_kernel(int32_t* phase, int32_t* remaining, double* q, 
 static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) {
   mcmcgpu_model* m = R->m;
   mcmcgpu_ctx* c = m->ctx;
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   cudaStream_t st = c->stream;
   const int64_t from = R->started ? R->step_limit : R->step0;
   if (from >= R->r.last) return fail(MCMCGPU_E_STATE, "run has already reached its last step");
@@ -736,7 +757,7 @@ int32_t mcmcgpu_run_set_state(mcmcgpu_run* R, int64_t step0, const double* leaps
   if (R->engine != MCMCGPU_ENGINE_WAVE) return fail(MCMCGPU_E_STATE, "mcmcgpu_run_set_state needs engine WAVE");
   if (step0 < 0 || step0 >= R->r.last) return fail(MCMCGPU_E_ARG, "step0 must be in [0, last)");
   if (R->r.first <= step0) return fail(MCMCGPU_E_ARG, "the kept range must start after step0");
-  CU(cudaSetDevice(R->m->ctx->device));
+  CU(use_ctx(R->m->ctx));
   R->step0 = step0;
   if (leapstep || dual_leapstep || dualH) {
     if (R->s.kind != MCMCGPU_HMCDA) return fail(MCMCGPU_E_ARG, "step-size state applies to HMCDA");
@@ -755,7 +776,7 @@ int32_t mcmcgpu_run_get_state(mcmcgpu_run* R, double* pars, double* leapstep, do
   if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
   if (R->engine != MCMCGPU_ENGINE_WAVE) return fail(MCMCGPU_E_STATE, "mcmcgpu_run_get_state needs engine WAVE");
-  CU(cudaSetDevice(R->m->ctx->device));
+  CU(use_ctx(R->m->ctx));
   cudaStream_t st = R->m->ctx->stream;
   if (pars) {
     double* tmp = nullptr;
@@ -763,7 +784,7 @@ int32_t mcmcgpu_run_get_state(mcmcgpu_run* R, double* pars, double* leapstep, do
     CU(transpose_to_chain_major(R->cur_pars, tmp, 0, R->C, R->d, R->Cp, st));
     CU(cudaMemcpyAsync(pars, tmp, sizeof(double) * (size_t)(R->C * R->d), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(tmp);
+    dfree(tmp);
   }
   const double* src[3] = {R->da_leapstep, R->da_dual, R->da_dualH};
   double* dst[3] = {leapstep, dual_leapstep, dualH};
@@ -802,7 +823,7 @@ static int fetch_chunked(mcmcgpu_run* R, const double* dev, int64_t K, double* h
 int32_t mcmcgpu_run_fetch(mcmcgpu_run* R, double* out_samples, double* out_grads, uint8_t* out_accept, double* out_logtarget) {
   if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
-  CU(cudaSetDevice(R->m->ctx->device));
+  CU(use_ctx(R->m->ctx));
   cudaStream_t st = R->m->ctx->stream;
   int rc;
   if (out_samples) { rc = fetch_chunked(R, R->samples, R->S * R->d, out_samples); if (rc) return rc; }
@@ -820,7 +841,7 @@ int32_t mcmcgpu_run_fetch(mcmcgpu_run* R, double* out_samples, double* out_grads
     CU(transpose_to_chain_major_u8(R->accept, tmp, 0, R->C, R->S, R->Cp, st));
     CU(cudaMemcpyAsync(out_accept, tmp, (size_t)(R->C * R->S), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(tmp);
+    dfree(tmp);
   }
   return MCMCGPU_OK;
 }
@@ -834,7 +855,7 @@ int32_t mcmcgpu_run_fetch_rb(mcmcgpu_run* R, double* out_rb) {
   if (!R || !out_rb) return fail(MCMCGPU_E_ARG, "NULL argument");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
   if (!R->rb) return fail(MCMCGPU_E_STATE, "Rao-Blackwell sums were not stored (store_rb = 0)");
-  CU(cudaSetDevice(R->m->ctx->device));
+  CU(use_ctx(R->m->ctx));
   return fetch_chunked(R, R->rb, R->S * R->d, out_rb);
 }
 
@@ -842,7 +863,7 @@ int32_t mcmcgpu_run_fetch_diag(mcmcgpu_run* R, double* out_eps, int64_t* out_nle
   if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
   if (!R->has_diag) return fail(MCMCGPU_E_STATE, "sampler has no step-size diagnostics");
-  CU(cudaSetDevice(R->m->ctx->device));
+  CU(use_ctx(R->m->ctx));
   cudaStream_t st = R->m->ctx->stream;
   if (out_eps) { int rc = fetch_chunked(R, R->eps, R->S, out_eps); if (rc) return rc; }
   if (out_nleaps) {
@@ -853,7 +874,7 @@ int32_t mcmcgpu_run_fetch_diag(mcmcgpu_run* R, double* out_eps, int64_t* out_nle
     i32_to_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->nleaps, wide, n);
     CU(cudaGetLastError());
     int rc = fetch_chunked(R, reinterpret_cast<const double*>(wide), R->S, reinterpret_cast<double*>(out_nleaps));
-    cudaFree(wide);
+    dfree(wide);
     if (rc) return rc;
   }
   return MCMCGPU_OK;
@@ -888,11 +909,11 @@ static int stats_common(mcmcgpu_ctx* c, const double* samples, const uint8_t* ac
     CU(launch_accept_rate(accept, S, C, Cp, rate, st));
     CU(cudaMemcpyAsync(out_accept_rate, rate, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    cudaFree(rate);
+    dfree(rate);
   }
   CU(cudaStreamSynchronize(st));
-  cudaFree(tmp);
-  for (int k = 0; k < 5; k++) if (outs[k]) cudaFree(outs[k]);
+  dfree(tmp);
+  for (int k = 0; k < 5; k++) if (outs[k]) dfree(outs[k]);
   return MCMCGPU_OK;
 }
 
@@ -900,7 +921,7 @@ int32_t mcmcgpu_run_stats(mcmcgpu_run* R, int32_t vtype, int64_t maxlag, int64_t
                           double* out_var, double* out_ess, double* out_actime, double* out_accept_rate) {
   if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
-  CU(cudaSetDevice(R->m->ctx->device));
+  CU(use_ctx(R->m->ctx));
   return stats_common(R->m->ctx, R->samples, R->accept, R->S, R->d, R->C, R->Cp, vtype, maxlag, batchlen, out_mean, out_var_iid,
                       out_var, out_ess, out_actime, out_accept_rate);
 }
@@ -908,7 +929,7 @@ int32_t mcmcgpu_run_stats(mcmcgpu_run* R, int32_t vtype, int64_t maxlag, int64_t
 int32_t mcmcgpu_stats(mcmcgpu_ctx* c, const double* samples, int64_t S, int64_t d, int64_t C, int32_t vtype, int64_t maxlag,
                       int64_t batchlen, double* out_mean, double* out_var_iid, double* out_var, double* out_ess, double* out_actime) {
   if (!c || !samples || S < 1 || d < 1 || C < 1) return fail(MCMCGPU_E_ARG, "bad arguments");
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   cudaStream_t st = c->stream;
   const int64_t Cp = round_up(C, K1_CHAINS), K = S * d;
   double *tmp = nullptr, *dev = nullptr;
@@ -918,7 +939,7 @@ int32_t mcmcgpu_stats(mcmcgpu_ctx* c, const double* samples, int64_t S, int64_t 
   CU(transpose_to_chain_minor(tmp, dev, C, K, Cp, st));
   int rc = stats_common(c, dev, nullptr, S, d, C, Cp, vtype, maxlag, batchlen, out_mean, out_var_iid, out_var, out_ess, out_actime, nullptr);
   cudaStreamSynchronize(st);
-  cudaFree(tmp); cudaFree(dev);
+  dfree(tmp); dfree(dev);
   return rc;
 }
 
@@ -956,14 +977,14 @@ int32_t mcmcgpu_run_zv(mcmcgpu_run* R, int32_t order, double* out_zv, double* ou
   if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
   if (!R->grads) return fail(MCMCGPU_E_STATE, "ZV needs the stored gradients (store_grad = 1)");
-  CU(cudaSetDevice(R->m->ctx->device));
+  CU(use_ctx(R->m->ctx));
   return zv_common(R->m->ctx, R->samples, R->grads, R->S, R->d, R->C, R->Cp, order, out_zv, out_a);
 }
 
 int32_t mcmcgpu_zv(mcmcgpu_ctx* c, const double* samples, const double* grads, int64_t S, int64_t d, int64_t C, int32_t order,
                    double* out_zv, double* out_a) {
   if (!c || !samples || !grads || S < 1 || d < 1 || C < 1) return fail(MCMCGPU_E_ARG, "bad arguments");
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   cudaStream_t st = c->stream;
   const int64_t Cp = round_up(C, K1_CHAINS), K = S * d;
   DevBufs B;
@@ -1001,7 +1022,7 @@ int32_t mcmcgpu_run_chains(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
 int32_t mcmcgpu_philox_draws(mcmcgpu_ctx* c, uint64_t seed, int64_t chain_offset, int64_t nchains, int64_t d, int64_t last,
                              double* out_normals, double* out_uniforms) {
   if (!c || !out_normals || !out_uniforms || nchains < 1 || d < 1 || last < 0) return fail(MCMCGPU_E_ARG, "bad arguments");
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   cudaStream_t st = c->stream;
   double *zn = nullptr, *un = nullptr;
   const int64_t n = nchains * (last + 1);
@@ -1011,7 +1032,7 @@ int32_t mcmcgpu_philox_draws(mcmcgpu_ctx* c, uint64_t seed, int64_t chain_offset
   CU(cudaMemcpyAsync(out_normals, zn, sizeof(double) * (size_t)(n * d), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(out_uniforms, un, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  cudaFree(zn); cudaFree(un);
+  dfree(zn); dfree(un);
   return MCMCGPU_OK;
 }
 
@@ -1047,7 +1068,7 @@ int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt,
   SeqArgs A;
   int rc = fill_tasks(A.T, family, d, nt, hypers, samplers);
   if (rc != MCMCGPU_OK) return rc;
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   cudaStream_t st = c->stream;
   DevBufs B;
   const int64_t Np = round_up(npart, 64), S = (steps - burnin) * npart, K = steps * nt * npart * (c->comm ? c->nranks : 1);
@@ -1130,7 +1151,7 @@ int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_
   TempArgs A;
   int rc = fill_tasks(A.T, family, d, nt, hypers, samplers);
   if (rc != MCMCGPU_OK) return rc;
-  CU(cudaSetDevice(c->device));
+  CU(use_ctx(c));
   cudaStream_t st = c->stream;
   DevBufs B;
   const int64_t S = steps - burnin;
