@@ -117,7 +117,6 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
   const double lt_q = F.lt;
   unsigned long long nev = (ph != PH_PAUSE) ? 1 : 0;
   bool begin = false;
-  bool accepted_now = false;
 
   auto uniform = [&](int64_t step) -> double {
     return W.inj_uniforms ? W.inj_uniforms[step * Cp + c] : philox_uniform(R.seed, gchain, (uint32_t)step);
@@ -278,7 +277,6 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       W.tn_acc[c] = 0; W.tn_prop[c] = 0;
     }
     i++; begin = true;
-    (void)accepted_now;
   }
 
   if (begin) {
