@@ -348,7 +348,7 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
     memcpy(pars, init, sizeof(double) * (size_t)d);
     double lt = orc_eval(m, pars);
     if (!isfinite(lt)) rc = -1;
-    for (int64_t i = 1; rc == 0 && i <= len; i++) {
+    for (int64_t i = s->start_step + 1; rc == 0 && i <= len; i++) {
       const double* z = normals + i * d;
       for (int64_t j = 0; j < d; j++) prop[j] = pars[j] + z[j] * sc[j]; /* :59 */
       double plt = orc_eval(m, prop);                                    /* :60 */
@@ -372,7 +372,7 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
     double lt = orc_evalallg(m, pars, grad); nev++;
     if (!isfinite(lt)) rc = -1;
     double tune_step = s->scale; int64_t accepted = 0, proposed = 0; /* EmpiricalMALATune :19-43 */
-    for (int64_t i = 1; rc == 0 && i <= len; i++) {
+    for (int64_t i = s->start_step + 1; rc == 0 && i <= len; i++) {
       double h;
       if (s->tuner_on) { proposed += 1; h = tune_step; } else h = s->scale; /* :91-96 */
       const double* z = normals + i * d;
@@ -409,7 +409,7 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
     hs_calc(&st0, m, &nev);                                       /* :119-120 */
     if (!isfinite(st0.logTarget)) rc = -1;                        /* :121 */
     int64_t t_nleaps = s->nleaps; double t_step = s->scale; int64_t accepted = 0, proposed = 0; /* :20-47 */
-    for (int64_t i = 1; rc == 0 && i <= len; i++) {
+    for (int64_t i = s->start_step + 1; rc == 0 && i <= len; i++) {
       int64_t nLeaps; double leapStep;
       if (s->tuner_on) { proposed += 1; nLeaps = t_nleaps; leapStep = t_step; }
       else { nLeaps = s->nleaps; leapStep = s->scale; }           /* :129-134 */
@@ -473,8 +473,11 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
         leapStep = ls;
       }
       mu = log(10.0 * leapStep);                                  /* :92 */
+      /* test aid (true resume, the engine's mcmcgpu_run_set_state): continue from a saved dual-averaging state.
+       * mu keeps the reference's value log(10 * 1.0): the initial search always returns 1.0 (see above). */
+      if (s->da_state) { leapStep = s->da_state[0]; dualLeapStep = s->da_state[1]; dualH = s->da_state[2]; }
     }
-    for (int64_t i = 1; rc == 0 && i <= len; i++) {
+    for (int64_t i = s->start_step + 1; rc == 0 && i <= len; i++) {
       memcpy(st0.m, normals + i * d, sizeof(double) * (size_t)d); /* :100 */
       hs_update(&st0, d);                                         /* :101 */
       hs_copy(&st, &st0, d);                                      /* :102 */
@@ -519,7 +522,7 @@ int32_t orc_run_chain(const orc_model* m, const orc_sampler* s, const orc_range*
     memcpy(pars, init, sizeof(double) * (size_t)d);
     double lt = orc_eval(m, pars);
     if (!isfinite(lt)) rc = -1;                                               /* :53 */
-    for (int64_t i = 1; rc == 0 && i <= len; i++) {
+    for (int64_t i = s->start_step + 1; rc == 0 && i <= len; i++) {
       const double* z = normals + i * d;                                      /* :59 rvec */
       for (int64_t a = 0; a < d; a++) {                                       /* :60 pars + S * rvec */
         double acc = 0.0;

@@ -64,6 +64,11 @@ typedef struct {
   /* HMC storeLeaps (HMC.jl:145-150): when rb_out != NULL (S x d) the leap states are kept for the step and the
    * Rao-Blackwell sums of mean_rb_hmc (src/stats/mean.jl:11-35) are written per kept step. */
   double* rb_out;
+  /* test aid (not in the reference, whose resume restarts from model.init, SerialMC.jl:93-97): the chain starts at
+   * step start_step + 1 from `init` (draw columns keep their absolute step index), and, for HMCDA, da_state != NULL
+   * restores {leapStep, dualLeapStep, dualH} -- the counterpart of the engine's mcmcgpu_run_set_state. */
+  int64_t start_step;
+  const double* da_state;
 } orc_sampler;
 
 typedef struct {

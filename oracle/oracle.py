@@ -32,7 +32,8 @@ class _Sampler(C.Structure):
                 ("rate", C.c_double), ("len", C.c_double), ("shrinkage", C.c_double),
                 ("t0", C.c_double), ("step", C.c_double), ("max_leaps", C.c_int64),
                 ("tuner_on", C.c_int32), ("adapt_step", C.c_int32), ("max_step", C.c_int32),
-                ("target_path", C.c_double), ("target_rate", C.c_double), ("force_eps", C.c_void_p), ("rb_out", C.c_void_p)]
+                ("target_path", C.c_double), ("target_rate", C.c_double), ("force_eps", C.c_void_p), ("rb_out", C.c_void_p),
+                ("start_step", C.c_int64), ("da_state", C.c_void_p)]
 
 
 class _Range(C.Structure):
@@ -110,8 +111,13 @@ class Model:
 
 
 def sampler(kind, scale=1.0, nleaps=10, rate=0.65, len=2.0, shrinkage=0.05, t0=10.0, step=0.75, max_leaps=0,
-            tuner=None, force_eps=None, rb_out=None):
+            tuner=None, force_eps=None, rb_out=None, start_step=0, da_state=None):
     s = _Sampler()
+    s.start_step = int(start_step)
+    if da_state is not None:
+        s._da = np.ascontiguousarray(da_state, dtype=np.float64)      # (leapStep, dualLeapStep, dualH); keep alive
+        assert s._da.shape == (3,)
+        s.da_state = s._da.ctypes.data
     if rb_out is not None:
         assert rb_out.flags["C_CONTIGUOUS"] and rb_out.dtype == np.float64
         s._rb = rb_out

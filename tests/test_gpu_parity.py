@@ -700,3 +700,129 @@ def test_readme_snippet():
     assert np.median(mj.acceptance(batch)) > 40 and np.isfinite(batch[7].samples.values).all()
     assert np.all(zv.var(0) < chain.samples.values.var(0))
     batch.close()
+
+
+# ---- the headline regime (BASELINE configs[3]: HMCDA on the logistic regression through K1 + leapfrog waves) ---------------
+def _oracle_chains(O, om, jobs):
+    """oracle chains on a thread pool (ctypes releases the GIL): jobs = [(sampler, range, init, normals, uniforms)]"""
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        return list(ex.map(lambda j: O.run_chain(om, j[0], j[1], j[2], None, j[3], j[4]), jobs))
+
+
+def _headline_problem(seed=11):
+    N, d, C = 4097, 100, 130
+    X, y, hy, b0 = make_regression("logistic", N, d, seed)
+    sc = math.sqrt(1e6 / N)                         # posterior scale relative to cfg4's N = 1e6
+    rng = np.random.default_rng(seed + 1)
+    eps = rng.uniform(1.2e-3, 2.2e-3, size=C) * sc  # per-chain step sizes around the adapted value of cfg4 (1.97e-3)
+    init = b0[None, :] + 0.02 * rng.standard_normal((C, d))
+    return N, d, C, X, y, hy, eps, 0.02 * sc, init, rng
+
+
+def test_hmcda_headline_regime_frozen_phase(O, capi, ctx):
+    """HMCDA on logistic, d = 100, per-chain step sizes restored with set_state (the state bench.py's cfg4 runs in):
+    ~8-17 leapfrogs per step, different per chain, so every wave mixes chains that finish a trajectory with chains in
+    the middle of one.  Draw-matched against the oracle: identical accept flags and leap counts, samples to 1e-9."""
+    N, d, C, X, y, hy, eps, L, init, rng = _headline_problem()
+    K = 32
+    zn = rng.standard_normal((C, K + 1, d)); un = rng.random((C, K + 1))
+    dm = capi.DeviceModel(ctx, "logistic", d, X, y, hy)
+    om = O.Model("logistic", d, X, y, hy)
+    run = capi.DeviceRun(dm, capi.sampler_cfg("HMCDA", len=L, max_leaps=64), (1, 1, K), C, init, normals=zn, uniforms=un, engine="wave")
+    run.set_state(0, eps, eps, np.zeros(C))
+    info = run.execute(); out = run.fetch(); geps, gnl = run.fetch_diag()
+    run.close(); dm.close()
+    refs = _oracle_chains(O, om, [(O.sampler("HMCDA", len=L, max_leaps=64, da_state=[eps[c], eps[c], 0.0]), (1, 1, K), init[c], zn[c], un[c])
+                                  for c in range(C)])
+    acc = out["accept"].mean()
+    assert 0.3 < acc < 1.0                                                      # a real mix of accepts and rejects
+    assert len(np.unique(gnl)) >= 5 and gnl.min() >= 6 and gnl.max() <= 20      # mixed trajectory lengths in every wave
+    assert info["n_grad_evals"] == C + gnl.sum()
+    gs = np.abs(X).sum(0)
+    for c in range(C):
+        r = refs[c]
+        assert r["rc"] == 0
+        assert np.array_equal(r["accept"], out["accept"][c]), c
+        assert np.array_equal(r["nleaps"], gnl[c]) and np.array_equal(r["eps"], geps[c]), c
+        assert np.allclose(r["samples"], out["samples"][c], rtol=1e-9, atol=1e-12), c
+        assert np.allclose(r["logtarget"], out["logtarget"][c], rtol=1e-11, atol=0), c
+        assert np.all(np.abs(r["grads"] - out["grads"][c]) <= 1e-9 * gs), c
+    assert sum(int(r["accept"].sum()) for r in refs) == int(out["accept"].sum()) > 0.3 * C * K
+
+
+def test_hmcda_headline_regime_adapting(O, capi, ctx):
+    """the same regime with the dual averaging ON (i < burnin, HMCDA.jl:133-138), continued from a restored state at step
+    100 whose dualH is consistent with the step size (eps = exp(mu - sqrt(i) dualH / shrinkage)): 25 adapting steps, then
+    15 kept ones.  Below the integrator's stability limit the adaptation is a contraction, so the GPU and the oracle must
+    agree on every kept step size (1e-7), leap count and decision."""
+    N, d, C, X, y, hy, eps, L, init, rng = _headline_problem(seed=12)
+    s0, B, last = 100, 125, 140
+    dualH = (math.log(10.0) - np.log(eps)) * 0.05 / math.sqrt(s0)
+    zn = rng.standard_normal((C, last + 1, d)); un = rng.random((C, last + 1))
+    dm = capi.DeviceModel(ctx, "logistic", d, X, y, hy)
+    om = O.Model("logistic", d, X, y, hy)
+    run = capi.DeviceRun(dm, capi.sampler_cfg("HMCDA", len=L, max_leaps=64), (B + 1, 1, last), C, init, normals=zn, uniforms=un, engine="wave")
+    run.set_state(s0, eps, eps, dualH)
+    run.execute(); out = run.fetch(); geps, gnl = run.fetch_diag(); st = run.get_state()
+    run.close(); dm.close()
+    refs = _oracle_chains(O, om, [(O.sampler("HMCDA", len=L, max_leaps=64, start_step=s0, da_state=[eps[c], eps[c], dualH[c]]),
+                                   (B + 1, 1, last), init[c], zn[c], un[c]) for c in range(C)])
+    assert 0.3 < out["accept"].mean() < 1.0
+    assert np.abs(geps[:, 0] / eps - 1).max() > 0.02                              # the adaptation moved the step sizes
+    for c in range(C):
+        r = refs[c]
+        assert np.array_equal(r["accept"], out["accept"][c]), c
+        assert np.array_equal(r["nleaps"], gnl[c]), c
+        assert np.allclose(r["eps"], geps[c], rtol=1e-7, atol=0), c
+        assert np.allclose(r["samples"], out["samples"][c], rtol=1e-8, atol=1e-11), c
+        assert np.allclose(st["leapstep"][c], r["eps"][-1], rtol=1e-7)            # frozen phase: leapStep = dualLeapStep
+
+
+@pytest.mark.parametrize("name,fam,N,d,C,splits", [("cfg4", "logistic", 1000000, 100, 10000, 13), ("cfg4-auto", "logistic", 1000000, 100, 8, 0),
+                                                   ("cfg3", "probit", 100000, 20, 16384, 0), ("cfg5-shard", "logistic", 200000, 200, 512, 0)])
+def test_full_geometry_logtarget_gradient(O, capi, ctx, name, fam, N, d, C, splits):
+    """one likelihood launch at the launch geometry of each BASELINE config (cfg4: 157 chain tiles x 13 row splits over
+    31 250 row tiles; cfg3: 256 chain tiles, 3 CTAs per SM; cfg5: d = 200, one CTA per SM), 8 chains spread over the
+    chain tiles checked against the oracle at 1e-12."""
+    import bench
+    X, y, b0 = (bench.synth_logistic if fam == "logistic" else bench.synth_probit)(N, d, 4 if fam == "logistic" else 3)
+    hy = (1.0, -1.0) if fam == "logistic" else (10.0,)
+    dm = capi.DeviceModel(ctx, fam, d, X, y, hy)
+    om = O.Model(fam, d, X, y, hy)
+    rng = np.random.default_rng(N + d)
+    B = b0[None, :] + (2.0 / math.sqrt(N)) * rng.standard_normal((C, d))
+    ctx.set_option("force_splits", splits)
+    try:
+        lt, g = dm.logtarget_grad(B)
+    finally:
+        ctx.set_option("force_splits", 0)
+    dm.close()
+    pick = sorted(set([0, 1, 63, 64, C // 2, C - 65 if C > 65 else C - 1, C - 2, C - 1]))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        refs = list(ex.map(lambda c: om.evalallg(B[c]), pick))
+    gs = np.abs(X).sum(0)
+    for c, (olt, og) in zip(pick, refs):
+        assert abs(lt[c] - olt) <= TOL * abs(olt), (name, c, lt[c], olt)
+        assert np.all(np.abs(g[c] - og) <= TOL * gs), (name, c)
+    assert np.all(np.isfinite(lt)) and np.all(np.isfinite(g))
+
+
+def test_regression_chain_sharding_invariance(capi, ctx):
+    """regression families: chain sharding reproduces the unsharded draws bit for bit when the row-split count is pinned
+    (`force_splits`; the automatic choice depends on the shard's chain count and changes the summation order by ~1e-16)."""
+    X, y, hy, b0 = make_regression("logistic", 3000, 12, 5)
+    dm = capi.DeviceModel(ctx, "logistic", 12, X, y, hy)
+    cfg = capi.sampler_cfg("HMC", scale=0.02, nleaps=5)
+    ctx.set_option("force_splits", 4)
+    try:
+        outs = []
+        for off, n in ((0, 200), (0, 72), (72, 128)):
+            r = capi.DeviceRun(dm, cfg, (1, 1, 40), n, b0, seed=7, chain_offset=off, engine="wave"); r.execute(); outs.append(r.fetch()); r.close()
+    finally:
+        ctx.set_option("force_splits", 0)
+    assert np.array_equal(outs[0]["samples"][:72], outs[1]["samples"]) and np.array_equal(outs[0]["samples"][72:], outs[2]["samples"])
+    assert np.array_equal(outs[0]["accept"][72:], outs[2]["accept"])
+    dm.close()

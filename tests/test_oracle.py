@@ -224,3 +224,137 @@ def test_golden_chains_regression(O):
         z = r.standard_normal((last + 1, 3)); u = r.random(last + 1)
         res = O.run_chain(O.Model("normal_fn", 3), O.sampler(g["kind"], **g["kw"]), g["range"], np.ones(3), None, z, u)
         assert np.array_equal(res["samples"], g["samples"]) and np.array_equal(res["accept"], g["accept"]), name
+
+
+# ---- second source for the headline path: the logistic AD chain + HMC / HMCDA steps, written independently ------------------
+def _logistic_ad_numpy(X, y, b, psd=1.0, sgn=-1.0):
+    """examples/logistic_regression.jl:16-20 through the reverse rules of src/dsl/definitions/MCMCDerivRules.jl, restated
+    in numpy from the reference text alone (forward sweep, then one adjoint per statement, as ReverseDiffSource emits):
+        vars ~ Normal(0, psd)            acc1 = sum logpdf(Normal(0, psd), vars);   dvars += (0 - vars)/(psd*psd)   (:57)
+        t1 = X * vars                    dvars += X' * dt1
+        t2 = sgn * t1 ; t3 = exp(t2)     dt2 = t3 .* dt3 ; dt1 = sgn * dt2
+        t4 = 1. + t3 ; prob = 1 / t4     dt3 = dt4 ; dt4 = -dprob ./ (t4 .* t4)
+        Y ~ Bernoulli(prob)              dprob = 1 ./ (prob - 1. + Y)                                             (:111)"""
+    t1 = X @ b
+    t3 = np.exp(sgn * t1)
+    t4 = 1.0 + t3
+    prob = 1.0 / t4
+    ll = np.where(y == 1.0, np.log(prob), np.log(1.0 - prob))
+    prior = -(0.5 * math.log(2 * math.pi) + 0.5 * (b / psd) ** 2 + math.log(psd))
+    lt = float(prior.sum() + ll.sum())
+    dprob = 1.0 / (prob - 1.0 + y)
+    dt4 = -dprob / (t4 * t4)
+    dt1 = sgn * (t3 * dt4)
+    grad = X.T @ dt1 + (0.0 - b) / (psd * psd)
+    return lt, grad
+
+
+def _logistic_mpmath(X, y, b, psd=1.0, sgn=-1.0):
+    """the same target from its mathematical definition at 50 digits (no AD chain): sum log sigma(+-eta) + log prior;
+    gradient X'(y - p) - b/psd^2 with p = P(y = 1)"""
+    import mpmath as mp
+    mp.mp.dps = 50
+    N, d = X.shape
+    lt = mp.mpf(0)
+    g = [mp.mpf(0)] * d
+    for j in range(d):
+        lt += -(mp.log(2 * mp.pi) / 2 + (mp.mpf(b[j]) / psd) ** 2 / 2 + mp.log(psd))
+        g[j] = -mp.mpf(b[j]) / (mp.mpf(psd) ** 2)
+    for i in range(N):
+        eta = mp.fsum(mp.mpf(X[i, j]) * mp.mpf(b[j]) for j in range(d))
+        p1 = 1 / (1 + mp.exp(sgn * eta))                  # prob: P(Y = 1)
+        lt += mp.log(p1) if y[i] == 1.0 else mp.log(1 - p1)
+        # d/d eta of log p1 = -sgn (1 - p1);  of log(1 - p1) = sgn p1
+        r = -sgn * (1 - p1) if y[i] == 1.0 else sgn * p1
+        for j in range(d):
+            g[j] += r * mp.mpf(X[i, j])
+    return float(lt), np.array([float(v) for v in g])
+
+
+@pytest.mark.parametrize("sgn", [-1.0, 1.0])
+def test_logistic_ad_chain_two_sources(O, sgn):
+    """oracle (C, written from the same reference lines) == numpy restatement of the AD chain (1e-13) == the mathematical
+    definition in 50-digit arithmetic (1e-12): three implementations by construction independent in their arithmetic."""
+    N, d = 300, 7
+    X, y, hy, b0 = make_regression("logistic", N, d, 21)
+    if sgn > 0:
+        y = 1.0 - y
+    m = O.Model("logistic", d, X, y, (1.0, sgn))
+    rng = np.random.default_rng(3)
+    gs = np.abs(X).sum(0)
+    for k in range(6):
+        b = b0 + (0.3 * k) * rng.standard_normal(d)
+        olt, og = m.evalallg(b)
+        nlt, ng = _logistic_ad_numpy(X, y, b, 1.0, sgn)
+        mlt, mg = _logistic_mpmath(X, y, b, 1.0, sgn)
+        assert abs(olt - nlt) <= 1e-13 * abs(nlt) and np.all(np.abs(og - ng) <= 1e-13 * gs)
+        assert abs(olt - mlt) <= 1e-12 * abs(mlt) and np.all(np.abs(og - mg) <= 1e-12 * gs)
+
+
+def test_hmc_and_hmcda_steps_on_logistic_two_sources(O):
+    """HMC.jl:93-102,136-158 and HMCDA.jl:97-142 (frozen and adapting, continued from a restored dual-averaging state)
+    restated in numpy on top of the numpy AD chain, against the oracle's run_chain on a logistic posterior at a
+    realistic step size (acceptance strictly inside (0, 1))."""
+    N, d, last = 400, 8, 40
+    X, y, hy, b0 = make_regression("logistic", N, d, 22)
+    m = O.Model("logistic", d, X, y, hy)
+    rng = np.random.default_rng(4)
+    z = rng.standard_normal((last + 1, d)); u = rng.random(last + 1)
+    f = lambda b: _logistic_ad_numpy(X, y, b)
+
+    def leapfrogs(p, mom, g, eps, n):
+        lt = None
+        for _ in range(n):
+            mom = mom + (0.5 * g) * eps          # HMC.jl:95
+            p = p + eps * mom                    # :96
+            lt, g = f(p)                         # :97
+            mom = mom + (0.5 * g) * eps          # :98
+        return p, mom, g, lt
+
+    # --- plain HMC ---
+    eps, nl = 0.09, 6
+    res = O.run_chain(m, O.sampler("HMC", scale=eps, nleaps=nl), (1, 1, last), b0, None, z, u)
+    pars = b0.copy(); lt, g = f(pars); out, acc = [], []
+    for i in range(1, last + 1):
+        mom = z[i].copy()
+        H0 = -lt + 0.5 * float(mom @ mom)
+        p, mom, gp, ltp = leapfrogs(pars.copy(), mom, g.copy(), eps, nl)
+        H = -ltp + 0.5 * float(mom @ mom)
+        a = u[i] < math.exp(min(H0 - H, 700.0))  # :154
+        if a:
+            pars, lt, g = p, ltp, gp
+        out.append(pars.copy()); acc.append(a)
+    assert 0.3 < np.mean(acc) < 1.0
+    assert np.array_equal(res["accept"], np.array(acc, dtype=np.uint8))
+    assert np.allclose(res["samples"], np.array(out), rtol=1e-10, atol=1e-13)
+    # --- HMCDA from a restored state (step0 = 60): 12 adapting steps (i < burnin = 72), then frozen ---
+    s0, B, last2 = 60, 72, 95
+    z2 = rng.standard_normal((last2 + 1, d)); u2 = rng.random(last2 + 1)
+    L, eps0, rate, shrink, t0, kappa = 0.6, 0.08, 0.65, 0.05, 10.0, 0.75
+    dualH0 = (math.log(10.0) - math.log(eps0)) * shrink / math.sqrt(s0)
+    res = O.run_chain(m, O.sampler("HMCDA", len=L, start_step=s0, da_state=[eps0, eps0, dualH0]), (B + 1, 1, last2), b0, None, z2, u2)
+    pars = b0.copy(); lt, g = f(pars)
+    ls, dual, dualH, mu = eps0, eps0, dualH0, math.log(10.0)
+    keep_eps, keep_nl, keep_acc, keep_s = [], [], [], []
+    for i in range(s0 + 1, last2 + 1):
+        mom = z2[i].copy()
+        H0 = -lt + 0.5 * float(mom @ mom)
+        n = max(1, int(math.floor(L / ls + 0.5)))                       # round(len/leapStep), HMCDA.jl:104
+        p, mom, gp, ltp = leapfrogs(pars.copy(), mom, g.copy(), ls, n)
+        pacc = min(1.0, math.exp(min(H0 - (-ltp + 0.5 * float(mom @ mom)), 700.0)))   # :120
+        a = u2[i] < pacc                                                # :121
+        if a:
+            pars, lt, g = p, ltp, gp
+        if i > B:
+            keep_eps.append(ls); keep_nl.append(n); keep_acc.append(a); keep_s.append(pars.copy())
+        if i < B:                                                       # :133-138
+            eta = 1.0 / (i + t0)
+            dualH = (1 - eta) * dualH + eta * (rate - pacc)
+            ls = math.exp(mu - math.sqrt(i) * dualH / shrink)
+            eta = i ** (-kappa)
+            dual = math.exp((1 - eta) * math.log(dual) + eta * math.log(ls))
+        else:
+            ls = dual                                                   # :140
+    assert 0.3 < np.mean(keep_acc) < 1.0 and abs(keep_eps[0] / eps0 - 1) > 1e-3
+    assert np.array_equal(res["accept"], np.array(keep_acc, dtype=np.uint8)) and np.array_equal(res["nleaps"], keep_nl)
+    assert np.allclose(res["eps"], keep_eps, rtol=1e-9) and np.allclose(res["samples"], np.array(keep_s), rtol=1e-9, atol=1e-12)
