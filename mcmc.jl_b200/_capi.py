@@ -5,6 +5,7 @@ compute call raises.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -126,11 +127,42 @@ def f64(a, order="C"):
     return None if a is None else np.require(a, dtype=np.float64, requirements=["C" if order == "C" else "F", "A"])
 
 
-class Context:
+def _destroy(fn_name, handle, _parent):
+    # `_parent` only keeps the owning object (context / model) alive until this handle has been released
+    getattr(lib(), fn_name)(C.c_void_p(handle))
+
+
+class _Owned:
+    """Lifetime of a library handle: freed by close(), by `with`, or when the Python object is collected -- always
+    children first (a run keeps its model alive, a model its context; closing a parent closes its live children)."""
+    h = None
+
+    def _own(self, fn_name, parent):
+        self._children = weakref.WeakSet()
+        self._fin = weakref.finalize(self, _destroy, fn_name, self.h.value, parent)
+        if parent is not None:
+            parent._children.add(self)
+
+    def close(self):
+        if self.h is not None:
+            for ch in list(self._children):
+                ch.close()
+            self.h = None
+            self._fin()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class Context(_Owned):
     def __init__(self, device=-1):
         h = C.c_void_p()
         check(lib().mcmcgpu_init(device, C.byref(h)))
         self.h = h
+        self._own("mcmcgpu_destroy", None)
 
     def set_stream(self, stream_ptr):
         check(lib().mcmcgpu_set_stream(self.h, C.c_void_p(stream_ptr) if stream_ptr else None))
@@ -211,13 +243,9 @@ class Context:
                                            at.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info)))
         return dict(samples=samples, at=at, info=info.as_dict())
 
-    def close(self):
-        if self.h:
-            lib().mcmcgpu_destroy(self.h)
-            self.h = None
 
 
-class DeviceModel:
+class DeviceModel(_Owned):
     def __init__(self, ctx, family, d, X=None, y=None, hyper=(), row_sharded=False):
         self.ctx, self.family, self.d = ctx, family, int(d)
         Xf = None if X is None else np.asfortranarray(X, dtype=np.float64)
@@ -230,6 +258,7 @@ class DeviceModel:
         check(lib().mcmcgpu_model_create(ctx.h, FAM[family], N, self.d, dptr(Xf), dptr(yf), dptr(hy) if len(hy) else None,
                                          len(hy), 1 if row_sharded else 0, C.byref(h)))
         self.h, self.N = h, N
+        self._own("mcmcgpu_model_destroy", ctx)
 
     @classmethod
     def from_device(cls, ctx, family, N, d, X_ptr, y_ptr, hyper=(), row_sharded=False):
@@ -241,6 +270,7 @@ class DeviceModel:
         check(lib().mcmcgpu_model_create_device(ctx.h, FAM[family], int(N), int(d), C.c_void_p(X_ptr), C.c_void_p(y_ptr),
                                                 dptr(hy) if len(hy) else None, len(hy), 1 if row_sharded else 0, C.byref(h)))
         self.h = h
+        self._own("mcmcgpu_model_destroy", ctx)
         return self
 
     def logtarget_grad(self, B, grad=True):
@@ -252,10 +282,6 @@ class DeviceModel:
         check(lib().mcmcgpu_logtarget_grad(self.h, dptr(B), Cn, dptr(lt), dptr(g)))
         return lt, g
 
-    def close(self):
-        if self.h:
-            lib().mcmcgpu_model_destroy(self.h)
-            self.h = None
 
 
 def sampler_cfg(kind, scale=1.0, nleaps=10, rate=0.65, len=2.0, shrinkage=0.05, t0=10.0, step=0.75, max_leaps=0,
@@ -272,7 +298,7 @@ def sampler_cfg(kind, scale=1.0, nleaps=10, rate=0.65, len=2.0, shrinkage=0.05, 
     return s
 
 
-class DeviceRun:
+class DeviceRun(_Owned):
     """Split-form run: inputs resident in HBM after construction; execute() may be timed alone."""
 
     def __init__(self, model, scfg, rng, nchains, init, scale=None, seed=0, chain_offset=0, normals=None, uniforms=None,
@@ -300,6 +326,7 @@ class DeviceRun:
         check(lib().mcmcgpu_run_create(model.h, C.byref(scfg), C.byref(r), dptr(init), dptr(sc), dptr(zn), dptr(un),
                                        C.byref(h)))
         self.h = h
+        self._own("mcmcgpu_run_destroy", model)
         self.info = None
 
     def execute(self):
@@ -370,7 +397,3 @@ class DeviceRun:
         check(lib().mcmcgpu_run_zv(self.h, order, dptr(zv), dptr(a)))
         return zv, a
 
-    def close(self):
-        if self.h:
-            lib().mcmcgpu_run_destroy(self.h)
-            self.h = None

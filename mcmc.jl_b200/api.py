@@ -14,6 +14,9 @@ _device = -1
 
 
 def set_default_device(device):
+    """Switch the process to another GPU.  The old context is closed together with everything that lives in it (cached
+    device models and device-resident runs: Context.close releases children first); models re-create their device
+    side lazily in the new context, batches of the old context keep only what they had already fetched."""
     global _device, _ctx
     if _ctx is not None:
         _ctx.close()
@@ -63,10 +66,23 @@ class MCMCLikelihoodModel:
 
     # -- device handle (lazy) --
     def device_model(self):
-        if self._dev is None:
-            self._dev = capi.DeviceModel(default_context(), self.family, self.size, self.X, self.y, self.hyper,
-                                         row_sharded=self.row_sharded)
+        ctx = default_context()
+        if self._dev is None or self._dev.h is None or self._dev.ctx is not ctx:   # never built, closed, or of an old context
+            self._dev = capi.DeviceModel(ctx, self.family, self.size, self.X, self.y, self.hyper, row_sharded=self.row_sharded)
         return self._dev
+
+    def close(self):
+        """release the device side (the packed design matrix) now; it is re-created on the next use, and released
+        automatically when the model object is collected"""
+        if self._dev is not None:
+            self._dev.close()
+            self._dev = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
     def eval(self, v):                                                     # likmodel.jl:21
         lt, _ = self.device_model().logtarget_grad(np.asarray(v, dtype=np.float64)[None, :], grad=False)
@@ -470,7 +486,14 @@ class MCMCChainBatch:
         return self._run.fetch_rb()
 
     def close(self):
+        """release the device-resident draws (also done when the batch is collected, or by `with run(...) as batch`)"""
         self._run.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
 
 # ---------------------------------------------------------------------------------------------------

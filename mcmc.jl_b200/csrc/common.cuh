@@ -42,7 +42,8 @@ __host__ __device__ __forceinline__ u4 philox4x32_10(uint32_t c0, uint32_t c1, u
   return o;
 }
 
-// 53-bit uniform in (0,1), exact in binary64
+// uniform from 53 random bits: (b + 0.5) / 2^53 in (0, 1]; exact for b < 2^52, while for b >= 2^52 the sum b + 0.5 is
+// rounded to even (so 1.0 itself occurs with probability 2^-54; harmless: log(1) = 0, and `u < p` then rejects)
 __host__ __device__ __forceinline__ double u01(uint32_t hi, uint32_t lo) {
   uint64_t b = (((uint64_t)hi << 21) ^ ((uint64_t)lo >> 11)) & ((1ull << 53) - 1);
   return ((double)b + 0.5) * (1.0 / 9007199254740992.0);

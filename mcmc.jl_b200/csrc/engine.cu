@@ -39,6 +39,7 @@ struct mcmcgpu_ctx {
   int64_t k1_debug = 0;       // option (experiments): see K1Args::debug
   int64_t use_graphs = 1;     // option: replay fixed-length wave loops from a CUDA graph
   int32_t* h_remaining = nullptr;  // pinned
+  cudaMemPool_t pool = nullptr;    // this context's own stream-ordered pool (the device's default pool is left alone)
 };
 
 struct mcmcgpu_model {
@@ -59,14 +60,17 @@ struct mcmcgpu_model {
   }
 };
 
-// Run and temporary buffers come from the device's stream-ordered memory pool (cudaMallocAsync / cudaFreeAsync on the
-// context's stream): with a release threshold the pool keeps freed blocks, so creating, fetching and destroying a run costs
-// no cudaMalloc / cudaFree round trips to the driver (measured on a 5-step cfg3 run: fetch 6..400 ms -> a few ms).
-// t_stream is the stream of the context the current API call works on (set by use_ctx at every entry point).
+// Run and temporary buffers come from a stream-ordered memory pool owned by the context (cudaMemPoolCreate;
+// cudaMallocFromPoolAsync / cudaFreeAsync on the context's stream): with a release threshold the pool keeps freed blocks, so
+// creating, fetching and destroying a run costs no cudaMalloc / cudaFree round trips to the driver (measured on a 5-step
+// cfg3 run: fetch 6..400 ms -> a few ms).  The pool is private: other users of the device's default pool in the same
+// process (e.g. PyTorch's cudaMallocAsync backend) keep their own threshold and cached blocks.
+// t_stream / t_pool belong to the context the current API call works on (set by use_ctx at every entry point).
 static thread_local cudaStream_t t_stream = nullptr;
+static thread_local cudaMemPool_t t_pool = nullptr;
 static cudaError_t use_ctx(const mcmcgpu_ctx* c);
 template <typename T>
-static cudaError_t dalloc(T** p, size_t n) { return cudaMallocAsync((void**)p, sizeof(T) * (n ? n : 1), t_stream); }
+static cudaError_t dalloc(T** p, size_t n) { return cudaMallocFromPoolAsync((void**)p, sizeof(T) * (n ? n : 1), t_pool, t_stream); }
 static void dfree(void* p) { if (p) cudaFreeAsync(p, t_stream); }
 
 struct mcmcgpu_run {
@@ -113,7 +117,7 @@ struct mcmcgpu_run {
   }
 };
 
-static cudaError_t use_ctx(const mcmcgpu_ctx* c) { t_stream = c->stream; return cudaSetDevice(c->device); }
+static cudaError_t use_ctx(const mcmcgpu_ctx* c) { t_stream = c->stream; t_pool = c->pool; return cudaSetDevice(c->device); }
 
 // ------------------------------------------------------------------------------------------------
 struct Events {    // CUDA events destroyed on scope exit (every return path of the CU() macro included)
@@ -163,11 +167,16 @@ int32_t mcmcgpu_init(int32_t device_id, mcmcgpu_ctx** out) {
   cudaError_t e2 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
   if (e2 == cudaSuccess) e2 = cudaMallocHost((void**)&c->h_remaining, sizeof(int32_t));
   if (e2 == cudaSuccess) {
-    // keep up to 2 GB of freed run / temporary buffers in the device's default memory pool (dalloc / dfree above)
-    cudaMemPool_t pool = nullptr;
-    e2 = cudaDeviceGetDefaultMemPool(&pool, device_id);
+    // a private pool that keeps up to 2 GB of freed run / temporary buffers (dalloc / dfree above)
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device_id;
+    e2 = cudaMemPoolCreate(&c->pool, &props);
     uint64_t keep = 2ull << 30;
-    if (e2 == cudaSuccess) e2 = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (e2 == cudaSuccess) e2 = cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep);
   }
   if (e2 != cudaSuccess) {
     mcmcgpu_destroy(c);
@@ -182,8 +191,7 @@ int32_t mcmcgpu_destroy(mcmcgpu_ctx* c) {
   use_ctx(c);
   if (c->comm) { const NcclApi* api = nccl_api(nullptr); if (api) api->CommDestroy(c->comm); }
   if (c->stream) cudaStreamSynchronize(c->stream);
-  cudaMemPool_t pool = nullptr;
-  if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);   // cached blocks back to the driver
+  if (c->pool) cudaMemPoolDestroy(c->pool);              // cached blocks back to the driver
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->h_remaining) cudaFreeHost(c->h_remaining);
   delete c;
@@ -475,12 +483,11 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   // inputs
   if (r->init_per_chain) {
     double* tmp = nullptr;
-    RCU(dalloc(&tmp, (size_t)(C * d)));
-    RCU(cudaMemcpyAsync(tmp, init, sizeof(double) * (size_t)(C * d), cudaMemcpyHostToDevice, st));
+    DevBufs staging;                        // released on every path, the failing ones of RCU included
+    RCU(staging.up(&tmp, init, (size_t)(C * d), st));
     RCU(R->alloc(&R->init, (size_t)(d * Cp)));
     RCU(transpose_to_chain_minor(tmp, R->init, C, d, Cp, st));
     RCU(cudaStreamSynchronize(st));
-    dfree(tmp);
   } else {
     RCU(R->alloc(&R->init, (size_t)d));
     RCU(cudaMemcpyAsync(R->init, init, sizeof(double) * (size_t)d, cudaMemcpyHostToDevice, st));
@@ -494,19 +501,15 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   }
   if (inj_normals) {
     const int64_t K = (r->last + 1) * d, Ku = r->last + 1;
-    double* tmp = nullptr;
-    RCU(dalloc(&tmp, (size_t)(C * K)));
-    RCU(cudaMemcpyAsync(tmp, inj_normals, sizeof(double) * (size_t)(C * K), cudaMemcpyHostToDevice, st));
+    double *tmp = nullptr, *tmpu = nullptr;
+    DevBufs staging;
+    RCU(staging.up(&tmp, inj_normals, (size_t)(C * K), st));
     RCU(R->alloc(&R->inj_normals, (size_t)(K * Cp)));
     RCU(transpose_to_chain_minor(tmp, R->inj_normals, C, K, Cp, st));
-    RCU(cudaStreamSynchronize(st));
-    dfree(tmp);
-    RCU(dalloc(&tmp, (size_t)(C * Ku)));
-    RCU(cudaMemcpyAsync(tmp, inj_uniforms, sizeof(double) * (size_t)(C * Ku), cudaMemcpyHostToDevice, st));
+    RCU(staging.up(&tmpu, inj_uniforms, (size_t)(C * Ku), st));
     RCU(R->alloc(&R->inj_uniforms, (size_t)(Ku * Cp)));
-    RCU(transpose_to_chain_minor(tmp, R->inj_uniforms, C, Ku, Cp, st));
+    RCU(transpose_to_chain_minor(tmpu, R->inj_uniforms, C, Ku, Cp, st));
     RCU(cudaStreamSynchronize(st));
-    dfree(tmp);
   }
   // outputs
   RCU(R->alloc(&R->samples, (size_t)(S * d * Cp), false));
@@ -784,11 +787,11 @@ int32_t mcmcgpu_run_get_state(mcmcgpu_run* R, double* pars, double* leapstep, do
   cudaStream_t st = R->m->ctx->stream;
   if (pars) {
     double* tmp = nullptr;
-    CU(dalloc(&tmp, (size_t)(R->C * R->d)));
+    DevBufs bufs;
+    CU(bufs.get(&tmp, (size_t)(R->C * R->d), st, false));
     CU(transpose_to_chain_major(R->cur_pars, tmp, 0, R->C, R->d, R->Cp, st));
     CU(cudaMemcpyAsync(pars, tmp, sizeof(double) * (size_t)(R->C * R->d), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    dfree(tmp);
   }
   const double* src[3] = {R->da_leapstep, R->da_dual, R->da_dualH};
   double* dst[3] = {leapstep, dual_leapstep, dualH};
@@ -841,11 +844,11 @@ int32_t mcmcgpu_run_fetch(mcmcgpu_run* R, double* out_samples, double* out_grads
   }
   if (out_accept) {
     uint8_t* tmp = nullptr;
-    CU(dalloc(&tmp, (size_t)(R->C * R->S)));
+    DevBufs bufs;
+    CU(bufs.get(&tmp, (size_t)(R->C * R->S), st, false));
     CU(transpose_to_chain_major_u8(R->accept, tmp, 0, R->C, R->S, R->Cp, st));
     CU(cudaMemcpyAsync(out_accept, tmp, (size_t)(R->C * R->S), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    dfree(tmp);
   }
   return MCMCGPU_OK;
 }
@@ -874,11 +877,11 @@ int32_t mcmcgpu_run_fetch_diag(mcmcgpu_run* R, double* out_eps, int64_t* out_nle
     // widen to double-sized lanes so the same transposer can be used
     int64_t n = R->S * R->Cp;
     int64_t* wide = nullptr;
-    CU(dalloc(&wide, (size_t)n));
+    DevBufs bufs;
+    CU(bufs.get(&wide, (size_t)n, st, false));
     i32_to_i64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(R->nleaps, wide, n);
     CU(cudaGetLastError());
     int rc = fetch_chunked(R, reinterpret_cast<const double*>(wide), R->S, reinterpret_cast<double*>(out_nleaps));
-    dfree(wide);
     if (rc) return rc;
   }
   return MCMCGPU_OK;
@@ -898,10 +901,11 @@ static int stats_common(mcmcgpu_ctx* c, const double* samples, const uint8_t* ac
     return fail(MCMCGPU_E_ARG, "Choose batch size such that the number of batches is greather than one");           // var.jl:22
   double* outs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double* hosts[5] = {out_mean, out_var_iid, out_var, out_ess, out_actime};
-  for (int k = 0; k < 5; k++) if (hosts[k]) CU(dalloc(&outs[k], (size_t)(d * Cp)));
+  DevBufs bufs;                              // every temporary below is released on every return path
+  for (int k = 0; k < 5; k++) if (hosts[k]) CU(bufs.get(&outs[k], (size_t)(d * Cp), st, false));
   CU(launch_stats(samples, S, d, C, Cp, vtype, maxlag, batchlen, outs[0], outs[1], outs[2], outs[3], outs[4], st));
   double* tmp = nullptr;
-  CU(dalloc(&tmp, (size_t)(C * d)));
+  CU(bufs.get(&tmp, (size_t)(C * d), st, false));
   for (int k = 0; k < 5; k++) if (hosts[k]) {
     CU(transpose_to_chain_major(outs[k], tmp, 0, C, d, Cp, st));
     CU(cudaMemcpyAsync(hosts[k], tmp, sizeof(double) * (size_t)(C * d), cudaMemcpyDeviceToHost, st));
@@ -909,15 +913,12 @@ static int stats_common(mcmcgpu_ctx* c, const double* samples, const uint8_t* ac
   }
   if (out_accept_rate && accept) {
     double* rate = nullptr;
-    CU(dalloc(&rate, (size_t)Cp));
+    CU(bufs.get(&rate, (size_t)Cp, st, false));
     CU(launch_accept_rate(accept, S, C, Cp, rate, st));
     CU(cudaMemcpyAsync(out_accept_rate, rate, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    dfree(rate);
   }
   CU(cudaStreamSynchronize(st));
-  dfree(tmp);
-  for (int k = 0; k < 5; k++) if (outs[k]) dfree(outs[k]);
   return MCMCGPU_OK;
 }
 
@@ -937,13 +938,12 @@ int32_t mcmcgpu_stats(mcmcgpu_ctx* c, const double* samples, int64_t S, int64_t 
   cudaStream_t st = c->stream;
   const int64_t Cp = round_up(C, K1_CHAINS), K = S * d;
   double *tmp = nullptr, *dev = nullptr;
-  CU(dalloc(&tmp, (size_t)(C * K)));
-  CU(dalloc(&dev, (size_t)(K * Cp)));
-  CU(cudaMemcpyAsync(tmp, samples, sizeof(double) * (size_t)(C * K), cudaMemcpyHostToDevice, st));
+  DevBufs bufs;
+  CU(bufs.up(&tmp, samples, (size_t)(C * K), st));
+  CU(bufs.get(&dev, (size_t)(K * Cp), st, false));
   CU(transpose_to_chain_minor(tmp, dev, C, K, Cp, st));
   int rc = stats_common(c, dev, nullptr, S, d, C, Cp, vtype, maxlag, batchlen, out_mean, out_var_iid, out_var, out_ess, out_actime, nullptr);
   cudaStreamSynchronize(st);
-  dfree(tmp); dfree(dev);
   return rc;
 }
 
@@ -1014,11 +1014,9 @@ int32_t mcmcgpu_run_chains(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   int rc = mcmcgpu_run_create(m, s, &rr, init, scale, inj_normals, inj_uniforms, &R);
   if (rc != MCMCGPU_OK) return rc;
   rc = mcmcgpu_run_execute(R, info);
-  if (rc == MCMCGPU_OK || rc == MCMCGPU_E_SUPPORT) {
-    std::string keep = g_err;
-    int rc2 = mcmcgpu_run_fetch(R, out_samples, out_grads, out_accept, out_logtarget);
-    if (rc2 != MCMCGPU_OK) rc = rc2; else g_err = keep;
-  }
+  // "Initial values out of model support" is an assertion in the reference (RWM.jl:55, ...): no chain is produced, so
+  // nothing is fetched (the kept-draw arrays of a chain that never started are not initialised)
+  if (rc == MCMCGPU_OK) rc = mcmcgpu_run_fetch(R, out_samples, out_grads, out_accept, out_logtarget);
   mcmcgpu_run_destroy(R);
   return rc;
 }
@@ -1030,13 +1028,13 @@ int32_t mcmcgpu_philox_draws(mcmcgpu_ctx* c, uint64_t seed, int64_t chain_offset
   cudaStream_t st = c->stream;
   double *zn = nullptr, *un = nullptr;
   const int64_t n = nchains * (last + 1);
-  CU(dalloc(&zn, (size_t)(n * d)));
-  CU(dalloc(&un, (size_t)n));
+  DevBufs bufs;
+  CU(bufs.get(&zn, (size_t)(n * d), st, false));
+  CU(bufs.get(&un, (size_t)n, st, false));
   CU(launch_philox_dump(seed, chain_offset, nchains, d, last, zn, un, st));
   CU(cudaMemcpyAsync(out_normals, zn, sizeof(double) * (size_t)(n * d), cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(out_uniforms, un, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
-  dfree(zn); dfree(un);
   return MCMCGPU_OK;
 }
 

@@ -61,6 +61,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "DONE:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// slot-release counter of the tile ring: acq_rel at CTA scope, so every warp's (generic-proxy) reads of the tile are ordered
+// before the last arriver's refill (release by each arriving lane 0 after __syncwarp, acquire by the one that sees WARPS-1)
+__device__ __forceinline__ unsigned atom_add_acq_rel_cta(unsigned int* p, unsigned v) {
+  unsigned old;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+  return old;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -562,11 +569,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
     // for the slowest one just to start a copy
     __syncwarp();
     if (lane == 0) {
-      const unsigned int prev = atomicAdd(&released[slot], 1u);
+      const unsigned int prev = atom_add_acq_rel_cta(&released[slot], 1u);
       if (prev == K1_WARPS - 1) {
+        // the counter reset is published by the release of mbarrier.arrive.expect_tx below (the next arrivals on this slot
+        // come after an acquire-wait on that barrier); with no refill left the slot is never counted again
         released[slot] = 0;
         if (it + K1_STAGES < nt) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy overwrite
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads (acquired above) before the async-proxy overwrite
           mbar_expect_tx(&full[slot], tile_bytes);
           bulk_g2s(tiles + (size_t)slot * TILE_D, a.P.tiles + (t0 + it + K1_STAGES) * a.P.tile_doubles, tile_bytes,
                    &full[slot]);
@@ -642,12 +651,13 @@ cudaError_t k1_pack(K1Pack& P, const double* dX, const double* dy, int64_t N, in
 }
 void k1_free(K1Pack& P) { if (P.tiles) cudaFree(P.tiles); P.tiles = nullptr; }
 
-int k1_choose_splits(const K1Pack& P, int64_t Cp) {
+int k1_choose_splits(const K1Pack& P, int64_t Cp, int device) {
   // Row splits: enough CTAs to fill the machine, and a CTA count whose last wave is nearly full
   // (two resident CTAs per SM).  Every split keeps >= 8 tiles so the prologue stays amortised.
   const int64_t ctiles = Cp / K1_CHAINS;
   int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  if (device < 0) cudaGetDevice(&device);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   const int64_t slots = (P.DK <= K1_MAX_DK_3CTA ? 3LL : (P.DK <= K1_MAX_DK_2CTA ? 2LL : 1LL)) * sms;
   int64_t maxs = P.ntiles / 8;
   if (maxs < 1) maxs = 1;

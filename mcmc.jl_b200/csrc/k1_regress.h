@@ -41,7 +41,7 @@ struct K1Args {
 cudaError_t k1_pack(K1Pack& P, const double* dX /* N x d col-major, device */, const double* dy, int64_t N, int64_t d,
                     cudaStream_t st);
 void k1_free(K1Pack& P);
-int k1_choose_splits(const K1Pack& P, int64_t Cp);
+int k1_choose_splits(const K1Pack& P, int64_t Cp, int device = -1);   // device < 0: the current device
 cudaError_t k1_launch(const K1Args& a, cudaStream_t st);
 bool k1_supported(int64_t d);
 

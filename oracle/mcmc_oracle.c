@@ -887,7 +887,7 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
-/* 53-bit uniform in (0,1): ((hi<<21 ^ lo>>11) + 0.5) * 2^-53 -- exact in binary64 */
+/* uniform from 53 random bits: (b + 0.5) * 2^-53 in (0, 1]; b + 0.5 rounds to even for b >= 2^52, so 1.0 occurs with probability 2^-54 (the engine does the same) */
 static double u01(uint32_t hi, uint32_t lo) {
   uint64_t b = (((uint64_t)hi << 21) ^ ((uint64_t)lo >> 11)) & ((1ull << 53) - 1);
   return ((double)b + 0.5) * (1.0 / 9007199254740992.0);

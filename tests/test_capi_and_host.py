@@ -206,3 +206,48 @@ def test_generated_link_tables_are_reproducible():
     for x in np.concatenate([rng.uniform(1e-12, 1, 300), 1 - 10 ** rng.uniform(-15, -2, 100)]):
         ref = mp.log(mp.mpf(float(x)))
         assert abs(mp.mpf(gl.log_dev(float(x), R, L)) - ref) <= mp.mpf(3e-16) * abs(ref) + mp.mpf(3e-18)
+
+
+def test_handle_lifetimes_children_first(capi, monkeypatch):
+    """runs, models and contexts are released children-first -- by close(), by `with`, and by garbage
+    collection -- and a closed parent leaves no dangling child handle (checked against a recording fake of the library)."""
+    import ctypes
+    import gc
+    calls = []
+
+    class FakeLib:
+        def __getattr__(self, name):
+            return lambda h: calls.append((name, h.value))
+
+    monkeypatch.setattr(capi, "lib", lambda: FakeLib())
+
+    def make(cls, handle, fn, parent):
+        o = cls.__new__(cls)
+        o.h = ctypes.c_void_p(handle)
+        o._own(fn, parent)
+        return o
+
+    ctx = make(capi.Context, 1, "mcmcgpu_destroy", None)
+    m = make(capi.DeviceModel, 2, "mcmcgpu_model_destroy", ctx); m.ctx = ctx
+    r1 = make(capi.DeviceRun, 3, "mcmcgpu_run_destroy", m); r1.model = m
+    r2 = make(capi.DeviceRun, 4, "mcmcgpu_run_destroy", m); r2.model = m
+    r2.close(); r2.close()                                   # idempotent
+    assert calls == [("mcmcgpu_run_destroy", 4)] and r2.h is None
+    ctx.close()                                              # closes the live run, then the model, then the context
+    assert calls[1:] == [("mcmcgpu_run_destroy", 3), ("mcmcgpu_model_destroy", 2), ("mcmcgpu_destroy", 1)]
+    assert r1.h is None and m.h is None and ctx.h is None
+    # garbage collection: dropping every reference releases run -> model -> context, in that order
+    del calls[:]
+    ctx = make(capi.Context, 10, "mcmcgpu_destroy", None)
+    m = make(capi.DeviceModel, 20, "mcmcgpu_model_destroy", ctx)
+    r = make(capi.DeviceRun, 30, "mcmcgpu_run_destroy", m)
+    del ctx, m
+    gc.collect()
+    assert calls == []                                       # the run still keeps its model and context alive
+    del r
+    gc.collect()
+    assert calls == [("mcmcgpu_run_destroy", 30), ("mcmcgpu_model_destroy", 20), ("mcmcgpu_destroy", 10)]
+    with make(capi.Context, 11, "mcmcgpu_destroy", None) as c2:
+        make(capi.DeviceModel, 21, "mcmcgpu_model_destroy", c2)
+    gc.collect()
+    assert calls[-2:] == [("mcmcgpu_model_destroy", 21), ("mcmcgpu_destroy", 11)]
