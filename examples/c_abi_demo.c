@@ -27,9 +27,9 @@ int main(int argc, char** argv) {
            offsetof(mcmcgpu_runner_cfg, nchains), offsetof(mcmcgpu_runner_cfg, chain_offset), offsetof(mcmcgpu_runner_cfg, seed),
            offsetof(mcmcgpu_runner_cfg, init_per_chain), offsetof(mcmcgpu_runner_cfg, store_grad), offsetof(mcmcgpu_runner_cfg, store_logtarget),
            offsetof(mcmcgpu_runner_cfg, engine), offsetof(mcmcgpu_runner_cfg, store_rb));
-    printf("run_info %zu gpu_ms %zu n_grad_evals %zu n_waves %zu n_launches %zu eval_ms %zu\n", sizeof(mcmcgpu_run_info),
+    printf("run_info %zu gpu_ms %zu n_grad_evals %zu n_waves %zu n_launches %zu eval_ms %zu comm_ms %zu\n", sizeof(mcmcgpu_run_info),
            offsetof(mcmcgpu_run_info, gpu_ms), offsetof(mcmcgpu_run_info, n_grad_evals), offsetof(mcmcgpu_run_info, n_waves),
-           offsetof(mcmcgpu_run_info, n_launches), offsetof(mcmcgpu_run_info, eval_ms));
+           offsetof(mcmcgpu_run_info, n_launches), offsetof(mcmcgpu_run_info, eval_ms), offsetof(mcmcgpu_run_info, comm_ms));
     return 0;
   }
   const int64_t N = 1000, d = 10, C = 8, first = 101, last = 1000, S = last - first + 1;

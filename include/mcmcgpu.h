@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MCMCGPU_ABI_VERSION 1
+#define MCMCGPU_ABI_VERSION 2   /* 2: mcmcgpu_run_info.comm_ms */
 
 /* status codes */
 #define MCMCGPU_OK 0
@@ -98,7 +98,9 @@ typedef struct {
   int64_t n_grad_evals;   /* log-target(+gradient) evaluations summed over chains                   */
   int64_t n_waves;        /* wave-engine iterations (0 for the fused engine)                        */
   int64_t n_launches;     /* kernels launched by the library during execute                         */
-  double eval_ms;         /* device time spent in the likelihood kernel (wave engine)               */
+  double eval_ms;         /* device time spent in the likelihood kernel (wave engine, option time_eval) */
+  double comm_ms;         /* device time between the likelihood kernel and the transition kernel: the fold of the
+                             row-split partials and, for row-sharded models, the NCCL all-reduce (time_eval)  */
 } mcmcgpu_run_info;
 
 /* ---- context ---- */

@@ -42,7 +42,7 @@ class RunnerCfg(C.Structure):
 
 class RunInfo(C.Structure):
     _fields_ = [("gpu_ms", C.c_double), ("n_grad_evals", C.c_int64), ("n_waves", C.c_int64),
-                ("n_launches", C.c_int64), ("eval_ms", C.c_double)]
+                ("n_launches", C.c_int64), ("eval_ms", C.c_double), ("comm_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

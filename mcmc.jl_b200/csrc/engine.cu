@@ -343,7 +343,7 @@ int32_t mcmcgpu_model_destroy(mcmcgpu_model* m) {
 // one evaluation of every chain at q -> part (and the all-reduce for row-sharded models)
 static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* red, int nsplit, int64_t C, int64_t Cp,
                      bool need_grad, const uint8_t* need_ll, const int32_t* phase, const int32_t* remaining,
-                     const double** part_out, int* nsplit_out) {
+                     const double** part_out, int* nsplit_out, cudaEvent_t ev_k1_done = nullptr) {
   cudaStream_t st = m->ctx->stream;
   *part_out = part; *nsplit_out = nsplit;
   if (m->is_regression) {
@@ -353,6 +353,7 @@ static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* re
     a.q = q; a.part = part; a.Cp = Cp; a.nsplit = nsplit; a.need_grad = need_grad ? 1 : 0;
     a.need_ll = need_ll; a.phase = phase; a.remaining = remaining; a.debug = (int32_t)m->ctx->k1_debug;
     CU(k1_launch(a, st));
+    if (ev_k1_done) CU(cudaEventRecord(ev_k1_done, st));   // what follows (split fold, all-reduce) is timed apart: run_info.comm_ms
     if (!m->row_sharded && nsplit > 4 && red) {
       // many row splits (small problems spread over the whole machine): fold them with a parallel pass, in split order,
       // so the per-chain transition thread does not walk nsplit partial buffers serially
@@ -369,6 +370,7 @@ static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* re
     }
   } else {
     CU(launch_eval_closed(m->dev(), q, part, C, Cp, phase, remaining, st));
+    if (ev_k1_done) CU(cudaEventRecord(ev_k1_done, st));
     *nsplit_out = 1;
   }
   return MCMCGPU_OK;
@@ -603,7 +605,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
   cudaEvent_t e0, e1;
   CU(events.make(&e0)); CU(events.make(&e1));
   int64_t launches = 0, waves = 0;
-  double eval_ms = 0.0;
+  double eval_ms = 0.0, comm_ms = 0.0;
   CU(cudaMemsetAsync(R->n_evals, 0, sizeof(unsigned long long), st));
   CU(cudaEventRecord(e0, st));
   if (R->engine == MCMCGPU_ENGINE_FUSED) {
@@ -667,12 +669,15 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     bool graph_done = false;
     for (;;) {
       if (known >= 0 && waves >= known) break;
-      // launch-bound regime (small N x C): when the number of waves is known, replay them from a CUDA graph
-      // (captured once: GRAPH_WAVES x [likelihood, transition]) instead of 2+ stream launches per wave
-      if (!graph_done && !first && known >= 0 && !c->time_eval && !m->row_sharded && c->use_graphs) {
+      // launch-bound regime (small N x C): replay the waves from a CUDA graph (captured once: GW x [likelihood, transition])
+      // instead of 2+ stream launches per wave.  With a known wave count the graph is launched todo / GW times; otherwise
+      // (HMCDA, tuned HMC: per-chain trajectory lengths) it is launched until the device counter of unfinished chains
+      // reads zero -- every kernel of a wave returns at once when it does, so the surplus waves of the last replay cost
+      // launch latency only.
+      if (!graph_done && !first && !c->time_eval && !m->row_sharded && c->use_graphs && (known >= 0 || poll > 1)) {
         graph_done = true;
         const int64_t GW = 32;
-        const int64_t todo = known - waves;
+        const int64_t todo = known >= 0 ? known - waves : GW * 2;
         if (todo >= 2 * GW) {
           cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
           CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -686,23 +691,36 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
           }
           cudaError_t ce = cudaStreamEndCapture(st, &graph);
           if (crc != MCMCGPU_OK || ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return fail(MCMCGPU_E_CUDA, "CUDA graph capture of the wave loop failed"); }
+          struct GraphGuard { cudaGraph_t g; cudaGraphExec_t e; ~GraphGuard() { if (e) cudaGraphExecDestroy(e); if (g) cudaGraphDestroy(g); } } gg{graph, nullptr};
           CU(cudaGraphInstantiate(&gexec, graph, 0));
-          const int64_t reps = todo / GW;
-          for (int64_t rp = 0; rp < reps; rp++) CU(cudaGraphLaunch(gexec, st));
-          waves += reps * GW;
-          launches += reps * GW * (2 + (is_ram ? 1 : 0));
-          CU(cudaStreamSynchronize(st));
-          cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph);
+          gg.e = gexec;
+          const int64_t per_wave = 2 + (is_ram ? 1 : 0) + ((m->is_regression && R->nsplit > 4 && R->red) ? 1 : 0);
+          if (known >= 0) {
+            const int64_t reps = todo / GW;
+            for (int64_t rp = 0; rp < reps; rp++) CU(cudaGraphLaunch(gexec, st));
+            waves += reps * GW;
+            launches += reps * GW * per_wave;
+            CU(cudaStreamSynchronize(st));
+          } else {
+            for (;;) {
+              CU(cudaGraphLaunch(gexec, st));
+              waves += GW; launches += GW * per_wave;
+              CU(cudaMemcpyAsync(c->h_remaining, R->remaining, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+              CU(cudaStreamSynchronize(st));
+              if (*c->h_remaining == 0) break;
+            }
+            break;      // every chain has finished (or paused at the step limit)
+          }
         }
       }
       if (known >= 0 && waves >= known) break;
       const double* pp; int ns;
-      cudaEvent_t a0 = nullptr, a1 = nullptr;
-      if (c->time_eval) { CU(events.make(&a0)); CU(events.make(&a1)); CU(cudaEventRecord(a0, st)); }
+      cudaEvent_t a0 = nullptr, am = nullptr, a1 = nullptr;
+      if (c->time_eval) { CU(events.make(&a0)); CU(events.make(&am)); CU(events.make(&a1)); CU(cudaEventRecord(a0, st)); }
       int rc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad || first,
-                         first ? nullptr : need_ll_flags, R->phase, R->remaining, &pp, &ns);
+                         first ? nullptr : need_ll_flags, R->phase, R->remaining, &pp, &ns, am);
       if (rc != MCMCGPU_OK) return rc;
-      if (c->time_eval) { CU(cudaEventRecord(a1, st)); evs.push_back(a0); evs.push_back(a1); }
+      if (c->time_eval) { CU(cudaEventRecord(a1, st)); evs.push_back(a0); evs.push_back(am); evs.push_back(a1); }
       W.part = pp; W.nsplit = ns;
       CU(launch_transition(W, st));
       if (is_ram) { CU(launch_ram(W, false, st)); launches++; }
@@ -718,8 +736,10 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     }
     if (c->time_eval) {
       CU(cudaStreamSynchronize(st));
-      for (size_t k = 0; k + 1 < evs.size(); k += 2) {
-        float ms = 0; cudaEventElapsedTime(&ms, evs[k], evs[k + 1]); eval_ms += ms;
+      for (size_t k = 0; k + 2 < evs.size(); k += 3) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, evs[k], evs[k + 1]); eval_ms += ms;        // the likelihood kernel
+        cudaEventElapsedTime(&ms, evs[k + 1], evs[k + 2]); comm_ms += ms;    // split fold + all-reduce (row-sharded models)
       }
     }
   }
@@ -731,7 +751,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
   R->step_limit = upto;
   unsigned long long nev = 0;
   CU(cudaMemcpy(&nev, R->n_evals, sizeof(nev), cudaMemcpyDeviceToHost));
-  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = waves; info->n_launches = launches; info->eval_ms = eval_ms; }
+  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = waves; info->n_launches = launches; info->eval_ms = eval_ms; info->comm_ms = comm_ms; }
   // initial-support check (RWM.jl:55, MALA.jl:85, HMC.jl:121, HMCDA.jl:88)
   std::vector<int32_t> stt((size_t)R->C);
   CU(cudaMemcpy(stt.data(), R->status, sizeof(int32_t) * (size_t)R->C, cudaMemcpyDeviceToHost));
@@ -1134,7 +1154,7 @@ int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt,
   CU(cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   if (out_nresamples) *out_nresamples = (int64_t)nres;
-  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = steps * nt; info->n_launches = launches; info->eval_ms = 0; }
+  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = steps * nt; info->n_launches = launches; info->eval_ms = 0; info->comm_ms = 0; }
   return MCMCGPU_OK;
 }
 
@@ -1186,7 +1206,7 @@ int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_
   CU(cudaMemcpyAsync(&nev, A.nevals, sizeof(nev), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = 0; info->n_launches = 1; info->eval_ms = 0; }
+  if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = 0; info->n_launches = 1; info->eval_ms = 0; info->comm_ms = 0; }
   for (int32_t v : stt) if (v) return fail(MCMCGPU_E_SUPPORT, "Initial values out of model support, try other values");
   return MCMCGPU_OK;
 }

@@ -86,19 +86,19 @@ __device__ __forceinline__ double fin_grad(const EvalFin& f, const ModelDev& M, 
   return part[j * Cp + c];
 }
 
-__global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One chain's share of a wave.  Returns the number of evaluations it consumed (0 or 1).  `interior_done`: the chain is in the
+// middle of a trajectory and its momentum / position update has already been made element-parallel by the caller
+// (transition_kernel, stage A); only the per-chain counters are left.
+__device__ int transition_chain(const WaveArgs& W, const int64_t c, const bool interior_done) {
   const RunnerDev& R = W.R;
   const SamplerDev& S = W.S;
   const ModelDev& M = W.M;
-  if (c >= R.C) return;
-  if (!W.resume && *W.remaining == 0) return;
   const int ph = W.phase[c];
-  if (ph == PH_DONE) return;
+  if (ph == PH_DONE) return 0;
   if (W.resume) {
-    if (ph != PH_PAUSE) return;
+    if (ph != PH_PAUSE) return 0;
     atomicAdd(W.remaining, 1);
-  } else if (ph == PH_PAUSE) return;
+  } else if (ph == PH_PAUSE) return 0;
   const int64_t d = M.d, Cp = R.Cp;
   const uint64_t gchain = (uint64_t)(R.chain_offset + c);
   const int64_t burnin = R.first - 1;
@@ -113,9 +113,9 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
   int nl_cur = hmc_like ? W.nleaps_cur[c] : 0;
   const bool interior = (ph == PH_LEAP) && (leap + 1 < nl_cur) && (W.rb == nullptr);   // storeLeaps needs H at every leap
   EvalFin F; F.lt = CUDART_NAN; F.oos = false; F.ginv = 0.0; F.fam = M.family;
-  if (ph != PH_PAUSE) F = finalize_eval(M, q, part, ns, Cp, c, !interior);
+  if (ph != PH_PAUSE && !interior_done) F = finalize_eval(M, q, part, ns, Cp, c, !interior);
   const double lt_q = F.lt;
-  unsigned long long nev = (ph != PH_PAUSE) ? 1 : 0;
+  const int nev = (ph != PH_PAUSE) ? 1 : 0;
   bool begin = false;
 
   auto uniform = [&](int64_t step) -> double {
@@ -138,8 +138,8 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
     begin = true;
   } else if (ph == PH_INIT) {
     if (!isfinite(lt_q)) {   // "Initial values out of model support" RWM.jl:55 MALA.jl:85 HMC.jl:121 HMCDA.jl:88
-      W.status[c] = 1; W.phase[c] = PH_DONE; atomicSub(W.remaining, 1); atomicAdd(W.n_evals, nev);
-      return;
+      W.status[c] = 1; W.phase[c] = PH_DONE; atomicSub(W.remaining, 1);
+      return nev;
     }
     W.status[c] = 0;
     W.cur_lt[c] = lt_q;
@@ -214,6 +214,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       for (int64_t j = 0; j < d; j++) W.rb_acc[j * Cp + c] += wl * q[j * Cp + c];
     }
     if (leap < nl_cur) {
+      if (!interior_done)
 #pragma unroll 4
       for (int64_t j = 0; j < d; j++) {
         double gj = fin_grad(F, M, q, part, ns, Cp, c, j);
@@ -227,8 +228,7 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
       }
       W.leap[c] = leap;
       W.need_ll[c] = (leap + 1 == nl_cur || W.rb) ? 1 : 0;
-      atomicAdd(W.n_evals, nev);
-      return;
+      return nev;
     }
     double mm = 0.0;
     for (int64_t j = 0; j < d; j++) {
@@ -290,20 +290,17 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
         W.final_eps[c] = fe;
       }
       atomicSub(W.remaining, 1);
-      atomicAdd(W.n_evals, nev);
-      return;
+      return nev;
     }
     W.istep[c] = i;
     if (i > W.step_limit) {   // pause: mcmcgpu_run_execute_steps continues from here
       W.phase[c] = PH_PAUSE;
       atomicSub(W.remaining, 1);
-      atomicAdd(W.n_evals, nev);
-      return;
+      return nev;
     }
     if (kind == MCMCGPU_RAM) {   // the proposal needs the updated factor: ram_kernel makes it
       W.phase[c] = PH_RAM_BEGIN;
-      atomicAdd(W.n_evals, nev);
-      return;
+      return nev;
     }
     // ---- start step i: draw and write the next pending point ----
     double eps = S.scale; int nl = 0;
@@ -362,12 +359,52 @@ __global__ void __launch_bounds__(128) transition_kernel(const WaveArgs W) {
     }
     W.eps_cur[c] = eps;
   }
-  atomicAdd(W.n_evals, nev);
+  return nev;
+}
+
+// CTA = TR_CHAINS chains x TR_GROUPS parameter groups.
+//   stage A (all threads, element-parallel): chains in the middle of a trajectory -- the bulk of every HMC / HMCDA wave --
+//     get the end of leapfrog k and the start of leapfrog k+1 (HMC.jl:98,95,96) for their parameters j = group, group +
+//     TR_GROUPS, ...: every load and store is a coalesced 512-byte segment and the machine is full, where one thread per
+//     chain walking all d parameters left it latency-bound.  Per element the operations and their order are unchanged.
+//   stage B (group 0, one thread per chain): the state machine for everything else (transition_chain).
+// Evaluation counts are summed per CTA before the one atomic (one atomic per chain per wave serialised on a single address).
+constexpr int TR_CHAINS = 64, TR_GROUPS = 4;
+__global__ void __launch_bounds__(TR_CHAINS * TR_GROUPS) transition_kernel(const WaveArgs W) {
+  const RunnerDev& R = W.R;
+  if (!W.resume && *W.remaining == 0) return;
+  const int grp = threadIdx.x / TR_CHAINS;
+  const int64_t c = (int64_t)blockIdx.x * TR_CHAINS + (threadIdx.x % TR_CHAINS);
+  const int64_t d = W.M.d, Cp = R.Cp;
+  bool interior = false;
+  if (c < R.C && !W.resume && W.rb == nullptr && W.phase[c] == PH_LEAP) interior = (W.leap[c] + 2 <= W.nleaps_cur[c]);
+  __syncthreads();     // every group has read the chain's counters before group 0 advances them in stage B
+  if (interior) {
+    const ModelDev& M = W.M;
+    EvalFin F; F.fam = M.family; F.lt = CUDART_NAN; F.oos = false; F.ginv = 0.0;
+    if (M.family == MCMCGPU_FAM_LINEAR || M.family == MCMCGPU_FAM_LOGISTIC) F.oos = sum_part(W.part, W.nsplit, d + 1, d, Cp, c) > 0.0;
+    else if (M.family == MCMCGPU_FAM_PROBIT) F.ginv = M.hyper[0] * M.hyper[0];
+    const double eps = W.eps_cur[c];
+    for (int64_t j = grp; j < d; j += TR_GROUPS) {
+      const double gj = fin_grad(F, M, W.q, W.part, W.nsplit, Cp, c, j);
+      double m = W.mom[j * Cp + c];
+      m += (0.5 * gj) * eps;          // end of this leapfrog      HMC.jl:98
+      m += (0.5 * gj) * eps;          // start of the next one     HMC.jl:95
+      double p = W.q[j * Cp + c];
+      p += eps * m;                   //                           HMC.jl:96
+      W.mom[j * Cp + c] = m;
+      W.q[j * Cp + c] = p;
+    }
+  }
+  int nev = 0;
+  if (grp == 0 && c < R.C) nev = transition_chain(W, c, interior);
+  const int total = __syncthreads_count(nev);
+  if (threadIdx.x == 0 && total) atomicAdd(W.n_evals, (unsigned long long)total);
 }
 
 cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st) {
-  int blocks = (int)((W.R.C + 127) / 128);
-  transition_kernel<<<blocks, 128, 0, st>>>(W);
+  int blocks = (int)((W.R.C + TR_CHAINS - 1) / TR_CHAINS);
+  transition_kernel<<<blocks, TR_CHAINS * TR_GROUPS, 0, st>>>(W);
   return cudaGetLastError();
 }
 

@@ -19,3 +19,9 @@ def test_reference_arm_json_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["config"]["workload"] == "cfg2" and line["vs_baseline"] is None
+    # the config object is built by one function for both arms, so the driver's `same_config` comparison holds
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.config_block("cfg2", bench.WORKLOADS["cfg2"], 1)
+    for key in ("chains_per_gpu", "seed", "eps", "len", "parallelism", "N", "d", "sampler"):
+        assert key in bench.config_block("cfg4", bench.WORKLOADS["cfg4"], 8)
