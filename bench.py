@@ -27,7 +27,7 @@ Keys of the line (headline leg):
              estimates; a sweep over the trajectory length `len` with the best one timed as well.
 Sub-blocks of the default (cfg4) run, each a driver-timed number for another BASELINE config:
 `configs`    cfg3 (MALA probit N=1e5 d=20, 16 384 chains/GPU), cfg2 (HMC(0.75) 3-D Normal, 65 536 chains/GPU, fused
-             per-chain kernel), smallN (HMC logistic N=256 d=100, 102 400 chains/GPU: the launch-bound regime in which
+             per-chain kernel), smallN (HMC logistic N=256 d=100, 94 720 chains/GPU: the launch-bound regime in which
              the north star's 1e9 gradient evaluations/s is arithmetically reachable).
 `row_sharded` cfg5: tall data (6.25e6 rows x d=200 per GPU; 5e7 rows at 8 GPUs), chains replicated, one NCCL all-reduce
              of the (d+2) x C partials per leapfrog; K1 ms/launch and fold+all-reduce ms/leapfrog from CUDA events; at
@@ -88,9 +88,9 @@ WORKLOADS = {
                  family="logistic", N=6250000, d=200, chains=256, sampler="HMC", seed=5),
     "cfg2": dict(desc="HMC(0.75) 3-D Normal -dot(v,v), 65536 chains/GPU (BASELINE configs[1])", family="normal_fn",
                  N=0, d=3, chains=65536, sampler="HMC", seed=1),
-    "smallN": dict(desc="HMC (8 leapfrogs) logistic regression N=256 d=100, 102400 chains/GPU: launch-bound small-N regime "
+    "smallN": dict(desc="HMC (8 leapfrogs) logistic regression N=256 d=100, 94720 chains/GPU (5 full waves of 296 resident 64-chain CTAs): launch-bound small-N regime "
                         "(SURVEY 8d: 1e9 gradient evaluations/s is reachable only for N <~ 740)", family="logistic",
-                   N=256, d=100, chains=102400, sampler="HMC", seed=6, nleaps=8, eps=0.1),
+                   N=256, d=100, chains=94720, sampler="HMC", seed=6, nleaps=8, eps=0.1),
 }
 
 

@@ -38,6 +38,7 @@ struct mcmcgpu_ctx {
   int64_t force_splits = 0;   // option: override K1 row splits
   int64_t k1_debug = 0;       // option (experiments): see K1Args::debug
   int64_t use_graphs = 1;     // option: replay fixed-length wave loops from a CUDA graph
+  int64_t fuse_leap = 1;      // option: interior leapfrog updates inside the likelihood kernel when it runs unsplit
   int32_t* h_remaining = nullptr;  // pinned
   cudaMemPool_t pool = nullptr;    // this context's own stream-ordered pool (the device's default pool is left alone)
 };
@@ -217,6 +218,7 @@ int32_t mcmcgpu_set_option(mcmcgpu_ctx* c, const char* key, int64_t value) {
   else if (k == "force_splits") c->force_splits = value;
   else if (k == "k1_debug") c->k1_debug = value;
   else if (k == "use_graphs") c->use_graphs = value;
+  else if (k == "fuse_leap") c->fuse_leap = value;
   else return fail(MCMCGPU_E_ARG, "unknown option " + k);
   return MCMCGPU_OK;
 }
@@ -343,7 +345,7 @@ int32_t mcmcgpu_model_destroy(mcmcgpu_model* m) {
 // one evaluation of every chain at q -> part (and the all-reduce for row-sharded models)
 static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* red, int nsplit, int64_t C, int64_t Cp,
                      bool need_grad, const uint8_t* need_ll, const int32_t* phase, const int32_t* remaining,
-                     const double** part_out, int* nsplit_out, cudaEvent_t ev_k1_done = nullptr) {
+                     const double** part_out, int* nsplit_out, cudaEvent_t ev_k1_done = nullptr, const mcmcgpu_run* fuse = nullptr) {
   cudaStream_t st = m->ctx->stream;
   *part_out = part; *nsplit_out = nsplit;
   if (m->is_regression) {
@@ -352,6 +354,10 @@ static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* re
     for (int i = 0; i < 4; i++) a.hyper[i] = m->k1_hyper[i];
     a.q = q; a.part = part; a.Cp = Cp; a.nsplit = nsplit; a.need_grad = need_grad ? 1 : 0;
     a.need_ll = need_ll; a.phase = phase; a.remaining = remaining; a.debug = (int32_t)m->ctx->k1_debug;
+    a.fuse_leap = 0; a.leap = nullptr; a.nleaps_cur = nullptr; a.eps_cur = nullptr; a.mom = nullptr; a.q_rw = nullptr;
+    if (fuse) {      // interior leapfrogs made by the likelihood kernel itself (run_fuses_leap)
+      a.fuse_leap = 1; a.leap = fuse->leap; a.nleaps_cur = fuse->nleaps_cur; a.eps_cur = fuse->eps_cur; a.mom = fuse->mom; a.q_rw = fuse->q;
+    }
     CU(k1_launch(a, st));
     if (ev_k1_done) CU(cudaEventRecord(ev_k1_done, st));   // what follows (split fold, all-reduce) is timed apart: run_info.comm_ms
     if (!m->row_sharded && nsplit > 4 && red) {
@@ -591,6 +597,13 @@ __global__ void wave_init_kernel(int32_t* phase, int32_t* remaining, double* q, 
   for (int64_t j = 0; j < d; j++) q[j * Cp + c] = (c < C) ? (init_per_chain ? init[j * Cp + c] : init[j]) : 0.0;
 }
 
+// the likelihood kernel can make the interior leapfrog updates itself when one CTA sees all rows of its chains
+static bool run_fuses_leap(const mcmcgpu_run* R) {
+  const mcmcgpu_model* m = R->m;
+  return m->is_regression && !m->row_sharded && R->nsplit == 1 && !R->r.store_rb && m->ctx->fuse_leap &&
+         (R->s.kind == MCMCGPU_HMC || R->s.kind == MCMCGPU_HMCDA);
+}
+
 static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) {
   mcmcgpu_model* m = R->m;
   mcmcgpu_ctx* c = m->ctx;
@@ -623,6 +636,8 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
   } else {
     WaveArgs W;
     W.M = m->dev(); W.S = sampler_dev(R); W.R = runner_dev(R);
+    const mcmcgpu_run* fuse = run_fuses_leap(R) ? R : nullptr;
+    W.fused_interior = fuse ? 1 : 0;
     W.nsplit = R->nsplit; W.resume = 0; W.restore_da = R->restore_da ? 1 : 0; W.step0 = R->step0; W.step_limit = upto;
     W.q = R->q; W.part = R->part;
     W.cur_pars = R->cur_pars; W.cur_grad = R->cur_grad; W.cur_lt = R->cur_lt; W.mom = R->mom; W.H0 = R->H0;
@@ -674,7 +689,10 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       // (HMCDA, tuned HMC: per-chain trajectory lengths) it is launched until the device counter of unfinished chains
       // reads zero -- every kernel of a wave returns at once when it does, so the surplus waves of the last replay cost
       // launch latency only.
-      if (!graph_done && !first && !c->time_eval && !m->row_sharded && c->use_graphs && (known >= 0 || poll > 1)) {
+      // (measured at N = 256, d = 100, 94 720 chains, 0.5 ms per wave: replay 0.537 ms per wave against 0.500 from the stream, so
+      //  graphs are kept for waves of well under 0.1 ms of likelihood work)
+      const bool tiny_wave = !m->is_regression || (double)m->N * (double)m->d * (double)R->Cp < 4e8;
+      if (!graph_done && !first && !c->time_eval && !m->row_sharded && c->use_graphs && tiny_wave && (known >= 0 || poll > 1)) {
         graph_done = true;
         const int64_t GW = 32;
         const int64_t todo = known >= 0 ? known - waves : GW * 2;
@@ -684,7 +702,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
           int crc = MCMCGPU_OK;
           for (int64_t g = 0; g < GW && crc == MCMCGPU_OK; g++) {
             const double* pp; int ns;
-            crc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad, need_ll_flags, R->phase, R->remaining, &pp, &ns);
+            crc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad, need_ll_flags, R->phase, R->remaining, &pp, &ns, nullptr, fuse);
             W.part = pp; W.nsplit = ns;
             if (crc == MCMCGPU_OK && launch_transition(W, st) != cudaSuccess) crc = MCMCGPU_E_CUDA;
             if (crc == MCMCGPU_OK && is_ram && launch_ram(W, false, st) != cudaSuccess) crc = MCMCGPU_E_CUDA;
@@ -718,7 +736,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       cudaEvent_t a0 = nullptr, am = nullptr, a1 = nullptr;
       if (c->time_eval) { CU(events.make(&a0)); CU(events.make(&am)); CU(events.make(&a1)); CU(cudaEventRecord(a0, st)); }
       int rc = eval_wave(m, R->q, R->part, R->red, R->nsplit, R->C, R->Cp, need_grad || first,
-                         first ? nullptr : need_ll_flags, R->phase, R->remaining, &pp, &ns, am);
+                         first ? nullptr : need_ll_flags, R->phase, R->remaining, &pp, &ns, am, fuse);
       if (rc != MCMCGPU_OK) return rc;
       if (c->time_eval) { CU(cudaEventRecord(a1, st)); evs.push_back(a0); evs.push_back(am); evs.push_back(a1); }
       W.part = pp; W.nsplit = ns;
@@ -922,8 +940,11 @@ static int stats_common(mcmcgpu_ctx* c, const double* samples, const uint8_t* ac
   double* outs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double* hosts[5] = {out_mean, out_var_iid, out_var, out_ess, out_actime};
   DevBufs bufs;                              // every temporary below is released on every return path
-  for (int k = 0; k < 5; k++) if (hosts[k]) CU(bufs.get(&outs[k], (size_t)(d * Cp), st, false));
-  CU(launch_stats(samples, S, d, C, Cp, vtype, maxlag, batchlen, outs[0], outs[1], outs[2], outs[3], outs[4], st));
+  for (int k = 0; k < 5; k++) if (hosts[k] || k == 0) CU(bufs.get(&outs[k], (size_t)(d * Cp), st, false));   // the mean is always formed (pass 2 reads it)
+  double* bmean = nullptr;      // scratch of the stats kernels: batch-mean means, or the state of unfinished Geyer scans
+  if (vtype == MCMCGPU_VAR_BM) CU(bufs.get(&bmean, (size_t)(d * Cp), st, false));
+  else if (vtype != MCMCGPU_VAR_IID) CU(bufs.get(&bmean, (size_t)(6 * d * Cp), st, false));
+  CU(launch_stats(samples, S, d, C, Cp, vtype, maxlag, batchlen, outs[0], outs[1], outs[2], outs[3], outs[4], bmean, st));
   double* tmp = nullptr;
   CU(bufs.get(&tmp, (size_t)(C * d), st, false));
   for (int k = 0; k < 5; k++) if (hosts[k]) {

@@ -1,7 +1,7 @@
 #pragma once
 #include "common.cuh"
 namespace mg {
-constexpr int FUSED_THREADS = 128;
+constexpr int FUSED_THREADS = 64;   // 65 536 chains = 1024 CTAs = 6.9 per SM: 64-thread CTAs balance the SMs to 1 % (128: 16 vs 12 warps per SM)
 constexpr int FUSED_MAX_D = 8;
 struct FusedArgs {
   ModelDev M;

@@ -31,6 +31,13 @@ namespace mg {
 constexpr int K1_STAGES = 2;
 constexpr int K1_NR = 4;          // 8-row groups per phase-1 pass (independent DMMA accumulator chains)
 constexpr int PH_IDLE_K1 = 98;  // phases >= PH_PAUSE (98) have no pending evaluation (transition.h)
+constexpr int PH_LEAP_K1 = 3;   // PH_LEAP (transition.h)
+// x / v for the prior gradient, as transition.cu's div_by_var: exact reciprocal when v is a power of two
+__device__ __forceinline__ double k1_div_by_var(double x, double v) {
+  const long long b = __double_as_longlong(v);
+  const bool pow2 = ((b & 0x000FFFFFFFFFFFFFll) == 0) && v > 1e-150 && v < 1e150 && fabs(x) < 1e150 && (fabs(x) > 1e-150 || x == 0.0);
+  return pow2 ? __dmul_rn(x, __ddiv_rn(1.0, v)) : __ddiv_rn(x, v);
+}
 
 // row permutation inside an 8-row group: column n of the phase-1 B fragment reads row PI[n]
 // (bank-conflict-free for both phases when the row stride is 4 mod 8 doubles)
@@ -596,12 +603,46 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
     part[(int64_t)(d + 1) * Cp + mychain] = (double)nbad;
   }
   if (a.need_grad) {
+    // fused interior leapfrog (K1Args::fuse_leap; one split, so G is the chain's complete X'r).  Written with explicit
+    // round-to-nearest intrinsics: this translation unit allows multiply-add contraction and the update must round as
+    // the transition kernel's does (HMC.jl:95-98: (0.5 g) eps, m += ., p += eps m).
+    bool fused = false;
+    if (a.fuse_leap) fused = (a.phase[mychain] == PH_LEAP_K1) && (a.leap[mychain] + 2 <= a.nleaps_cur[mychain]);
+    if (fused) {
+      const double eps = a.eps_cur[mychain];
+      const bool linlog = (FAM == MCMCGPU_FAM_LINEAR || FAM == MCMCGPU_FAM_LOGISTIC);
+      const bool oos = linlog && nbad > 0;                 // LLAcc: out of support => zero gradient (modelparser.jl:64-72)
+      const double pvar = __dmul_rn(hy[0], hy[0]);
+      const double* brow = betas + (warp * 8 + g) * S;
 #pragma unroll
-    for (int jb = 0; jb < DK; jb++) {
+      for (int jb = 0; jb < DK; jb++) {
 #pragma unroll
-      for (int i = 0; i < 2; i++) {
-        int j = 8 * jb + 2 * t + i;   // C fragment: row g (chain), column 2t+i (feature)
-        if (j < d) part[(int64_t)j * Cp + mychain] = G[jb][i];
+        for (int i = 0; i < 2; i++) {
+          const int j = 8 * jb + 2 * t + i;
+          if (j < d) {
+            const int64_t idx = (int64_t)j * Cp + mychain;
+            const double qj = __dmul_rn(bsign, brow[j]);   // beta tile holds sign * q, sign = +-1: exact
+            double gj;
+            if (linlog) gj = oos ? 0.0 : __dadd_rn(G[jb][i], k1_div_by_var(__dsub_rn(0.0, qj), pvar));
+            else gj = __dsub_rn(G[jb][i], k1_div_by_var(qj, pvar));
+            const double hg = __dmul_rn(__dmul_rn(0.5, gj), eps);
+            double m = a.mom[idx];
+            m = __dadd_rn(m, hg);                          // end of this leapfrog      HMC.jl:98
+            m = __dadd_rn(m, hg);                          // start of the next one     HMC.jl:95
+            const double p = __dadd_rn(qj, __dmul_rn(eps, m));   //                     HMC.jl:96
+            a.mom[idx] = m;
+            a.q_rw[idx] = p;
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int jb = 0; jb < DK; jb++) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          int j = 8 * jb + 2 * t + i;   // C fragment: row g (chain), column 2t+i (feature)
+          if (j < d) part[(int64_t)j * Cp + mychain] = G[jb][i];
+        }
       }
     }
   }

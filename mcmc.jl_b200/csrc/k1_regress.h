@@ -36,6 +36,16 @@ struct K1Args {
   const int32_t* phase;    // [Cp] per-chain phase (PH_DONE chains are skipped), or null
   const int32_t* remaining; // device counter of unfinished chains, or null
   int32_t debug;           // experiments only: 1 = skip the link function (r = eta), 2 = skip phase 2
+  // fused interior leapfrog (nsplit == 1 only: the CTA then holds the complete gradient of its 64 chains in registers).
+  // A chain in the middle of an HMC / HMCDA trajectory (phase PH_LEAP, leap + 2 <= nleaps_cur) gets the end of this
+  // leapfrog and the start of the next one (HMC.jl:98,95,96) right here instead of a round trip of X'r through `part`
+  // and a pass of the transition kernel over mom / q; the transition kernel then only advances the chain's counters.
+  int32_t fuse_leap;
+  const int32_t* leap;       // [Cp]
+  const int32_t* nleaps_cur; // [Cp]
+  const double* eps_cur;     // [Cp]
+  double* mom;               // [d][Cp]
+  double* q_rw;              // == q
 };
 
 cudaError_t k1_pack(K1Pack& P, const double* dX /* N x d col-major, device */, const double* dy, int64_t N, int64_t d,

@@ -9,100 +9,228 @@
 //                     demeaned, 1/n-normalised autocovariance (StatsBase.acf(...; correlation=false))
 //   ess / actime      src/stats/ess.jl:6-19
 // The reference computes all n lags (O(n^2)) and then reads only those before the first non-positive
-// pair sum; here lags are produced LAGS_PER_PASS at a time from a register window and the scan stops
-// at the truncation point, which gives the same value with O(n * m) work.
-// Compiled with -fmad=false (sums in the reference's order).
+// pair sum; here the lags are produced a window at a time and the scan stops at the truncation point:
+// the same value with O(n m) work.
+//
+// Bound: HBM (8 S d C algorithmic bytes per pass).  Two passes over the draws in the common case:
+//   pass 1  stats_mean_kernel   the mean (serial sum, the reference's order) and, for batch means, the mean of
+//                               the batch means;
+//   pass 2  stats_var_kernel    the centred sum of squares (== lag 0) together with the first NL_FIRST - 1 lags
+//                               from ONE register ring of the last NL_FIRST centred values (Geyer's scan usually
+//                               stops inside it: IAT 1.7 for HMC(0.75)), or the batch-means variance.
+//   Only a chain whose pair sums are still positive after NL_FIRST lags goes on, NL_MORE lags per further pass.
+// Round 1 made four passes for IMSE (mean, variance, and a 16-lag window pass re-reading x[t] and x[t + lag]) at 120
+// registers per thread (16 warps per SM) and shifted the window through registers (~30 moves per element: issue-bound).
+// The rings below are rotated by unrolling (static register names, no moves), the next chunk's loads are issued before
+// the current chunk's arithmetic, and the kernels are specialised per estimator (32-80 registers; the windows beyond
+// NL_FIRST lags, which need two load streams, live in their own kernel and touch only the unfinished series).
+// Compiled with -fmad=false: the mean, the variance and lag 0 are summed exactly as the reference does (mul, then add);
+// the lag >= 1 products use an explicit fma (1e-16 per term, agreement with the oracle 1e-13), which halves the FP64
+// instructions of the window.
 #include "stats.h"
 
 namespace mg {
 
-constexpr int LW = 16;  // lags per pass (8 Geyer pairs)
+constexpr int ST_THREADS = 128;
+constexpr int NL_FIRST = 8;   // lags produced together with the variance (4 Geyer pairs)
+constexpr int NL_MORE = 8;    // lags per further pass (two load streams: x[t] and the ring at t + lag)
 
-__global__ void __launch_bounds__(128) stats_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C,
-                                                    int64_t Cp, int vtype, int64_t maxlag, int64_t batchlen,
-                                                    double* mean_o, double* viid_o, double* var_o, double* ess_o,
-                                                    double* act_o) {
+// ---- pass 1: mean (mean.jl:6), and the mean of the batch means (var.jl:20-26) ----
+__global__ void __launch_bounds__(ST_THREADS) stats_mean_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C,
+                                                                 int64_t Cp, int64_t batchlen, double* __restrict__ mean_o,
+                                                                 double* __restrict__ bmean_o) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t j = blockIdx.y;
   if (c >= C) return;
-  const double* x = samples + j * Cp + c;     // x[t] at x[t * d * Cp]
+  const double* x = samples + j * Cp + c;     // x[t] at x[t * st]
+  const int64_t st = d * Cp;
+  double s = 0.0;
+  constexpr int U = 16;                        // independent loads in flight per thread
+  int64_t t = 0;
+  if (bmean_o == nullptr) {
+    for (; t + U <= S; t += U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = x[(t + u) * st];
+#pragma unroll
+      for (int u = 0; u < U; u++) s += v[u];
+    }
+    for (; t < S; t++) s += x[t * st];
+  } else {
+    const int64_t nb = S / batchlen;
+    double sm = 0.0, bs = 0.0;
+    int64_t inb = 0, b = 0;
+    auto take = [&](double v) {
+      s += v;
+      if (b < nb) {
+        bs += v;
+        if (++inb == batchlen) { sm += bs / (double)batchlen; bs = 0.0; inb = 0; b++; }
+      }
+    };
+    for (; t + U <= S; t += U) {
+      double v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) v[u] = x[(t + u) * st];
+#pragma unroll
+      for (int u = 0; u < U; u++) take(v[u]);
+    }
+    for (; t < S; t++) take(x[t * st]);
+    bmean_o[j * Cp + c] = sm / (double)nb;
+  }
+  mean_o[j * Cp + c] = s / (double)S;
+}
+
+// autocovariance sums a[l] = sum_t (x[t] - mu)(x[t + lag0 + l] - mu), l = 0..NL-1, one pass.
+// A ring r[0..NL-1] holds the centred values at positions p .. p+NL-1; the chunk loop is unrolled over the ring so that
+// "the value l places ahead" is a register known at compile time.  lag0 == 0: the ring is also the stream of x[t]
+// (one load per element).  EXACT0: lag 0 is accumulated as mul + add (the reference's variance, bit for bit).
+template <int NL, bool LAG0_ZERO>
+__device__ __forceinline__ void acov_pass(const double* __restrict__ x, int64_t st, int64_t S, double mu, int64_t lag0, double (&a)[NL]) {
+#pragma unroll
+  for (int l = 0; l < NL; l++) a[l] = 0.0;
+  double r[NL], nx[NL], xt[NL];
+  auto cent = [&](int64_t idx) -> double { return (idx < S) ? x[idx * st] - mu : 0.0; };   // beyond the end: exact zeros
+#pragma unroll
+  for (int u = 0; u < NL; u++) r[u] = cent(lag0 + u);
+  const int64_t T = S - lag0;                  // t runs over 0 .. T-1
+  for (int64_t t0 = 0; t0 < T; t0 += NL) {
+    // the next chunk of the ring (and of x[t] when lag0 > 0) is requested before this chunk's arithmetic
+#pragma unroll
+    for (int u = 0; u < NL; u++) nx[u] = cent(t0 + lag0 + NL + u);
+    if (!LAG0_ZERO) {
+#pragma unroll
+      for (int u = 0; u < NL; u++) xt[u] = (t0 + u < T) ? x[(t0 + u) * st] - mu : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < NL; u++) {
+      const double v = LAG0_ZERO ? r[u] : xt[u];
+      if (LAG0_ZERO) {
+        a[0] += v * v;                                             // == sum (x - mu)^2 of Base.var, same roundings
+#pragma unroll
+        for (int l = 1; l < NL; l++) a[l] = fma(v, r[(u + l) % NL], a[l]);
+      } else {
+#pragma unroll
+        for (int l = 0; l < NL; l++) a[l] = fma(v, r[(u + l) % NL], a[l]);
+      }
+      r[u] = nx[u];
+    }
+  }
+}
+
+// Geyer scan over the pairs of one window (var.jl:56-71); returns true when the sequence is truncated
+template <int NL>
+__device__ __forceinline__ bool geyer_window(const double (&a)[NL], double n, int64_t lag0, int64_t k, bool monotone, int64_t& jj,
+                                             double& acv0, double& gsum, double& gprev) {
+#pragma unroll
+  for (int l = 0; l < NL; l += 2) {
+    if (jj > k) return true;
+    const double c0 = a[l] / n, c1 = a[l + 1] / n;
+    if (lag0 + l == 0) acv0 = c0;
+    double g = c0 + c1;                          // var.jl:57
+    if (g <= 0) return true;                     // :58-61 (m = j)
+    if (monotone && jj >= 1 && g > gprev) g = gprev;   // :65-71
+    gsum += g; gprev = g;
+    jj++;
+  }
+  return jj > k;
+}
+
+// ---- pass 2 (and the rare further passes): variance / batch means / Geyer ----
+template <int VT>
+__global__ void __launch_bounds__(ST_THREADS) stats_var_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C,
+                                                                int64_t Cp, int64_t maxlag, int64_t batchlen,
+                                                                const double* __restrict__ mean_i, const double* __restrict__ bmean_i,
+                                                                double* viid_o, double* var_o, double* ess_o, double* act_o,
+                                                                double* __restrict__ more) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (c >= C) return;
+  const double* x = samples + j * Cp + c;
   const int64_t st = d * Cp;
   const double n = (double)S;
-  // mean (mean.jl:6) and variance (Base.var: two-pass, n-1)
-  double s = 0.0;
-#pragma unroll 8
-  for (int64_t t = 0; t < S; t++) s += x[t * st];            // loads are independent: 8 in flight per thread
-  const double mu = s / n;
-  double ss = 0.0;
-#pragma unroll 8
-  for (int64_t t = 0; t < S; t++) { double v = x[t * st] - mu; ss += v * v; }
-  const double viid = (ss / (double)(S - 1)) / n;   // var.jl:7-8
-  double v = CUDART_NAN;
-  if (vtype == MCMCGPU_VAR_IID) {
-    v = viid;
-  } else if (vtype == MCMCGPU_VAR_BM) {
-    // var.jl:20-26
-    const int64_t nb = S / batchlen;
-    if (nb > 1) {
-      double sm = 0.0;
-      for (int64_t b = 0; b < nb; b++) {
-        double bs = 0.0;
-        for (int64_t t = 0; t < batchlen; t++) bs += x[(b * batchlen + t) * st];
-        sm += bs / (double)batchlen;
+  const double mu = mean_i[j * Cp + c];
+  const int64_t o = j * Cp + c;
+  double ss = 0.0, v = CUDART_NAN;
+  if (VT == MCMCGPU_VAR_IID || VT == MCMCGPU_VAR_BM) {
+    constexpr int U = 16;
+    const int64_t nb = (VT == MCMCGPU_VAR_BM) ? S / batchlen : 0;
+    const double mb = (VT == MCMCGPU_VAR_BM) ? bmean_i[j * Cp + c] : 0.0;
+    double sv = 0.0, bs = 0.0;
+    int64_t inb = 0, b = 0;
+    auto take = [&](double xv) {
+      const double dv = xv - mu;
+      ss += dv * dv;
+      if (VT == MCMCGPU_VAR_BM && b < nb) {
+        bs += xv;
+        if (++inb == batchlen) { const double e = bs / (double)batchlen - mb; sv += e * e; bs = 0.0; inb = 0; b++; }
       }
-      const double mb = sm / (double)nb;
-      double sv = 0.0;
-      for (int64_t b = 0; b < nb; b++) {
-        double bs = 0.0;
-        for (int64_t t = 0; t < batchlen; t++) bs += x[(b * batchlen + t) * st];
-        double dv = bs / (double)batchlen - mb;
-        sv += dv * dv;
-      }
-      v = (double)batchlen * (sv / (double)(nb - 1)) / (double)(nb * batchlen);
+    };
+    int64_t t = 0;
+    for (; t + U <= S; t += U) {
+      double w[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) w[u] = x[(t + u) * st];
+#pragma unroll
+      for (int u = 0; u < U; u++) take(w[u]);
     }
+    for (; t < S; t++) take(x[t * st]);
+    if (VT == MCMCGPU_VAR_BM && nb > 1) v = (double)batchlen * (sv / (double)(nb - 1)) / (double)(nb * batchlen);   // var.jl:20-26
   } else {
     // Geyer IMSE / IPSE (var.jl:45-75 / :95-116)
     const int64_t k = (maxlag - 1 >= 0) ? (maxlag - 1) / 2 : -1;   // floor((maxlag-1)/2)
-    if (k >= 0) {
-      const bool monotone = (vtype == MCMCGPU_VAR_IMSE);
-      double acv0 = 0.0, gsum = 0.0, gprev = 0.0;
-      int64_t jj = 0;          // Geyer pair index
-      bool stop = false;
-      for (int64_t lag0 = 0; !stop && jj <= k; lag0 += LW) {
-        // autocovariances at lags lag0 .. lag0+LW-1 in one pass over the series
-        double a[LW];
-#pragma unroll
-        for (int l = 0; l < LW; l++) a[l] = 0.0;
-        // window w[l] = x[t + lag0 + l] - mu, slid along t
-        double w[LW];
-#pragma unroll
-        for (int l = 0; l < LW; l++) { int64_t idx = lag0 + l; w[l] = (idx < S) ? x[idx * st] - mu : 0.0; }
-        for (int64_t t = 0; t + lag0 < S; t++) {
-          const double xt = x[t * st] - mu;
-#pragma unroll
-          for (int l = 0; l < LW; l++) a[l] += xt * w[l];   // terms beyond the end are exact zeros
-#pragma unroll
-          for (int l = 0; l + 1 < LW; l++) w[l] = w[l + 1];
-          int64_t nx = t + lag0 + LW;
-          w[LW - 1] = (nx < S) ? x[nx * st] - mu : 0.0;
-        }
-#pragma unroll
-        for (int l = 0; l < LW; l += 2) {
-          if (stop || jj > k) break;
-          double c0 = a[l] / n, c1 = a[l + 1] / n;
-          if (lag0 + l == 0) acv0 = c0;
-          double g = c0 + c1;                       // var.jl:57
-          if (g <= 0) { stop = true; break; }      // :58-61 (m = j)
-          if (monotone && jj >= 1 && g > gprev) g = gprev;   // :65-71
-          gsum += g; gprev = g;
-          jj++;
-        }
-      }
-      v = (-acv0 + 2.0 * gsum) / n;                 // :74
+    const bool monotone = (VT == MCMCGPU_VAR_IMSE);
+    double acv0 = 0.0, gsum = 0.0, gprev = 0.0;
+    int64_t jj = 0;
+    bool stop;
+    {
+      double a[NL_FIRST];
+      acov_pass<NL_FIRST, true>(x, st, S, mu, 0, a);
+      ss = a[0];
+      stop = (k < 0) || geyer_window<NL_FIRST>(a, n, 0, k, monotone, jj, acv0, gsum, gprev);
     }
+    // a series whose pair sums are still positive goes on in stats_more_kernel (its windows need two load streams and
+    // twice the registers: kept out of this kernel so that the common case runs at full occupancy)
+    const int64_t plane = d * Cp;
+    more[o] = stop ? 0.0 : 1.0;
+    if (!stop) {
+      more[plane + o] = acv0; more[2 * plane + o] = gsum; more[3 * plane + o] = gprev; more[4 * plane + o] = (double)jj;
+      more[5 * plane + o] = (ss / (double)(S - 1)) / n;
+      return;
+    }
+    if (k >= 0) v = (-acv0 + 2.0 * gsum) / n;                      // :74
   }
-  const int64_t o = j * Cp + c;
-  if (mean_o) mean_o[o] = mu;
+  const double viid = (ss / (double)(S - 1)) / n;                  // var.jl:7-8
+  if (VT == MCMCGPU_VAR_IID) v = viid;
+  if (viid_o) viid_o[o] = viid;
+  if (var_o) var_o[o] = v;
+  if (ess_o) ess_o[o] = n * viid / v;               // ess.jl:9
+  if (act_o) act_o[o] = v / viid;                   // ess.jl:18
+}
+
+// the windows beyond NL_FIRST lags, for the series stats_var_kernel left unfinished (slowly mixing chains)
+__global__ void __launch_bounds__(ST_THREADS) stats_more_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C, int64_t Cp,
+                                                                 int64_t maxlag, int monotone, const double* __restrict__ mean_i,
+                                                                 const double* __restrict__ more, double* viid_o, double* var_o,
+                                                                 double* ess_o, double* act_o) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t j = blockIdx.y;
+  if (c >= C) return;
+  const int64_t o = j * Cp + c, plane = d * Cp;
+  if (more[o] == 0.0) return;
+  const double* x = samples + j * Cp + c;
+  const int64_t st = d * Cp;
+  const double n = (double)S, mu = mean_i[o];
+  const int64_t k = (maxlag - 1) / 2;
+  double acv0 = more[plane + o], gsum = more[2 * plane + o], gprev = more[3 * plane + o];
+  int64_t jj = (int64_t)more[4 * plane + o];
+  const double viid = more[5 * plane + o];
+  bool stop = false;
+  for (int64_t lag0 = NL_FIRST; !stop; lag0 += NL_MORE) {
+    double a[NL_MORE];
+    acov_pass<NL_MORE, false>(x, st, S, mu, lag0, a);
+    stop = geyer_window<NL_MORE>(a, n, lag0, k, monotone != 0, jj, acv0, gsum, gprev);
+  }
+  const double v = (-acv0 + 2.0 * gsum) / n;        // var.jl:74
   if (viid_o) viid_o[o] = viid;
   if (var_o) var_o[o] = v;
   if (ess_o) ess_o[o] = n * viid / v;               // ess.jl:9
@@ -111,10 +239,29 @@ __global__ void __launch_bounds__(128) stats_kernel(const double* __restrict__ s
 
 cudaError_t launch_stats(const double* samples, int64_t S, int64_t d, int64_t C, int64_t Cp, int vtype, int64_t maxlag,
                          int64_t batchlen, double* mean, double* var_iid, double* var, double* ess, double* actime,
-                         cudaStream_t st) {
-  dim3 grid((unsigned)((C + 127) / 128), (unsigned)d);
-  stats_kernel<<<grid, 128, 0, st>>>(samples, S, d, C, Cp, vtype, maxlag, batchlen, mean, var_iid, var, ess, actime);
-  return cudaGetLastError();
+                         double* scratch, cudaStream_t st) {
+  // `mean` must be a device buffer [d][Cp] (pass 2 reads it); scratch: [d][Cp] for batch means, [6][d][Cp] for IMSE / IPSE
+  double* bmean_scratch = scratch;
+  dim3 grid((unsigned)((C + ST_THREADS - 1) / ST_THREADS), (unsigned)d);
+  const bool bm = (vtype == MCMCGPU_VAR_BM);
+  stats_mean_kernel<<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, batchlen, mean, bm ? bmean_scratch : nullptr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (!var_iid && !var && !ess && !actime) return cudaSuccess;
+  switch (vtype) {
+    case MCMCGPU_VAR_IID: stats_var_kernel<MCMCGPU_VAR_IID><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, nullptr); break;
+    case MCMCGPU_VAR_BM: stats_var_kernel<MCMCGPU_VAR_BM><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, bmean_scratch, var_iid, var, ess, actime, nullptr); break;
+    case MCMCGPU_VAR_IMSE: stats_var_kernel<MCMCGPU_VAR_IMSE><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, scratch); break;
+    case MCMCGPU_VAR_IPSE: stats_var_kernel<MCMCGPU_VAR_IPSE><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, scratch); break;
+    default: return cudaErrorInvalidValue;
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (vtype == MCMCGPU_VAR_IMSE || vtype == MCMCGPU_VAR_IPSE) {
+    stats_more_kernel<<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, vtype == MCMCGPU_VAR_IMSE ? 1 : 0, mean, scratch, var_iid, var, ess, actime);
+    e = cudaGetLastError();
+  }
+  return e;
 }
 
 __global__ void accept_rate_kernel(const uint8_t* accept, int64_t S, int64_t C, int64_t Cp, double* rate) {

@@ -3,9 +3,10 @@
 namespace mg {
 // K3: src/stats over stored draws, one thread per (chain, parameter) series.
 // samples: [S][d][Cp] chain-minor.  Outputs [d][Cp] (any may be null).
+// `mean` is required (the second pass reads it); scratch: [d][Cp] doubles for MCMCGPU_VAR_BM, [6][d][Cp] for IMSE / IPSE.
 cudaError_t launch_stats(const double* samples, int64_t S, int64_t d, int64_t C, int64_t Cp, int vtype, int64_t maxlag,
                          int64_t batchlen, double* mean, double* var_iid, double* var, double* ess, double* actime,
-                         cudaStream_t st);
+                         double* scratch, cudaStream_t st);
 // acceptance(c) in percent per chain (summary.jl:6-15): accept [S][Cp] -> rate [Cp]
 cudaError_t launch_accept_rate(const uint8_t* accept, int64_t S, int64_t C, int64_t Cp, double* rate, cudaStream_t st);
 }  // namespace mg

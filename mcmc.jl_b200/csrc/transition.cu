@@ -28,6 +28,14 @@ struct EvalFin {
   double ginv;   // gradient of the prior is (0 - q_j) * ginv  (or -q_j * ginv for probit)
   int fam;
 };
+// x / v for the prior gradient: when v is a power of two (prior sd 1, the examples' value: v = 1) the division is a
+// multiplication by the exact reciprocal -- the same double for every x whose quotient is a normal number -- instead of the
+// ~20-instruction IEEE division sequence
+__device__ __forceinline__ double div_by_var(double x, double v) {
+  const long long b = __double_as_longlong(v);
+  const bool pow2 = ((b & 0x000FFFFFFFFFFFFFll) == 0) && v > 1e-150 && v < 1e150 && fabs(x) < 1e150 && (fabs(x) > 1e-150 || x == 0.0);
+  return pow2 ? x * (1.0 / v) : x / v;
+}
 
 __device__ __forceinline__ EvalFin finalize_eval(const ModelDev& M, const double* q, const double* part, int nsplit,
                                                  int64_t Cp, int64_t c, bool want_lt) {
@@ -47,7 +55,7 @@ __device__ __forceinline__ EvalFin finalize_eval(const ModelDev& M, const double
       double s = 0.0;
 #pragma unroll 4
       for (int64_t j = 0; j < d; j++) {
-        double z = (q[j * Cp + c] - 0.0) / psd;
+        double z = div_by_var(q[j * Cp + c] - 0.0, psd);
         s += -(MG_LN_SQRT_2PI + 0.5 * z * z + lsd);
       }
       acc = 0.0 + s;
@@ -79,9 +87,9 @@ __device__ __forceinline__ double fin_grad(const EvalFin& f, const ModelDev& M, 
   if (f.fam == MCMCGPU_FAM_LINEAR || f.fam == MCMCGPU_FAM_LOGISTIC) {
     if (f.oos) return 0.0;
     double psd = M.hyper[0];
-    return sum_part(part, nsplit, j, M.d, Cp, c) + (0.0 - q[j * Cp + c]) / (psd * psd);
+    return sum_part(part, nsplit, j, M.d, Cp, c) + div_by_var(0.0 - q[j * Cp + c], psd * psd);
   } else if (f.fam == MCMCGPU_FAM_PROBIT) {
-    return sum_part(part, nsplit, j, M.d, Cp, c) - q[j * Cp + c] / f.ginv;
+    return sum_part(part, nsplit, j, M.d, Cp, c) - div_by_var(q[j * Cp + c], f.ginv);
   }
   return part[j * Cp + c];
 }
@@ -369,7 +377,7 @@ __device__ int transition_chain(const WaveArgs& W, const int64_t c, const bool i
 //     chain walking all d parameters left it latency-bound.  Per element the operations and their order are unchanged.
 //   stage B (group 0, one thread per chain): the state machine for everything else (transition_chain).
 // Evaluation counts are summed per CTA before the one atomic (one atomic per chain per wave serialised on a single address).
-constexpr int TR_CHAINS = 64, TR_GROUPS = 4;
+constexpr int TR_CHAINS = 64, TR_GROUPS = 4, TR_UNROLL = 5;
 __global__ void __launch_bounds__(TR_CHAINS * TR_GROUPS) transition_kernel(const WaveArgs W) {
   const RunnerDev& R = W.R;
   if (!W.resume && *W.remaining == 0) return;
@@ -385,15 +393,25 @@ __global__ void __launch_bounds__(TR_CHAINS * TR_GROUPS) transition_kernel(const
     if (M.family == MCMCGPU_FAM_LINEAR || M.family == MCMCGPU_FAM_LOGISTIC) F.oos = sum_part(W.part, W.nsplit, d + 1, d, Cp, c) > 0.0;
     else if (M.family == MCMCGPU_FAM_PROBIT) F.ginv = M.hyper[0] * M.hyper[0];
     const double eps = W.eps_cur[c];
-    for (int64_t j = grp; j < d; j += TR_GROUPS) {
-      const double gj = fin_grad(F, M, W.q, W.part, W.nsplit, Cp, c, j);
-      double m = W.mom[j * Cp + c];
-      m += (0.5 * gj) * eps;          // end of this leapfrog      HMC.jl:98
-      m += (0.5 * gj) * eps;          // start of the next one     HMC.jl:95
-      double p = W.q[j * Cp + c];
-      p += eps * m;                   //                           HMC.jl:96
-      W.mom[j * Cp + c] = m;
-      W.q[j * Cp + c] = p;
+    // TR_UNROLL elements per pass: all loads first (the stores to q / mom could alias them as far as the compiler knows)
+    for (int64_t j0 = grp; j0 < d; j0 += TR_GROUPS * TR_UNROLL) {
+      double gj[TR_UNROLL], m[TR_UNROLL], p[TR_UNROLL];
+#pragma unroll
+      for (int u = 0; u < TR_UNROLL; u++) {
+        const int64_t j = j0 + (int64_t)u * TR_GROUPS;
+        if (j < d) { gj[u] = fin_grad(F, M, W.q, W.part, W.nsplit, Cp, c, j); m[u] = W.mom[j * Cp + c]; p[u] = W.q[j * Cp + c]; }
+      }
+#pragma unroll
+      for (int u = 0; u < TR_UNROLL; u++) {
+        const int64_t j = j0 + (int64_t)u * TR_GROUPS;
+        if (j < d) {
+          m[u] += (0.5 * gj[u]) * eps;          // end of this leapfrog      HMC.jl:98
+          m[u] += (0.5 * gj[u]) * eps;          // start of the next one     HMC.jl:95
+          p[u] += eps * m[u];                   //                           HMC.jl:96
+          W.mom[j * Cp + c] = m[u];
+          W.q[j * Cp + c] = p[u];
+        }
+      }
     }
   }
   int nev = 0;
@@ -402,7 +420,342 @@ __global__ void __launch_bounds__(TR_CHAINS * TR_GROUPS) transition_kernel(const
   if (threadIdx.x == 0 && total) atomicAdd(W.n_evals, (unsigned long long)total);
 }
 
+// ---- cooperative transition for the regression families ------------------------------------------------------------
+// The regression families are compared with the reference arithmetic within a tolerance by nature (K1 sums X beta and X'r in
+// DMMA order), so here the O(d) sums of a decision -- kinetic energy, MALA proposal densities, the prior -- may be formed
+// as CO_GROUPS partial sums (added in group order: deterministic, independent of the chain's neighbours).  That lets the
+// whole state machine run element-parallel: 64 chains x CO_GROUPS parameter groups per CTA, a group owning the Philox
+// pairs k = group (mod CO_GROUPS), i.e. parameters 2k and 2k+1.  Per element every operation and its order is the
+// serial kernel's; the scalar decisions are taken by group 0 between the element-parallel stages:
+//   A  interior leapfrogs (as in transition_kernel)            B1 partial sums of the pending decision
+//   B2 decision, adaptation, keep/thin bookkeeping, next step  B3 accept copy, kept-draw stores, next draw and proposal
+//   B4 initial Hamiltonian / phase of the step just started
+// (one thread per chain walking all d parameters took 1.01 ms per decision wave at 102 400 chains x d = 100: every
+// Box-Muller pair, division and store of a chain in sequence.)
+constexpr int CO_CHAINS = 64, CO_GROUPS = 4, CO_UNROLL = 5;
+enum { CM_NONE = 0, CM_INTERIOR, CM_FINAL, CM_MALA, CM_RWM, CM_INIT, CM_RESUME };
+
+__global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 4) transition_coop_kernel(const WaveArgs W) {
+  __shared__ double s_sum[CO_GROUPS][3][CO_CHAINS];      // partial sums [group][slot][chain]
+  __shared__ double s_eps[CO_CHAINS];                    // step size of the step being started
+  __shared__ long long s_k[CO_CHAINS], s_i[CO_CHAINS];   // kept index of the step just decided (-1: not kept); step being started
+  __shared__ int s_acc[CO_CHAINS], s_begin[CO_CHAINS], s_nl[CO_CHAINS];
+  const RunnerDev& R = W.R;
+  const SamplerDev& S = W.S;
+  const ModelDev& M = W.M;
+  if (!W.resume && *W.remaining == 0) return;
+  const int lc = threadIdx.x % CO_CHAINS, grp = threadIdx.x / CO_CHAINS;
+  const int64_t c = (int64_t)blockIdx.x * CO_CHAINS + lc;
+  const int64_t d = M.d, Cp = R.Cp;
+  const int kind = S.kind;
+  const bool hmc_like = (kind == MCMCGPU_HMC || kind == MCMCGPU_HMCDA);
+  const bool linlog = (M.family == MCMCGPU_FAM_LINEAR || M.family == MCMCGPU_FAM_LOGISTIC);
+  const double* part = W.part;
+  const int ns = W.nsplit;
+  double* q = W.q;
+  const int64_t npairs = (d + 1) / 2;
+
+  // ---- stage 0: classify (every group reads the chain's counters; nobody has advanced them yet) ----
+  int mode = CM_NONE;
+  if (c < R.C) {
+    const int ph = W.phase[c];
+    if (W.resume) mode = (ph == PH_PAUSE) ? CM_RESUME : CM_NONE;
+    else if (ph == PH_INIT) mode = CM_INIT;
+    else if (ph == PH_RWM) mode = CM_RWM;
+    else if (ph == PH_MALA) mode = CM_MALA;
+    else if (ph == PH_LEAP) mode = (W.leap[c] + 2 <= W.nleaps_cur[c]) ? CM_INTERIOR : CM_FINAL;
+  }
+  const double eps_cur = (mode == CM_INTERIOR || mode == CM_FINAL || mode == CM_MALA) ? W.eps_cur[c] : 0.0;
+  EvalFin F; F.fam = M.family; F.lt = CUDART_NAN; F.oos = false; F.ginv = 0.0;
+  if (mode != CM_NONE && mode != CM_RESUME) {
+    if (linlog) F.oos = sum_part(part, ns, d + 1, d, Cp, c) > 0.0;    // LLAcc: a non-finite likelihood term => zero gradient
+    else F.ginv = M.hyper[0] * M.hyper[0];
+  }
+  __syncthreads();
+
+  // ---- stage A: interior leapfrogs ----
+  if (mode == CM_INTERIOR && !W.fused_interior) {
+    // CO_UNROLL elements per pass, all loads first (the stores to q / mom could alias them as far as the compiler knows)
+    for (int64_t j0 = grp; j0 < d; j0 += CO_GROUPS * CO_UNROLL) {
+      double gj[CO_UNROLL], m[CO_UNROLL], p[CO_UNROLL];
+#pragma unroll
+      for (int u = 0; u < CO_UNROLL; u++) {
+        const int64_t j = j0 + (int64_t)u * CO_GROUPS;
+        if (j < d) { gj[u] = fin_grad(F, M, q, part, ns, Cp, c, j); m[u] = W.mom[j * Cp + c]; p[u] = q[j * Cp + c]; }
+      }
+#pragma unroll
+      for (int u = 0; u < CO_UNROLL; u++) {
+        const int64_t j = j0 + (int64_t)u * CO_GROUPS;
+        if (j < d) {
+          m[u] += (0.5 * gj[u]) * eps_cur;          // end of this leapfrog      HMC.jl:98
+          m[u] += (0.5 * gj[u]) * eps_cur;          // start of the next one     HMC.jl:95
+          p[u] += eps_cur * m[u];                   //                           HMC.jl:96
+          W.mom[j * Cp + c] = m[u];
+          q[j * Cp + c] = p[u];
+        }
+      }
+    }
+  }
+
+  // ---- stage B1: partial sums of the pending decision over this group's parameters ----
+  const bool decide = (mode == CM_FINAL || mode == CM_MALA || mode == CM_RWM || mode == CM_INIT);
+  if (decide) {
+    double s0 = 0.0, s1 = 0.0, s2v = 0.0;      // slot 0: kinetic energy / q(new|old); slot 1: prior; slot 2: q(old|new)
+    const double psd = M.hyper[0];
+    const double lsd = linlog ? log(psd) : 0.0;
+    const double h = eps_cur;
+    const double lc2 = (mode == CM_MALA) ? log(MG_TWO_PI * h) / 2.0 : 0.0;
+    for (int64_t k = grp; k < npairs; k += CO_GROUPS) {
+#pragma unroll
+      for (int t2 = 0; t2 < 2; t2++) {
+        const int64_t j = 2 * k + t2;
+        if (j >= d) break;
+        const double qj = q[j * Cp + c];
+        if (linlog) { const double z = div_by_var(qj - 0.0, psd); s1 += -(MG_LN_SQRT_2PI + 0.5 * z * z + lsd); }   // vars ~ Normal(0, prior_sd)
+        else s1 += qj * qj;                                                                               // probit_regression.jl:19-22
+        if (mode == CM_FINAL) {
+          const double gj = fin_grad(F, M, q, part, ns, Cp, c, j);
+          double m = W.mom[j * Cp + c];
+          m += (0.5 * gj) * eps_cur;        // HMC.jl:98
+          s0 += m * m;
+        } else if (mode == CM_MALA) {       // MALA.jl:98,103-105
+          const double pj = W.cur_pars[j * Cp + c], gcur = W.cur_grad[j * Cp + c];
+          const double mean = pj + (h / 2.0) * gcur;
+          const double t1 = mean - qj;   s0 += -(t1 * t1) / (2.0 * h) - lc2;
+          const double mean2 = qj + (h / 2.0) * fin_grad(F, M, q, part, ns, Cp, c, j);
+          const double t3 = mean2 - pj;  s2v += -(t3 * t3) / (2.0 * h) - lc2;
+        }
+      }
+    }
+    s_sum[grp][0][lc] = s0; s_sum[grp][1][lc] = s1; s_sum[grp][2][lc] = s2v;
+  }
+  __syncthreads();
+
+  // ---- stage B2: the decision (group 0, one thread per chain) ----
+  int nev = 0;
+  if (grp == 0) {
+    s_acc[lc] = 0; s_begin[lc] = 0; s_k[lc] = -1; s_nl[lc] = 0; s_eps[lc] = 0.0; s_i[lc] = 0;
+    if (mode != CM_NONE) {
+      const uint64_t gchain = (uint64_t)(R.chain_offset + c);
+      const int64_t burnin = R.first - 1;
+      auto uniform = [&](int64_t step) -> double {
+        return W.inj_uniforms ? W.inj_uniforms[step * Cp + c] : philox_uniform(R.seed, gchain, (uint32_t)step);
+      };
+      nev = (mode == CM_RESUME) ? 0 : 1;
+      int64_t i = W.istep[c];
+      bool begin = false, acc = false;
+      double lt_q = CUDART_NAN;
+      if (decide) {            // the model-side finish of the evaluation (finalize_eval), from the partial sums
+        double pr = 0.0;
+        for (int g = 0; g < CO_GROUPS; g++) pr += s_sum[g][1][lc];
+        const double ll = sum_part(part, ns, d, d, Cp, c);
+        if (linlog) {
+          bool oos = F.oos;
+          const double a1 = 0.0 + pr;
+          if (!isfinite(a1)) oos = true;
+          const double a2 = a1 + ll;
+          if (!isfinite(a2)) oos = true;
+          lt_q = oos ? -CUDART_INF : a2;
+        } else {
+          const double pvar = F.ginv;
+          lt_q = (-0.5 * ((double)d * MG_LOG2PI + (double)d * log(pvar)) - 0.5 * (pr / pvar)) + ll;
+        }
+      }
+      double st_eps = CUDART_NAN; int st_nl = 0; bool stored = false;
+      if (mode == CM_RESUME) {
+        atomicAdd(W.remaining, 1);
+        begin = true;
+      } else if (mode == CM_INTERIOR) {
+        const int leap = W.leap[c] + 1;
+        W.leap[c] = leap;
+        W.need_ll[c] = (leap + 1 == W.nleaps_cur[c]) ? 1 : 0;
+      } else if (mode == CM_INIT) {
+        if (!isfinite(lt_q)) {     // "Initial values out of model support" RWM.jl:55 MALA.jl:85 HMC.jl:121 HMCDA.jl:88
+          W.status[c] = 1; W.phase[c] = PH_DONE; atomicSub(W.remaining, 1);
+        } else {
+          W.status[c] = 0;
+          W.cur_lt[c] = lt_q;
+          acc = true;              // "accept" the initial point: stage B3 copies q (and its gradient) into the state
+          if (kind == MCMCGPU_HMCDA && !W.restore_da) { W.da_leapstep[c] = 1.0; W.da_dual[c] = 1.0; W.da_dualH[c] = 0.0; }   // HMCDA.jl:90-94
+          if (S.tuner_on) { W.tn_step[c] = S.scale; W.tn_nleaps[c] = S.nleaps; W.tn_acc[c] = 0; W.tn_prop[c] = 0; }
+          i = W.step0 + 1;
+          begin = true;
+        }
+      } else if (mode == CM_RWM) {                                       // RWM.jl:62-70
+        const double ratio = lt_q - W.cur_lt[c];
+        acc = ratio > 0 || ratio > log_lean_normal(uniform(i));
+        if (acc) W.cur_lt[c] = lt_q;
+        stored = true; st_eps = CUDART_NAN; st_nl = 0;
+      } else if (mode == CM_MALA) {                                      // MALA.jl:103-118
+        double qno = 0.0, qon = 0.0;
+        for (int g = 0; g < CO_GROUPS; g++) { qno += s_sum[g][0][lc]; qon += s_sum[g][2][lc]; }
+        const double ratio = lt_q + qon - W.cur_lt[c] - qno;             // :107
+        acc = ratio > 0 || ratio > log_lean_normal(uniform(i));          // :108
+        if (acc) { W.cur_lt[c] = lt_q; if (S.tuner_on) W.tn_acc[c] += 1; }
+        stored = true; st_eps = eps_cur; st_nl = 0;
+      } else if (mode == CM_FINAL) {                                     // HMC.jl:154 / HMCDA.jl:120-121
+        double mm = 0.0;
+        for (int g = 0; g < CO_GROUPS; g++) mm += s_sum[g][0][lc];
+        const double H = -lt_q + 0.5 * mm;                               // update! HMC.jl:91
+        const double e = exp(W.H0[c] - H);
+        const double u = uniform(i);
+        double pacc = 0.0;
+        if (kind == MCMCGPU_HMCDA) { pacc = isnan(e) ? 0.0 : (e < 1.0 ? e : 1.0); acc = u < pacc; }
+        else acc = u < e;
+        if (acc) { W.cur_lt[c] = lt_q; if (S.tuner_on) W.tn_acc[c] += 1; }
+        stored = true; st_eps = eps_cur; st_nl = W.nleaps_cur[c];
+        if (kind == MCMCGPU_HMCDA) {
+          if (i < burnin) {                                               // HMCDA.jl:133-138
+            const double fi = (double)i;
+            double eta = 1.0 / (fi + S.t0);
+            const double dualH = (1.0 - eta) * W.da_dualH[c] + eta * (S.rate - pacc);
+            const double ls = exp(log(10.0 * 1.0) - sqrt(fi) * dualH / S.shrinkage);
+            eta = pow(fi, -S.step);
+            W.da_dual[c] = exp((1.0 - eta) * log(W.da_dual[c]) + eta * log(ls));
+            W.da_dualH[c] = dualH; W.da_leapstep[c] = ls;
+          } else {
+            W.da_leapstep[c] = W.da_dual[c];                              // :140
+          }
+        }
+      }
+      if (stored) {
+        if (in_range(i, R.first, R.step, R.last)) {                       // SerialMC.jl:49-66
+          const int64_t k = W.kept[c];
+          s_k[lc] = k;
+          W.accept[k * Cp + c] = acc ? 1 : 0;
+          if (W.logtarget) W.logtarget[k * Cp + c] = W.cur_lt[c];
+          if (W.eps) W.eps[k * Cp + c] = st_eps;
+          if (W.nleaps) W.nleaps[k * Cp + c] = st_nl;
+          W.kept[c] = k + 1;
+        }
+        if (S.tuner_on && i <= burnin && (i % S.adapt_step) == 0) {       // MALA.jl:116-118 / HMC.jl:167-169
+          const double rate = (double)W.tn_acc[c] / (double)W.tn_prop[c];
+          const double ts = W.tn_step[c] * (1.0 / (1.0 + exp(-11.0 * (rate - S.target_rate))) + 0.5);
+          W.tn_step[c] = ts;
+          if (kind == MCMCGPU_HMC) {
+            const double cl = ceil(S.target_path / ts);
+            W.tn_nleaps[c] = (cl < (double)S.max_step) ? (int64_t)cl : (int64_t)S.max_step;
+          }
+          W.tn_acc[c] = 0; W.tn_prop[c] = 0;
+        }
+        i++; begin = true;
+      }
+      s_acc[lc] = acc ? 1 : 0;
+      if (begin) {
+        W.istep[c] = i;
+        if (i > R.last) {
+          W.phase[c] = PH_DONE;
+          if (W.final_eps) W.final_eps[c] = (kind == MCMCGPU_HMCDA) ? W.da_leapstep[c] : (S.tuner_on ? W.tn_step[c] : S.scale);
+          atomicSub(W.remaining, 1);
+        } else if (i > W.step_limit) {
+          W.phase[c] = PH_PAUSE;
+          atomicSub(W.remaining, 1);
+        } else {
+          double eps = S.scale; int nl = 0;
+          if (kind == MCMCGPU_HMCDA) {
+            eps = W.da_leapstep[c];
+            double r = round(S.len / eps);                                // HMCDA.jl:104
+            if (!(r >= 1.0)) r = 1.0;
+            if (r > (double)S.max_leaps) r = (double)S.max_leaps;
+            nl = (int)r;
+          } else if (kind == MCMCGPU_HMC) {
+            if (S.tuner_on) { W.tn_prop[c] += 1; nl = (int)W.tn_nleaps[c]; eps = W.tn_step[c]; } else nl = S.nleaps;
+          } else if (kind == MCMCGPU_MALA) {
+            if (S.tuner_on) { W.tn_prop[c] += 1; eps = W.tn_step[c]; }
+          }
+          s_begin[lc] = 1; s_eps[lc] = eps; s_nl[lc] = nl; s_i[lc] = i;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- stage B3: accept copy, kept-draw stores, next draw and proposal (element-parallel) ----
+  const bool acc = s_acc[lc] != 0, begin = s_begin[lc] != 0;
+  const long long kk = s_k[lc];
+  double mm_part = 0.0;
+  if (acc || kk >= 0 || begin) {
+    const bool need_grad_state = (kind != MCMCGPU_RWM);
+    const double eps = s_eps[lc];
+    const int64_t inext = s_i[lc];
+    const double sq = (kind == MCMCGPU_MALA) ? sqrt(eps) : 0.0;
+    const uint64_t gchain = (uint64_t)(R.chain_offset + c);
+    for (int64_t k = grp; k < npairs; k += CO_GROUPS) {
+      double z0 = 0.0, z1 = 0.0;
+      if (begin) {
+        if (W.inj_normals) {
+          z0 = W.inj_normals[(inext * d + 2 * k) * Cp + c];
+          if (2 * k + 1 < d) z1 = W.inj_normals[(inext * d + 2 * k + 1) * Cp + c];
+        } else {
+          philox_normal_pair(R.seed, gchain, (uint32_t)inext, (uint32_t)k, z0, z1);
+        }
+      }
+#pragma unroll
+      for (int t2 = 0; t2 < 2; t2++) {
+        const int64_t j = 2 * k + t2;
+        if (j >= d) break;
+        double pj, gj = 0.0;
+        if (acc) {
+          pj = q[j * Cp + c];
+          W.cur_pars[j * Cp + c] = pj;
+          if (need_grad_state) { gj = fin_grad(F, M, q, part, ns, Cp, c, j); W.cur_grad[j * Cp + c] = gj; }
+        } else {
+          pj = W.cur_pars[j * Cp + c];
+          if (need_grad_state) gj = W.cur_grad[j * Cp + c];
+        }
+        if (kk >= 0) {                    // the post-decision state is what is kept (SerialMC.jl:49-53)
+          W.samples[(kk * d + j) * Cp + c] = pj;
+          if (W.grads) W.grads[(kk * d + j) * Cp + c] = need_grad_state ? gj : CUDART_NAN;
+        }
+        if (begin) {
+          const double z = t2 ? z1 : z0;
+          if (kind == MCMCGPU_RWM) {
+            q[j * Cp + c] = pj + z * (W.scale[j] * S.scale);            // RWM.jl:52,59
+          } else if (kind == MCMCGPU_MALA) {
+            const double mean = pj + (eps / 2.0) * gj;                   // MALA.jl:98
+            q[j * Cp + c] = mean + sq * z;                               // :100
+          } else {
+            double m = z;                                                // HMC.jl:136
+            mm_part += m * m;
+            m += (0.5 * gj) * eps;                                       // HMC.jl:95
+            double p = pj;
+            p += eps * m;                                                // HMC.jl:96
+            W.mom[j * Cp + c] = m;
+            q[j * Cp + c] = p;
+          }
+        }
+      }
+    }
+  }
+  if (begin && hmc_like) s_sum[grp][0][lc] = mm_part;
+  __syncthreads();
+
+  // ---- stage B4: the step just started ----
+  if (grp == 0 && begin) {
+    if (hmc_like) {
+      double mm = 0.0;
+      for (int g = 0; g < CO_GROUPS; g++) mm += s_sum[g][0][lc];
+      W.H0[c] = -W.cur_lt[c] + 0.5 * mm;                                 // update! HMC.jl:91
+      W.leap[c] = 0; W.nleaps_cur[c] = s_nl[lc];
+      W.need_ll[c] = (s_nl[lc] == 1) ? 1 : 0;
+      W.phase[c] = PH_LEAP;
+    } else {
+      W.need_ll[c] = 1;
+      W.phase[c] = (kind == MCMCGPU_RWM) ? PH_RWM : PH_MALA;
+    }
+    W.eps_cur[c] = s_eps[lc];
+  }
+  const int total = __syncthreads_count(nev);
+  if (threadIdx.x == 0 && total) atomicAdd(W.n_evals, (unsigned long long)total);
+}
+
 cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st) {
+  const bool regression = (W.M.family == MCMCGPU_FAM_LINEAR || W.M.family == MCMCGPU_FAM_LOGISTIC || W.M.family == MCMCGPU_FAM_PROBIT);
+  if (regression && W.S.kind != MCMCGPU_RAM && W.rb == nullptr) {
+    int blocks = (int)((W.R.C + CO_CHAINS - 1) / CO_CHAINS);
+    transition_coop_kernel<<<blocks, CO_CHAINS * CO_GROUPS, 0, st>>>(W);
+    return cudaGetLastError();
+  }
   int blocks = (int)((W.R.C + TR_CHAINS - 1) / TR_CHAINS);
   transition_kernel<<<blocks, TR_CHAINS * TR_GROUPS, 0, st>>>(W);
   return cudaGetLastError();

@@ -20,6 +20,7 @@ struct WaveArgs {
   int32_t restore_da;          // 1: HMCDA adaptation state was set by the host (mcmcgpu_run_set_state)
   int64_t step0;               // chains start at step step0 + 1
   int64_t step_limit;          // chains pause before starting a step > step_limit
+  int32_t fused_interior;      // 1: the likelihood kernel has already made the interior leapfrog updates (K1Args::fuse_leap)
   // evaluation in/out
   double* q;                   // [d][Cp]
   const double* part;          // [nsplit][d+2][Cp]
