@@ -593,7 +593,17 @@ def cfg2_block(B, wl, K, W, clock=False):
     ms = e0.elapsed_time(e1)
     r.close()
     e2e_s, h2d, d2h = B.e2e_leg(dm, scfg, C, d, np.ones(d), Ks, wl["seed"], rank * C, None, engine="fused")
-    ms_max, e2e_ms = B.max_over_ranks(ms, e2e_s * 1e3)
+    # summaries instead of draws: the same run, then src/stats on the device-resident draws (mean, MC variance, ESS, acceptance:
+    # what ess(batch) / mean(batch) / acceptance(batch) of the host API do); only the d x C summaries cross PCIe
+    B.barrier()
+    t0 = time.perf_counter()
+    r = capi.DeviceRun(dm, scfg, (1, 1, Ks), C, np.ones(d), seed=wl["seed"], chain_offset=rank * C, engine="fused", store_grad=False, store_logtarget=False)
+    r.execute()
+    st = r.stats("imse")
+    torch.cuda.synchronize()
+    sum_s = time.perf_counter() - t0
+    r.close()
+    ms_max, e2e_ms, sum_ms = B.max_over_ranks(ms, e2e_s * 1e3, sum_s * 1e3)
     dm.close()
     bytes_per = 8 * d * 2 + 8 + 1       # sample + gradient + log-target + accept flag per kept chain-step
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -602,6 +612,10 @@ def cfg2_block(B, wl, K, W, clock=False):
     return dict(description=wl["desc"], chains_per_gpu=C, steps=Ks, warmup=Ws, ms=ms_max, value=C * world * Ks / (ms_max / 1e3),
                 unit="chain-steps/s", gpu_launches=int(info["n_launches"]), clocks=clk.summary() if clk else None,
                 e2e=dict(value=C * world * Ks / (e2e_ms / 1e3), unit="chain-steps/s", h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K),
+                e2e_summaries=dict(value=C * world * Ks / (sum_ms / 1e3), unit="chain-steps/s", h2d_bytes_per_step=d * 8 / K,
+                                   d2h_bytes_per_step=(5 * d + 1) * C * 8 / K, median_ess_per_step=float(np.median(st["ess"])) / Ks,
+                                   note="run + mean / var_iid / var_imse / ess / actime / acceptance on the device-resident draws (mcmcgpu_run_stats); "
+                                        "the kept draws never leave HBM"),
                 roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, kernel="fused_chain_kernel",
                               note="store bandwidth of kept draws; the kernel is FP64-ALU/latency bound, see DESIGN.md"))
 

@@ -208,6 +208,13 @@ int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* ctx, int32_t family, int64_t d, int32_t n
                           int64_t npart, const double* particles, uint64_t seed, const double* inj_normals,
                           const double* inj_uniforms, const double* inj_res_uniforms, double* out_samples,
                           double* out_weights, int64_t* out_nresamples, mcmcgpu_run_info* info);
+/* SeqMC over arbitrary models of this context (any family, any d; the regression families evaluate all particles at once
+ * through the likelihood kernel): task t = (models[t], samplers[t]); everything else as mcmcgpu_run_seqmc. */
+int32_t mcmcgpu_run_seqmc_models(mcmcgpu_ctx* ctx, int32_t nt, mcmcgpu_model* const* models, const mcmcgpu_sampler_cfg* samplers,
+                                 int64_t steps, int64_t burnin, double trigger, int64_t npart, const double* particles,
+                                 uint64_t seed, const double* inj_normals, const double* inj_uniforms,
+                                 const double* inj_res_uniforms, double* out_samples, double* out_weights,
+                                 int64_t* out_nresamples, mcmcgpu_run_info* info);
 int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* ctx, int32_t family, int64_t d, int32_t nt, const double* hypers,
                                const mcmcgpu_sampler_cfg* samplers, int64_t steps, int64_t burnin, int64_t swap_period,
                                int64_t nrep, const double* inits, uint64_t seed, const double* inj_normals,

@@ -55,6 +55,7 @@ EXPORTS = [
     "mcmcgpu_run_execute", "mcmcgpu_run_execute_steps", "mcmcgpu_run_set_state", "mcmcgpu_run_get_state",
     "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_rb", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
     "mcmcgpu_run_destroy", "mcmcgpu_stats", "mcmcgpu_philox_draws", "mcmcgpu_run_seqmc", "mcmcgpu_run_serialtemp", "mcmcgpu_run_zv", "mcmcgpu_zv",
+    "mcmcgpu_run_seqmc_models",
 ]
 
 _lib = None
@@ -101,6 +102,8 @@ def lib():
         L.mcmcgpu_run_seqmc.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(SamplerCfg), C.c_int64, C.c_int64,
                                         C.c_double, C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int64),
                                         C.POINTER(RunInfo)]
+        L.mcmcgpu_run_seqmc_models.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(SamplerCfg), C.c_int64, C.c_int64, C.c_double,
+                                               C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int64), C.POINTER(RunInfo)]
         L.mcmcgpu_run_serialtemp.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(SamplerCfg), C.c_int64, C.c_int64,
                                              C.c_int64, C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int32),
                                              C.POINTER(RunInfo)]
@@ -226,6 +229,22 @@ class Context(_Owned):
         zn, un, ru = f64(normals), f64(uniforms), f64(res_uniforms)
         check(lib().mcmcgpu_run_seqmc(self.h, FAM[family], d, nt, dptr(hy), sc, steps, burnin, trigger, npart, dptr(particles), seed,
                                       dptr(zn), dptr(un), dptr(ru), dptr(samples), dptr(weights), C.byref(nres), C.byref(info)))
+        return dict(samples=samples, weights=weights, n_resamples=nres.value, info=info.as_dict())
+
+    def run_seqmc_models(self, models, samplers, steps, burnin, trigger, particles, seed=0, normals=None, uniforms=None,
+                         res_uniforms=None):
+        """SeqMC over DeviceModels of this context (any family, any d): task t = (models[t], samplers[t]).  With a
+        communicator the population is sharded: `particles` is this rank's share, injected draws are the GLOBAL arrays."""
+        particles = f64(particles)
+        npart, nt, d = particles.shape[0], len(samplers), models[0].d
+        mh = (C.c_void_p * nt)(*[m.h for m in models])
+        sc = (SamplerCfg * nt)(*samplers)
+        S = max(steps - burnin, 0) * npart
+        samples, weights = np.empty((S, d)), np.empty(S)
+        nres, info = C.c_int64(0), RunInfo()
+        zn, un, ru = f64(normals), f64(uniforms), f64(res_uniforms)
+        check(lib().mcmcgpu_run_seqmc_models(self.h, nt, mh, sc, steps, burnin, trigger, npart, dptr(particles), seed, dptr(zn), dptr(un),
+                                             dptr(ru), dptr(samples), dptr(weights), C.byref(nres), C.byref(info)))
         return dict(samples=samples, weights=weights, n_resamples=nres.value, info=info.as_dict())
 
     def run_serialtemp(self, family, d, hypers, samplers, steps, burnin, swap_period, nrep, inits, seed=0, normals=None,

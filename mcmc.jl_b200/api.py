@@ -597,8 +597,6 @@ def run(*args, **kw):
 def _population_tasks(tasks):
     m0 = tasks[-1].model
     assert all(t.model.size == m0.size for t in tasks), "Models do not have the same parameter vector size"   # SeqMC.jl:47
-    if any(t.model.family != m0.family for t in tasks):
-        raise NotImplementedError("population runners need every task on the same likelihood family")
     for t in tasks:
         if t.sampler.needs_gradient and not t.model.has_gradient:
             raise AssertionError(f"{type(t.sampler).__name__} sampler requires model with gradient function")
@@ -616,8 +614,16 @@ def _run_seqmc(tasks, particles=None, seed=0, normals=None, uniforms=None, res_u
     if particles is None:                                                  # SeqMC.jl:39 default: 100 particles of randn()
         particles = np.random.default_rng(seed).standard_normal((100, m0.size))
     particles = np.asarray([np.atleast_1d(p) for p in particles], dtype=np.float64)
-    res = default_context().run_seqmc(m0.family, m0.size, hypers, samplers, r.steps, r.burnin, r.trigger, particles, seed=seed,
-                                      normals=normals, uniforms=uniforms, res_uniforms=res_uniforms)
+    same_family = all(t.model.family == m0.family for t in tasks)
+    if same_family and m0.family in ("normal_fn", "normal_dsl", "abs_normal") and m0.size <= 8:
+        # closed-form ladder: one thread mutates one particle, everything in registers
+        res = default_context().run_seqmc(m0.family, m0.size, hypers, samplers, r.steps, r.burnin, r.trigger, particles, seed=seed,
+                                          normals=normals, uniforms=uniforms, res_uniforms=res_uniforms)
+    else:
+        # any models (regression families, d > 8, mixed families): particles are chains of one-step runs of the wave engine,
+        # the likelihood kernel evaluates the whole population at once
+        res = default_context().run_seqmc_models([t.model.device_model() for t in tasks], samplers, r.steps, r.burnin, r.trigger,
+                                                 particles, seed=seed, normals=normals, uniforms=uniforms, res_uniforms=res_uniforms)
     npart, S = particles.shape[0], (r.steps - r.burnin) * particles.shape[0]
     diags = {"weigths": res["weights"], "particle": np.tile(np.arange(1, npart + 1), r.steps - r.burnin)}
     chain = MCMCChain(range(r.burnin + 1, S + 1), res["samples"], None, diags, tasks, time.time() - t0, _colnames(m0))
@@ -633,6 +639,8 @@ def _run_serialtempmc(tasks, nreplicas=1, seed=0, **draws):
     t0 = time.time()
     r = tasks[-1].runner
     m0, hypers, samplers = _population_tasks(tasks)
+    if any(t.model.family != m0.family for t in tasks) or m0.family not in ("normal_fn", "normal_dsl", "abs_normal") or m0.size > 8:
+        raise NotImplementedError("SerialTempMC on the device: closed-form families with d <= 8, every task on the same family")
     inits = np.stack([t.model.init for t in tasks])
     try:
         res = default_context().run_serialtemp(m0.family, m0.size, hypers, samplers, r.steps, r.burnin, r.swapPeriod, nreplicas,

@@ -95,6 +95,7 @@ struct mcmcgpu_run {
   unsigned long long* n_evals = nullptr;
   // wave state
   double *rb = nullptr, *rb_acc = nullptr;
+  double* init_lt = nullptr;   // log-target at the initial point (the `reset` evaluation of the population runners)
   double *ram_S = nullptr, *ram_al = nullptr;
   uint8_t* ram_pending = nullptr;
   double *q = nullptr, *part = nullptr, *red = nullptr, *cur_pars = nullptr, *cur_grad = nullptr, *cur_lt = nullptr,
@@ -464,9 +465,13 @@ int32_t mcmcgpu_run_destroy(mcmcgpu_run* run) {
   return MCMCGPU_OK;
 }
 
-int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r, const double* init,
-                           const double* scale, const double* inj_normals, const double* inj_uniforms, mcmcgpu_run** out) {
-  if (!m || !s || !r || !init || !out) return fail(MCMCGPU_E_ARG, "NULL argument");
+}  // extern "C"
+
+// init_dev_cm: initial points already on the device, chain-minor [d][Cp] (population runners); overrides `init`
+static int run_create_impl(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r, const double* init,
+                           const double* init_dev_cm, const double* scale, const double* inj_normals, const double* inj_uniforms,
+                           mcmcgpu_run** out) {
+  if (!m || !s || !r || (!init && !init_dev_cm) || !out) return fail(MCMCGPU_E_ARG, "NULL argument");
   int rc = check_cfg(m, s, r);
   if (rc != MCMCGPU_OK) return rc;
   if ((inj_normals == nullptr) != (inj_uniforms == nullptr)) return fail(MCMCGPU_E_ARG, "inject both normals and uniforms or neither");
@@ -475,6 +480,8 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   cudaStream_t st = c->stream;
   mcmcgpu_run* R = new mcmcgpu_run();
   R->m = m; R->s = *s; R->r = *r;
+  if (init_dev_cm) R->r.init_per_chain = 1;
+  r = &R->r;
   if (R->s.max_leaps <= 0) R->s.max_leaps = 1LL << 20;
   const int64_t d = m->d, C = r->nchains, Cp = round_up(C, K1_CHAINS);
   const int64_t S = (r->last - r->first) / r->step + 1;
@@ -489,7 +496,10 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   if (s->kind == MCMCGPU_RAM && engine == MCMCGPU_ENGINE_WAVE && d > RAM_WAVE_MAX_D) { delete R; return fail(MCMCGPU_E_ARG, "RAM supports d <= 16"); }
 #define RCU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { std::string msg = std::string("CUDA: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__); mcmcgpu_run_destroy(R); return fail(MCMCGPU_E_CUDA, msg); } } while (0)
   // inputs
-  if (r->init_per_chain) {
+  if (init_dev_cm) {
+    RCU(R->alloc(&R->init, (size_t)(d * Cp), false));
+    RCU(cudaMemcpyAsync(R->init, init_dev_cm, sizeof(double) * (size_t)(d * Cp), cudaMemcpyDeviceToDevice, st));
+  } else if (r->init_per_chain) {
     double* tmp = nullptr;
     DevBufs staging;                        // released on every path, the failing ones of RCU included
     RCU(staging.up(&tmp, init, (size_t)(C * d), st));
@@ -560,6 +570,7 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     RCU(R->alloc(&R->tn_acc, (size_t)Cp));
     RCU(R->alloc(&R->tn_prop, (size_t)Cp));
     RCU(R->alloc(&R->need_ll, (size_t)Cp));
+    RCU(R->alloc(&R->init_lt, (size_t)Cp));
     if (r->store_rb) RCU(R->alloc(&R->rb_acc, (size_t)(d * Cp)));
     if (s->kind == MCMCGPU_RAM) {
       RCU(R->alloc(&R->ram_S, (size_t)(d * d * Cp)));
@@ -570,6 +581,13 @@ int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   RCU(cudaStreamSynchronize(st));
   *out = R;
   return MCMCGPU_OK;
+}
+
+extern "C" {
+int32_t mcmcgpu_run_create(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const mcmcgpu_runner_cfg* r, const double* init,
+                           const double* scale, const double* inj_normals, const double* inj_uniforms, mcmcgpu_run** out) {
+  if (!init) return fail(MCMCGPU_E_ARG, "NULL argument");
+  return run_create_impl(m, s, r, init, nullptr, scale, inj_normals, inj_uniforms, out);
 }
 
 static RunnerDev runner_dev(const mcmcgpu_run* R) {
@@ -649,6 +667,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     W.init = R->init; W.scale = R->scale; W.inj_normals = R->inj_normals; W.inj_uniforms = R->inj_uniforms;
     W.samples = R->samples; W.grads = R->grads; W.accept = R->accept; W.logtarget = R->logtarget;
     W.eps = R->eps; W.nleaps = R->nleaps; W.final_eps = R->final_eps; W.rb = R->rb; W.rb_acc = R->rb_acc;
+    W.init_lt = R->init_lt;
     const int kind = R->s.kind;
     const bool need_grad = (kind != MCMCGPU_RWM && kind != MCMCGPU_RAM);
     const bool is_ram = (kind == MCMCGPU_RAM);
@@ -1176,6 +1195,130 @@ int32_t mcmcgpu_run_seqmc(mcmcgpu_ctx* c, int32_t family, int64_t d, int32_t nt,
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   if (out_nresamples) *out_nresamples = (int64_t)nres;
   if (info) { info->gpu_ms = ms; info->n_grad_evals = (int64_t)nev; info->n_waves = steps * nt; info->n_launches = launches; info->eval_ms = 0; info->comm_ms = 0; }
+  return MCMCGPU_OK;
+}
+
+// SeqMC over arbitrary models (regression families through K1; SURVEY.md 8f.1 "reuses K1"): the mutation of every particle
+// by task t -- reset(task, particle) + one sampler step (SeqMC.jl:66-72) -- is a one-step run of the wave engine on model t
+// started at the particles (its initial evaluation is the `reset` evaluation), so particles are chains: K1 evaluates all
+// of them at once.  Weights, trigger, cumulative sum, resampling and the multi-GPU all-gather are the kernels of
+// population.cu.  Draw conventions as mcmcgpu_run_seqmc (Philox key = global particle id, step = (iter-1) nt + t + 1).
+int32_t mcmcgpu_run_seqmc_models(mcmcgpu_ctx* c, int32_t nt, mcmcgpu_model* const* models, const mcmcgpu_sampler_cfg* samplers,
+                                 int64_t steps, int64_t burnin, double trigger, int64_t npart, const double* particles,
+                                 uint64_t seed, const double* inj_normals, const double* inj_uniforms,
+                                 const double* inj_res_uniforms, double* out_samples, double* out_weights,
+                                 int64_t* out_nresamples, mcmcgpu_run_info* info) {
+  if (!c || !models || !samplers || !particles || !out_samples || !out_weights) return fail(MCMCGPU_E_ARG, "NULL argument");
+  if (burnin < 0) return fail(MCMCGPU_E_ARG, "Burnin rounds should be >= 0");                   // SeqMC.jl:29
+  if (steps <= burnin) return fail(MCMCGPU_E_ARG, "Steps should be > to burnin");               // SeqMC.jl:30
+  if (npart < 2 || nt < 1 || nt > POP_MAX_TASKS) return fail(MCMCGPU_E_ARG, "at least 2 particles and between 1 and 64 tasks");
+  const bool inj = inj_normals != nullptr;
+  if (inj != (inj_uniforms != nullptr) || inj != (inj_res_uniforms != nullptr)) return fail(MCMCGPU_E_ARG, "inject all three draw arrays or none");
+  for (int t = 0; t < nt; t++) {
+    if (!models[t] || models[t]->ctx != c) return fail(MCMCGPU_E_ARG, "every model must belong to this context");
+    if (models[t]->d != models[0]->d) return fail(MCMCGPU_E_ARG, "Models do not have the same parameter vector size");   // SeqMC.jl:47
+    const mcmcgpu_sampler_cfg& sc = samplers[t];
+    if (sc.tuner_on || (sc.kind != MCMCGPU_RWM && sc.kind != MCMCGPU_MALA && sc.kind != MCMCGPU_HMC))
+      return fail(MCMCGPU_E_ARG, "population runners take RWM, MALA or HMC tasks without tuner");
+  }
+  CU(use_ctx(c));
+  cudaStream_t st = c->stream;
+  const int64_t d = models[0]->d;
+  SeqArgs A;
+  A.T.nt = nt; A.T.family = models[0]->family; A.T.d = (int32_t)d;
+  DevBufs B;
+  const int nranks = c->comm ? c->nranks : 1;
+  const int64_t Np = round_up(npart, K1_CHAINS), S = (steps - burnin) * npart;
+  A.npart = npart; A.Np = Np; A.steps = steps; A.burnin = burnin; A.seed = seed; A.trigger = trigger;
+  A.rank = c->comm ? c->rank : 0; A.nranks = nranks;
+  A.gpart = npart * nranks; A.sendbuf = nullptr; A.gathered = nullptr;
+  const NcclApi* api = nullptr;
+  if (nranks > 1) {
+    api = nccl_api(nullptr);
+    if (!api) return fail(MCMCGPU_E_COMM, "NCCL unavailable");
+    double* gb = nullptr;
+    CU(B.get(&A.sendbuf, (size_t)((d + 2) * Np), st));
+    CU(B.get(&gb, (size_t)(nranks * (d + 2) * Np), st));
+    A.gathered = gb;
+  }
+  double* hp = nullptr;
+  CU(B.up(&hp, particles, (size_t)(npart * d), st));
+  CU(B.get(&A.pars, (size_t)(d * Np), st));
+  CU(transpose_to_chain_minor(hp, A.pars, npart, d, Np, st));
+  CU(B.get(&A.pars_tmp, (size_t)(d * Np), st));
+  CU(B.get(&A.logW, (size_t)Np, st)); CU(B.get(&A.logtarget, (size_t)Np, st)); CU(B.get(&A.lt_tmp, (size_t)Np, st));
+  CU(B.get(&A.W, (size_t)(Np * nranks), st)); CU(B.get(&A.cp, (size_t)(Np * nranks), st));
+  CU(B.get(&A.samples, (size_t)(S * d), st, false)); CU(B.get(&A.weights, (size_t)S, st, false));
+  CU(B.get(&A.nres, 1, st)); CU(B.get(&A.nevals, 1, st));
+  A.inj_normals = A.inj_uniforms = A.inj_res = nullptr;
+  if (inj) {      // only the resampling uniforms are read by a population kernel; the sampler draws go through the runs
+    double* r = nullptr;
+    CU(B.up(&r, inj_res_uniforms, (size_t)(steps * nt * A.gpart), st));
+    A.inj_res = r;
+  }
+  std::vector<double> zst, ust;      // injected sampler draws of one (iteration, target) in the run layout [particle][2][d]
+  if (inj) { zst.assign((size_t)(npart * 2 * d), 0.0); ust.assign((size_t)(npart * 2), 0.0); }
+  Events events;
+  cudaEvent_t e0, e1;
+  CU(events.make(&e0)); CU(events.make(&e1));
+  CU(cudaEventRecord(e0, st));
+  int64_t launches = 0, nev_total = 0, waves = 0;
+  const int64_t time_eval_saved = c->time_eval;
+  c->time_eval = 0;
+  struct Restore { mcmcgpu_ctx* c; int64_t v; ~Restore() { c->time_eval = v; } } restore{c, time_eval_saved};
+  for (int64_t i = 1; i <= steps; i++) {                                                        // SeqMC.jl:62
+    A.iter = i;
+    for (int t = 0; t < nt; t++) {                                                              // :64
+      A.target = t;
+      const int64_t pstep = (i - 1) * nt + t + 1;
+      mcmcgpu_runner_cfg rc;
+      memset(&rc, 0, sizeof(rc));
+      rc.step = 1; rc.nchains = npart; rc.chain_offset = (int64_t)A.rank * npart; rc.seed = seed;
+      rc.init_per_chain = 1; rc.store_grad = 0; rc.store_logtarget = 1; rc.engine = MCMCGPU_ENGINE_WAVE; rc.store_rb = 0;
+      const double *zn = nullptr, *un = nullptr;
+      if (inj) {
+        rc.first = 1; rc.last = 1;
+        const int64_t kbase = ((i - 1) * nt + t) * A.gpart + (int64_t)A.rank * npart;
+        for (int64_t n = 0; n < npart; n++) {
+          memcpy(&zst[(size_t)((n * 2 + 1) * d)], inj_normals + (kbase + n) * d, sizeof(double) * (size_t)d);
+          ust[(size_t)(n * 2 + 1)] = inj_uniforms[kbase + n];
+        }
+        zn = zst.data(); un = ust.data();
+      } else {
+        rc.first = pstep; rc.last = pstep;
+      }
+      mcmcgpu_run* R = nullptr;
+      int rcode = run_create_impl(models[t], &samplers[t], &rc, nullptr, A.pars, nullptr, zn, un, &R);
+      if (rcode != MCMCGPU_OK) return rcode;
+      struct RunGuard { mcmcgpu_run* r; ~RunGuard() { mcmcgpu_run_destroy(r); } } guard{R};
+      if (!inj) R->step0 = pstep - 1;              // the step's Philox counter is (iter-1) nt + t + 1, as in the closed-form runner
+      mcmcgpu_run_info ri;
+      rcode = execute_impl(R, -1, &ri);
+      if (rcode != MCMCGPU_OK) return rcode;
+      nev_total += ri.n_grad_evals; launches += ri.n_launches; waves += ri.n_waves;
+      CU(launch_seqmc_apply(A, R->samples, R->logtarget, R->init_lt, st));
+      if (nranks > 1) {
+        CU(launch_seqmc_pack(A, st));
+        int nrc = api->AllGather(A.sendbuf, (void*)A.gathered, (size_t)((d + 2) * Np), NCCL_FLOAT64, c->comm, st);
+        if (nrc != 0) return fail(MCMCGPU_E_COMM, std::string("ncclAllGather: ") + (api->GetErrorString ? api->GetErrorString(nrc) : "error"));
+        launches++;
+      }
+      CU(launch_seqmc_resample(A, st));
+      launches += 2;
+      CU(cudaStreamSynchronize(st));               // the run's buffers are released by `guard` right after
+    }
+    CU(launch_seqmc_store(A, st));
+    launches++;
+  }
+  CU(cudaEventRecord(e1, st));
+  CU(cudaMemcpyAsync(out_samples, A.samples, sizeof(double) * (size_t)(S * d), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(out_weights, A.weights, sizeof(double) * (size_t)S, cudaMemcpyDeviceToHost, st));
+  unsigned long long nres = 0;
+  CU(cudaMemcpyAsync(&nres, A.nres, sizeof(nres), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+  if (out_nresamples) *out_nresamples = (int64_t)nres;
+  if (info) { info->gpu_ms = ms; info->n_grad_evals = nev_total; info->n_waves = waves; info->n_launches = launches; info->eval_ms = 0; info->comm_ms = 0; }
   return MCMCGPU_OK;
 }
 

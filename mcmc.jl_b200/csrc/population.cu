@@ -186,6 +186,20 @@ __global__ void __launch_bounds__(1024) seqmc_resample_kernel(const SeqArgs A) {
   }
 }
 
+// mutation made by the wave engine (any family, any d): take over its one-step result and update the weights (:70-71)
+__global__ void seqmc_apply_kernel(const SeqArgs A, const double* __restrict__ ppars, const double* __restrict__ plt,
+                                   const double* __restrict__ ll0) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= A.npart) return;
+  for (int j = 0; j < A.T.d; j++) A.pars[j * A.Np + n] = ppars[j * A.Np + n];
+  A.logW[n] += ll0[n] - A.logtarget[n];                                          // :70
+  A.logtarget[n] = plt[n];                                                       // :71
+}
+cudaError_t launch_seqmc_apply(const SeqArgs& A, const double* ppars, const double* plt, const double* ll0, cudaStream_t st) {
+  seqmc_apply_kernel<<<(unsigned)((A.npart + 127) / 128), 128, 0, st>>>(A, ppars, plt, ll0);
+  return cudaGetLastError();
+}
+
 __global__ void seqmc_store_kernel(const SeqArgs A) {
   // SeqMC.jl:92-100: logtarget = zeros; after burn-in store every particle and its weight
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

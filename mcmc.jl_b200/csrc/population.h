@@ -30,6 +30,8 @@ cudaError_t launch_seqmc_mutate(const SeqArgs& A, cudaStream_t st);
 cudaError_t launch_seqmc_resample(const SeqArgs& A, cudaStream_t st);
 cudaError_t launch_seqmc_store(const SeqArgs& A, cudaStream_t st);
 cudaError_t launch_seqmc_pack(const SeqArgs& A, cudaStream_t st);
+// ppars [d][Np], plt [Np], ll0 [Np]: the one-step result of the wave engine for the current (iteration, target)
+cudaError_t launch_seqmc_apply(const SeqArgs& A, const double* ppars, const double* plt, const double* ll0, cudaStream_t st);
 
 struct TempArgs {
   PopTasks T;

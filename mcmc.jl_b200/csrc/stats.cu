@@ -15,25 +15,24 @@
 // Bound: HBM (8 S d C algorithmic bytes per pass).  Two passes over the draws in the common case:
 //   pass 1  stats_mean_kernel   the mean (serial sum, the reference's order) and, for batch means, the mean of
 //                               the batch means;
-//   pass 2  stats_var_kernel    the centred sum of squares (== lag 0) together with the first NL_FIRST - 1 lags
-//                               from ONE register ring of the last NL_FIRST centred values (Geyer's scan usually
-//                               stops inside it: IAT 1.7 for HMC(0.75)), or the batch-means variance.
-//   Only a chain whose pair sums are still positive after NL_FIRST lags goes on, NL_MORE lags per further pass.
+//   pass 2  stats_var_kernel    the centred sum of squares (== lag 0) together with the first NP_WIN Geyer pair sums
+//                               (16 lags) from one register ring (Geyer's scan usually stops inside it: a noise-level
+//                               pair sum is negative with probability 1/2), or the batch-means variance.
+//   Only a series whose pair sums are all still positive goes on, NP_WIN pairs per further pass (stats_more_kernel).
 // Round 1 made four passes for IMSE (mean, variance, and a 16-lag window pass re-reading x[t] and x[t + lag]) at 120
 // registers per thread (16 warps per SM) and shifted the window through registers (~30 moves per element: issue-bound).
 // The rings below are rotated by unrolling (static register names, no moves), the next chunk's loads are issued before
 // the current chunk's arithmetic, and the kernels are specialised per estimator (32-80 registers; the windows beyond
-// NL_FIRST lags, which need two load streams, live in their own kernel and touch only the unfinished series).
+// the first window live in their own kernel and touch only the unfinished series).
 // Compiled with -fmad=false: the mean, the variance and lag 0 are summed exactly as the reference does (mul, then add);
-// the lag >= 1 products use an explicit fma (1e-16 per term, agreement with the oracle 1e-13), which halves the FP64
-// instructions of the window.
+// the pair sums use an explicit fma on v_t (v_{t+2j} + v_{t+2j+1}) (1e-16 per term, agreement with the oracle 1e-13): a
+// quarter of the FP64 instructions of two separate mul + add lags.
 #include "stats.h"
 
 namespace mg {
 
 constexpr int ST_THREADS = 128;
-constexpr int NL_FIRST = 8;   // lags produced together with the variance (4 Geyer pairs)
-constexpr int NL_MORE = 8;    // lags per further pass (two load streams: x[t] and the ring at t + lag)
+constexpr int NP_WIN = 8;     // Geyer pairs (2 lags each) per window: the first window comes with the variance
 
 // ---- pass 1: mean (mean.jl:6), and the mean of the batch means (var.jl:20-26) ----
 __global__ void __launch_bounds__(ST_THREADS) stats_mean_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C,
@@ -80,53 +79,50 @@ __global__ void __launch_bounds__(ST_THREADS) stats_mean_kernel(const double* __
   mean_o[j * Cp + c] = s / (double)S;
 }
 
-// autocovariance sums a[l] = sum_t (x[t] - mu)(x[t + lag0 + l] - mu), l = 0..NL-1, one pass.
-// A ring r[0..NL-1] holds the centred values at positions p .. p+NL-1; the chunk loop is unrolled over the ring so that
-// "the value l places ahead" is a register known at compile time.  lag0 == 0: the ring is also the stream of x[t]
-// (one load per element).  EXACT0: lag 0 is accumulated as mul + add (the reference's variance, bit for bit).
-template <int NL, bool LAG0_ZERO>
-__device__ __forceinline__ void acov_pass(const double* __restrict__ x, int64_t st, int64_t S, double mu, int64_t lag0, double (&a)[NL]) {
+// Geyer's scan only needs the PAIR sums Gamma_j = gamma_{2j} + gamma_{2j+1} (var.jl:57), and
+//   n Gamma_j = sum_t v_t (v_{t+2j} + v_{t+2j+1}) = sum_t v_t s_{t+2j},   v = x - mu,  s_u = v_u + v_{u+1}  (zeros beyond the end),
+// i.e. one multiply-add per pair and element instead of two.  One window produces NP pairs starting at the even lag lag0:
+// a ring sr[0 .. 2 NP) holds s at positions t + lag0 .. t + lag0 + 2 NP - 1 and is rotated by unrolling (static register
+// names, no moves); it is refilled from ONE stream of x (position p + 1 completes s_p), the multiplier v_t is a second
+// stream that trails the first by lag0 + 2 NP elements (L1 / L2 hits for the first window).  FIRST also accumulates
+// a0 = sum v^2 as mul + add: the reference's variance and gamma_0, bit for bit.
+template <int NP, bool FIRST>
+__device__ __forceinline__ void acov_pairs(const double* __restrict__ x, int64_t st, int64_t S, double mu, int64_t lag0, double& a0,
+                                           double (&G)[NP]) {
+  constexpr int R = 2 * NP;
 #pragma unroll
-  for (int l = 0; l < NL; l++) a[l] = 0.0;
-  double r[NL], nx[NL], xt[NL];
+  for (int j = 0; j < NP; j++) G[j] = 0.0;
+  a0 = 0.0;
+  double sr[R], nx[R];
   auto cent = [&](int64_t idx) -> double { return (idx < S) ? x[idx * st] - mu : 0.0; };   // beyond the end: exact zeros
+  double vcur = cent(lag0);                    // v at the position whose s is formed next
 #pragma unroll
-  for (int u = 0; u < NL; u++) r[u] = cent(lag0 + u);
+  for (int u = 0; u < R; u++) { const double vn = cent(lag0 + u + 1); sr[u] = vcur + vn; vcur = vn; }
   const int64_t T = S - lag0;                  // t runs over 0 .. T-1
-  for (int64_t t0 = 0; t0 < T; t0 += NL) {
-    // the next chunk of the ring (and of x[t] when lag0 > 0) is requested before this chunk's arithmetic
+  for (int64_t t0 = 0; t0 < T; t0 += R) {
+    // the refill values of this chunk are requested before its arithmetic: position t0 + lag0 + R + u + 1 completes the s
+    // that replaces ring entry u
 #pragma unroll
-    for (int u = 0; u < NL; u++) nx[u] = cent(t0 + lag0 + NL + u);
-    if (!LAG0_ZERO) {
+    for (int u = 0; u < R; u++) nx[u] = cent(t0 + lag0 + R + u + 1);
 #pragma unroll
-      for (int u = 0; u < NL; u++) xt[u] = (t0 + u < T) ? x[(t0 + u) * st] - mu : 0.0;
-    }
+    for (int u = 0; u < R; u++) {
+      const double v = (t0 + u < T) ? x[(t0 + u) * st] - mu : 0.0;
+      if (FIRST) a0 += v * v;                                       // == sum (x - mu)^2 of Base.var, same roundings
 #pragma unroll
-    for (int u = 0; u < NL; u++) {
-      const double v = LAG0_ZERO ? r[u] : xt[u];
-      if (LAG0_ZERO) {
-        a[0] += v * v;                                             // == sum (x - mu)^2 of Base.var, same roundings
-#pragma unroll
-        for (int l = 1; l < NL; l++) a[l] = fma(v, r[(u + l) % NL], a[l]);
-      } else {
-#pragma unroll
-        for (int l = 0; l < NL; l++) a[l] = fma(v, r[(u + l) % NL], a[l]);
-      }
-      r[u] = nx[u];
+      for (int j = 0; j < NP; j++) G[j] = fma(v, sr[(u + 2 * j) % R], G[j]);
+      sr[u] = vcur + nx[u]; vcur = nx[u];
     }
   }
 }
 
 // Geyer scan over the pairs of one window (var.jl:56-71); returns true when the sequence is truncated
-template <int NL>
-__device__ __forceinline__ bool geyer_window(const double (&a)[NL], double n, int64_t lag0, int64_t k, bool monotone, int64_t& jj,
-                                             double& acv0, double& gsum, double& gprev) {
+template <int NP>
+__device__ __forceinline__ bool geyer_window(const double (&G)[NP], double n, int64_t k, bool monotone, int64_t& jj, double& gsum,
+                                             double& gprev) {
 #pragma unroll
-  for (int l = 0; l < NL; l += 2) {
+  for (int l = 0; l < NP; l++) {
     if (jj > k) return true;
-    const double c0 = a[l] / n, c1 = a[l + 1] / n;
-    if (lag0 + l == 0) acv0 = c0;
-    double g = c0 + c1;                          // var.jl:57
+    double g = G[l] / n;                         // var.jl:57 (c0 + c1, formed here as one sum)
     if (g <= 0) return true;                     // :58-61 (m = j)
     if (monotone && jj >= 1 && g > gprev) g = gprev;   // :65-71
     gsum += g; gprev = g;
@@ -183,10 +179,10 @@ __global__ void __launch_bounds__(ST_THREADS) stats_var_kernel(const double* __r
     int64_t jj = 0;
     bool stop;
     {
-      double a[NL_FIRST];
-      acov_pass<NL_FIRST, true>(x, st, S, mu, 0, a);
-      ss = a[0];
-      stop = (k < 0) || geyer_window<NL_FIRST>(a, n, 0, k, monotone, jj, acv0, gsum, gprev);
+      double G[NP_WIN];
+      acov_pairs<NP_WIN, true>(x, st, S, mu, 0, ss, G);
+      acv0 = ss / n;                                                // gamma_0 (var.jl:53)
+      stop = (k < 0) || geyer_window<NP_WIN>(G, n, k, monotone, jj, gsum, gprev);
     }
     // a series whose pair sums are still positive goes on in stats_more_kernel (its windows need two load streams and
     // twice the registers: kept out of this kernel so that the common case runs at full occupancy)
@@ -207,7 +203,7 @@ __global__ void __launch_bounds__(ST_THREADS) stats_var_kernel(const double* __r
   if (act_o) act_o[o] = v / viid;                   // ess.jl:18
 }
 
-// the windows beyond NL_FIRST lags, for the series stats_var_kernel left unfinished (slowly mixing chains)
+// the windows beyond the first NP_WIN pairs, for the series stats_var_kernel left unfinished (slowly mixing chains)
 __global__ void __launch_bounds__(ST_THREADS) stats_more_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C, int64_t Cp,
                                                                  int64_t maxlag, int monotone, const double* __restrict__ mean_i,
                                                                  const double* __restrict__ more, double* viid_o, double* var_o,
@@ -225,10 +221,10 @@ __global__ void __launch_bounds__(ST_THREADS) stats_more_kernel(const double* __
   int64_t jj = (int64_t)more[4 * plane + o];
   const double viid = more[5 * plane + o];
   bool stop = false;
-  for (int64_t lag0 = NL_FIRST; !stop; lag0 += NL_MORE) {
-    double a[NL_MORE];
-    acov_pass<NL_MORE, false>(x, st, S, mu, lag0, a);
-    stop = geyer_window<NL_MORE>(a, n, lag0, k, monotone != 0, jj, acv0, gsum, gprev);
+  for (int64_t lag0 = 2 * NP_WIN; !stop; lag0 += 2 * NP_WIN) {
+    double G[NP_WIN], unused;
+    acov_pairs<NP_WIN, false>(x, st, S, mu, lag0, unused, G);
+    stop = geyer_window<NP_WIN>(G, n, k, monotone != 0, jj, gsum, gprev);
   }
   const double v = (-acv0 + 2.0 * gsum) / n;        // var.jl:74
   if (viid_o) viid_o[o] = viid;

@@ -151,6 +151,7 @@ __device__ int transition_chain(const WaveArgs& W, const int64_t c, const bool i
     }
     W.status[c] = 0;
     W.cur_lt[c] = lt_q;
+    if (W.init_lt) W.init_lt[c] = lt_q;
     for (int64_t j = 0; j < d; j++) {
       W.cur_pars[j * Cp + c] = q[j * Cp + c];
       if (kind != MCMCGPU_RWM && kind != MCMCGPU_RAM) W.cur_grad[j * Cp + c] = fin_grad(F, M, q, part, ns, Cp, c, j);
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 4) transition_coop_kern
         } else {
           W.status[c] = 0;
           W.cur_lt[c] = lt_q;
+          if (W.init_lt) W.init_lt[c] = lt_q;
           acc = true;              // "accept" the initial point: stage B3 copies q (and its gradient) into the state
           if (kind == MCMCGPU_HMCDA && !W.restore_da) { W.da_leapstep[c] = 1.0; W.da_dual[c] = 1.0; W.da_dualH[c] = 0.0; }   // HMCDA.jl:90-94
           if (S.tuner_on) { W.tn_step[c] = S.scale; W.tn_nleaps[c] = S.nleaps; W.tn_acc[c] = 0; W.tn_prop[c] = 0; }

@@ -45,6 +45,7 @@ struct WaveArgs {
   double* final_eps;
   double* rb;                  // [S][d][Cp] Rao-Blackwell sums (store_rb) or null
   double* rb_acc;              // [d][Cp] running sum_k w_k pars_k of the current trajectory
+  double* init_lt;             // [Cp] log-target at the initial point, or null
 };
 
 cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st);

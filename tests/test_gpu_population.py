@@ -94,3 +94,56 @@ def test_serialtemp_host_api():
     #  (:53,62), the reference's chain is not a per-task sampler of N(0, sigma_t); parity is what is checked above)
     reps = mj.run(tasks, nreplicas=8, seed=6)
     assert len(reps) == 8 and not np.array_equal(reps[0].samples.values, reps[1].samples.values)
+
+
+def test_seqmc_models_equals_closed_form_runner(O, capi, ctx):
+    """the model-array SeqMC (wave engine) on a closed-form ladder reproduces the in-register runner and the oracle"""
+    fam, d = "normal_dsl", 3
+    kinds = [("MALA", dict(scale=0.3)), ("HMC", dict(scale=0.4, nleaps=3)), ("RWM", dict(scale=0.5))]
+    hypers = [(0.0, float(s)) for s in np.logspace(1, -1, 3)]
+    models, osmp, gsmp = _ladder(O, capi, fam, d, hypers, kinds)
+    rng = np.random.default_rng(5)
+    npart, steps, burnin, trigger = 130, 5, 1, 0.5
+    parts = rng.standard_normal((npart, d))
+    zn = rng.standard_normal((steps, 3, npart, d)); un = rng.random((steps, 3, npart)); ru = rng.random((steps, 3, npart))
+    ref = O.run_seqmc(models, osmp, steps, burnin, trigger, parts, zn, un, ru)
+    dms = [capi.DeviceModel(ctx, fam, d, hyper=h) for h in hypers]
+    out = ctx.run_seqmc_models(dms, gsmp, steps, burnin, trigger, parts, normals=zn, uniforms=un, res_uniforms=ru)
+    assert out["n_resamples"] == ref["n_resamples"] and np.array_equal(out["samples"], ref["samples"])
+    assert np.allclose(out["weights"], ref["weights"], rtol=1e-14, atol=0)
+    # Philox mode: both runners key the draws by (seed, particle, (iter-1) nt + t + 1): identical populations
+    a = ctx.run_seqmc(fam, d, hypers, gsmp, steps, burnin, trigger, parts, seed=9)
+    b = ctx.run_seqmc_models(dms, gsmp, steps, burnin, trigger, parts, seed=9)
+    assert a["n_resamples"] == b["n_resamples"] and np.array_equal(a["samples"], b["samples"])
+    for m in dms:
+        m.close()
+
+
+@pytest.mark.parametrize("fam", ["logistic", "probit", "linear"])
+def test_seqmc_over_regression_models(O, capi, ctx, fam):
+    """SeqMC with the regression families (the population reuses K1): a ladder of priors from wide to the
+    model's own over the same data, RWM / MALA / HMC tasks, particles = chains of the likelihood kernel; against the oracle
+    with injected draws: same resampling events, samples to 1e-9, weights to 1e-8."""
+    from conftest import make_regression
+    N, d, npart, steps, burnin = 400, 12, 200, 4, 1
+    X, y, hy, b0 = make_regression(fam, N, d, 31)
+    sds = [4.0, 2.0, 1.0] if fam != "probit" else [40.0, 20.0, 10.0]
+    hys = [(sd,) + tuple(hy[1:]) for sd in sds]
+    kinds = [("RWM", dict(scale=0.02)), ("MALA", dict(scale=0.002)), ("HMC", dict(scale=0.03, nleaps=3))]
+    oms = [O.Model(fam, d, X, y, h) for h in hys]
+    dms = [capi.DeviceModel(ctx, fam, d, X, y, h) for h in hys]
+    osmp = [O.sampler(k, **kw) for k, kw in kinds]; gsmp = [capi.sampler_cfg(k, **kw) for k, kw in kinds]
+    rng = np.random.default_rng(3)
+    parts = b0 + 0.1 * rng.standard_normal((npart, d))
+    zn = rng.standard_normal((steps, 3, npart, d)); un = rng.random((steps, 3, npart)); ru = rng.random((steps, 3, npart))
+    # a trigger between the weight variances seen, so that some targets resample and some do not
+    probe = O.run_seqmc(oms, osmp, steps, burnin, 0.0, parts, zn, un, ru)
+    trig = float(np.median(np.var(probe["weights"].reshape(steps - burnin, npart), axis=1, ddof=1)))
+    ref = O.run_seqmc(oms, osmp, steps, burnin, trig, parts, zn, un, ru)
+    out = ctx.run_seqmc_models(dms, gsmp, steps, burnin, trig, parts, normals=zn, uniforms=un, res_uniforms=ru)
+    assert ref["rc"] == 0 and out["n_resamples"] == ref["n_resamples"]
+    assert np.allclose(out["samples"], ref["samples"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(out["weights"], ref["weights"], rtol=1e-7, atol=0)
+    assert out["info"]["n_grad_evals"] == npart * steps * (2 + 2 + 4)
+    for m in dms:
+        m.close()
