@@ -79,6 +79,9 @@ typedef struct {
 double orc_eval(const orc_model* m, const double* beta);                  /* model.eval     */
 double orc_evalallg(const orc_model* m, const double* beta, double* grad); /* model.evalallg */
 double orc_log_ndtr(double x); /* log Phi(x) */
+/* CPU-baseline shape of the logistic evaluation (row-blocked, X read once, 4 partial sums per dot product); process-wide
+ * switch, used by bench.py's timed CPU legs only -- parity tests run with it off */
+void orc_set_fast_baseline(int on);
 
 /* ---- one chain, injected draws (SerialMC.jl:37-85 around the sampler loop bodies) ----
  * normals : d x (last+1) column-major; column 0 is the pre-loop draw (used by HMCDA only,

@@ -75,6 +75,13 @@ def lib():
     return _lib
 
 
+def set_fast_baseline(on):
+    """row-blocked logistic evaluation for the timed CPU baseline (bench.py); never used by parity tests"""
+    lib().orc_set_fast_baseline.argtypes = [C.c_int]
+    lib().orc_set_fast_baseline.restype = None
+    lib().orc_set_fast_baseline(1 if on else 0)
+
+
 def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
 

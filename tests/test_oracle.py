@@ -358,3 +358,21 @@ def test_hmc_and_hmcda_steps_on_logistic_two_sources(O):
     assert 0.3 < np.mean(keep_acc) < 1.0 and abs(keep_eps[0] / eps0 - 1) > 1e-3
     assert np.array_equal(res["accept"], np.array(keep_acc, dtype=np.uint8)) and np.array_equal(res["nleaps"], keep_nl)
     assert np.allclose(res["eps"], keep_eps, rtol=1e-9) and np.allclose(res["samples"], np.array(keep_s), rtol=1e-9, atol=1e-12)
+
+
+def test_fast_baseline_variant_agrees(O):
+    """the row-blocked evaluation timed by bench.py's CPU legs is the same function (reassociated sums: 1e-13)"""
+    X, y, hy, b0 = make_regression("logistic", 1300, 9, 33)
+    m = O.Model("logistic", 9, X, y, hy)
+    rng = np.random.default_rng(1)
+    gs = np.abs(X).sum(0)
+    try:
+        for k in range(4):
+            b = b0 + 0.2 * k * rng.standard_normal(9)
+            O.set_fast_baseline(False); lt0, g0 = m.evalallg(b); e0 = m.eval(b)
+            O.set_fast_baseline(True); lt1, g1 = m.evalallg(b); e1 = m.eval(b)
+            assert abs(lt1 - lt0) <= 1e-13 * abs(lt0) and abs(e1 - e0) <= 1e-13 * abs(e0) and np.all(np.abs(g1 - g0) <= 1e-13 * gs)
+        O.set_fast_baseline(True)
+        assert m.evalallg(np.array([0.0, 800.0] + [0.0] * 7))[0] == -np.inf          # LLAcc semantics kept
+    finally:
+        O.set_fast_baseline(False)
