@@ -215,6 +215,15 @@ int32_t mcmcgpu_run_seqmc_models(mcmcgpu_ctx* ctx, int32_t nt, mcmcgpu_model* co
                                  uint64_t seed, const double* inj_normals, const double* inj_uniforms,
                                  const double* inj_res_uniforms, double* out_samples, double* out_weights,
                                  int64_t* out_nresamples, mcmcgpu_run_info* info);
+/* SerialTempMC over arbitrary models of this context (any family, any d): nrep independent replicas, regrouped at every
+ * iteration by the task they consume; rep_offset = global id of this context's first replica (Philox key: replicas shard
+ * over GPUs with no communication -- serial tempering moves ONE chain between tasks, SerialTempMC.jl:57-66, it never
+ * exchanges states between chains).  Everything else as mcmcgpu_run_serialtemp. */
+int32_t mcmcgpu_run_serialtemp_models(mcmcgpu_ctx* ctx, int32_t nt, mcmcgpu_model* const* models, const mcmcgpu_sampler_cfg* samplers,
+                                      int64_t steps, int64_t burnin, int64_t swap_period, int64_t nrep, int64_t rep_offset,
+                                      const double* inits, uint64_t seed, const double* inj_normals, const double* inj_uniforms,
+                                      const double* inj_pick, const double* inj_swap, double* out_samples, int32_t* out_at,
+                                      mcmcgpu_run_info* info);
 int32_t mcmcgpu_run_serialtemp(mcmcgpu_ctx* ctx, int32_t family, int64_t d, int32_t nt, const double* hypers,
                                const mcmcgpu_sampler_cfg* samplers, int64_t steps, int64_t burnin, int64_t swap_period,
                                int64_t nrep, const double* inits, uint64_t seed, const double* inj_normals,

@@ -55,7 +55,7 @@ EXPORTS = [
     "mcmcgpu_run_execute", "mcmcgpu_run_execute_steps", "mcmcgpu_run_set_state", "mcmcgpu_run_get_state",
     "mcmcgpu_run_fetch", "mcmcgpu_run_fetch_rb", "mcmcgpu_run_fetch_diag", "mcmcgpu_run_stats",
     "mcmcgpu_run_destroy", "mcmcgpu_stats", "mcmcgpu_philox_draws", "mcmcgpu_run_seqmc", "mcmcgpu_run_serialtemp", "mcmcgpu_run_zv", "mcmcgpu_zv",
-    "mcmcgpu_run_seqmc_models",
+    "mcmcgpu_run_seqmc_models", "mcmcgpu_run_serialtemp_models",
 ]
 
 _lib = None
@@ -104,6 +104,9 @@ def lib():
                                         C.POINTER(RunInfo)]
         L.mcmcgpu_run_seqmc_models.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(SamplerCfg), C.c_int64, C.c_int64, C.c_double,
                                                C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int64), C.POINTER(RunInfo)]
+        L.mcmcgpu_run_serialtemp_models.argtypes = [vp, C.c_int32, C.POINTER(vp), C.POINTER(SamplerCfg), C.c_int64, C.c_int64, C.c_int64,
+                                                    C.c_int64, C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int32),
+                                                    C.POINTER(RunInfo)]
         L.mcmcgpu_run_serialtemp.argtypes = [vp, C.c_int32, C.c_int64, C.c_int32, dp, C.POINTER(SamplerCfg), C.c_int64, C.c_int64,
                                              C.c_int64, C.c_int64, dp, C.c_uint64, dp, dp, dp, dp, dp, C.POINTER(C.c_int32),
                                              C.POINTER(RunInfo)]
@@ -246,6 +249,22 @@ class Context(_Owned):
         check(lib().mcmcgpu_run_seqmc_models(self.h, nt, mh, sc, steps, burnin, trigger, npart, dptr(particles), seed, dptr(zn), dptr(un),
                                              dptr(ru), dptr(samples), dptr(weights), C.byref(nres), C.byref(info)))
         return dict(samples=samples, weights=weights, n_resamples=nres.value, info=info.as_dict())
+
+    def run_serialtemp_models(self, models, samplers, steps, burnin, swap_period, nrep, inits, seed=0, rep_offset=0, normals=None,
+                              uniforms=None, pick=None, swap=None):
+        """SerialTempMC over DeviceModels of this context (any family, any d); arrays as run_serialtemp.  rep_offset: global id
+        of this context's first replica (replicas shard over GPUs without communication)."""
+        inits = f64(inits)
+        nt, d = len(samplers), models[0].d
+        mh = (C.c_void_p * nt)(*[m.h for m in models])
+        sc = (SamplerCfg * nt)(*samplers)
+        S = max(steps - burnin, 0)
+        samples, at, info = np.empty((nrep, S, d)), np.empty((nrep, S), dtype=np.int32), RunInfo()
+        zn, un, pk, sw = f64(normals), f64(uniforms), f64(pick), f64(swap)
+        check(lib().mcmcgpu_run_serialtemp_models(self.h, nt, mh, sc, steps, burnin, swap_period, nrep, rep_offset, dptr(inits), seed,
+                                                  dptr(zn), dptr(un), dptr(pk), dptr(sw), dptr(samples),
+                                                  at.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(info)))
+        return dict(samples=samples, at=at, info=info.as_dict())
 
     def run_serialtemp(self, family, d, hypers, samplers, steps, burnin, swap_period, nrep, inits, seed=0, normals=None,
                        uniforms=None, pick=None, swap=None):

@@ -639,12 +639,15 @@ def _run_serialtempmc(tasks, nreplicas=1, seed=0, **draws):
     t0 = time.time()
     r = tasks[-1].runner
     m0, hypers, samplers = _population_tasks(tasks)
-    if any(t.model.family != m0.family for t in tasks) or m0.family not in ("normal_fn", "normal_dsl", "abs_normal") or m0.size > 8:
-        raise NotImplementedError("SerialTempMC on the device: closed-form families with d <= 8, every task on the same family")
     inits = np.stack([t.model.init for t in tasks])
+    closed = all(t.model.family == m0.family for t in tasks) and m0.family in ("normal_fn", "normal_dsl", "abs_normal") and m0.size <= 8
     try:
-        res = default_context().run_serialtemp(m0.family, m0.size, hypers, samplers, r.steps, r.burnin, r.swapPeriod, nreplicas,
-                                               inits, seed=seed, **draws)
+        if closed:      # one thread = one replica, the whole run in one launch
+            res = default_context().run_serialtemp(m0.family, m0.size, hypers, samplers, r.steps, r.burnin, r.swapPeriod, nreplicas,
+                                                   inits, seed=seed, **draws)
+        else:           # any models: replicas regrouped by task, each group a one-step run of the wave engine (K1)
+            res = default_context().run_serialtemp_models([t.model.device_model() for t in tasks], samplers, r.steps, r.burnin,
+                                                          r.swapPeriod, nreplicas, inits, seed=seed, **draws)
     except MCMCGPUError as e:
         if e.code == capi.E_SUPPORT:
             raise AssertionError("Initial values out of model support, try other values") from e

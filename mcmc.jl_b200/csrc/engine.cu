@@ -96,6 +96,7 @@ struct mcmcgpu_run {
   // wave state
   double *rb = nullptr, *rb_acc = nullptr;
   double* init_lt = nullptr;   // log-target at the initial point (the `reset` evaluation of the population runners)
+  const int64_t* chain_ids = nullptr;   // per-chain Philox keys (population runners that regroup replicas); not owned
   double *ram_S = nullptr, *ram_al = nullptr;
   uint8_t* ram_pending = nullptr;
   double *q = nullptr, *part = nullptr, *red = nullptr, *cur_pars = nullptr, *cur_grad = nullptr, *cur_lt = nullptr,
@@ -667,7 +668,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     W.init = R->init; W.scale = R->scale; W.inj_normals = R->inj_normals; W.inj_uniforms = R->inj_uniforms;
     W.samples = R->samples; W.grads = R->grads; W.accept = R->accept; W.logtarget = R->logtarget;
     W.eps = R->eps; W.nleaps = R->nleaps; W.final_eps = R->final_eps; W.rb = R->rb; W.rb_acc = R->rb_acc;
-    W.init_lt = R->init_lt;
+    W.init_lt = R->init_lt; W.chain_ids = R->chain_ids;
     const int kind = R->s.kind;
     const bool need_grad = (kind != MCMCGPU_RWM && kind != MCMCGPU_RAM);
     const bool is_ram = (kind == MCMCGPU_RAM);
@@ -962,7 +963,7 @@ static int stats_common(mcmcgpu_ctx* c, const double* samples, const uint8_t* ac
   for (int k = 0; k < 5; k++) if (hosts[k] || k == 0) CU(bufs.get(&outs[k], (size_t)(d * Cp), st, false));   // the mean is always formed (pass 2 reads it)
   double* bmean = nullptr;      // scratch of the stats kernels: batch-mean means, or the state of unfinished Geyer scans
   if (vtype == MCMCGPU_VAR_BM) CU(bufs.get(&bmean, (size_t)(d * Cp), st, false));
-  else if (vtype != MCMCGPU_VAR_IID) CU(bufs.get(&bmean, (size_t)(6 * d * Cp), st, false));
+  else if (vtype != MCMCGPU_VAR_IID) CU(bufs.get(&bmean, (size_t)(STATS_SCRATCH_PLANES * d * Cp + 2), st, false));
   CU(launch_stats(samples, S, d, C, Cp, vtype, maxlag, batchlen, outs[0], outs[1], outs[2], outs[3], outs[4], bmean, st));
   double* tmp = nullptr;
   CU(bufs.get(&tmp, (size_t)(C * d), st, false));
@@ -1318,6 +1319,143 @@ int32_t mcmcgpu_run_seqmc_models(mcmcgpu_ctx* c, int32_t nt, mcmcgpu_model* cons
   CU(cudaStreamSynchronize(st));
   float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   if (out_nresamples) *out_nresamples = (int64_t)nres;
+  if (info) { info->gpu_ms = ms; info->n_grad_evals = nev_total; info->n_waves = waves; info->n_launches = launches; info->eval_ms = 0; info->comm_ms = 0; }
+  return MCMCGPU_OK;
+}
+
+// SerialTempMC over arbitrary models (regression families through K1): at every iteration a replica consumes ONE task --
+// its own, or at a swap attempt the candidate task, restarted at s.pars (SerialTempMC.jl:57-71) -- so the replicas are
+// regrouped by task and each group is a one-step run of the wave engine on that task's model (particles = chains, as in
+// mcmcgpu_run_seqmc_models); per-chain Philox keys keep a replica's draws independent of its position in the group.
+// Draw conventions as mcmcgpu_run_serialtemp (key = global replica id, sampler step = column + 1, pick / swap blocks).
+int32_t mcmcgpu_run_serialtemp_models(mcmcgpu_ctx* c, int32_t nt, mcmcgpu_model* const* models, const mcmcgpu_sampler_cfg* samplers,
+                                      int64_t steps, int64_t burnin, int64_t swap_period, int64_t nrep, int64_t rep_offset,
+                                      const double* inits, uint64_t seed, const double* inj_normals, const double* inj_uniforms,
+                                      const double* inj_pick, const double* inj_swap, double* out_samples, int32_t* out_at,
+                                      mcmcgpu_run_info* info) {
+  if (!c || !models || !samplers || !inits || !out_samples) return fail(MCMCGPU_E_ARG, "NULL argument");
+  if (burnin < 0) return fail(MCMCGPU_E_ARG, "Burnin rounds should be >= 0");                   // SerialTempMC.jl:22
+  if (steps <= burnin) return fail(MCMCGPU_E_ARG, "Steps should be > to burnin");               // SerialTempMC.jl:23
+  if (nt < 2 || nt > POP_MAX_TASKS || swap_period < 1 || nrep < 1) return fail(MCMCGPU_E_ARG, "need 2..64 tasks, swapPeriod >= 1, nrep >= 1");
+  const bool inj = inj_normals != nullptr;
+  if (inj != (inj_uniforms != nullptr) || inj != (inj_pick != nullptr) || inj != (inj_swap != nullptr))
+    return fail(MCMCGPU_E_ARG, "inject all four draw arrays or none");
+  for (int t = 0; t < nt; t++) {
+    if (!models[t] || models[t]->ctx != c) return fail(MCMCGPU_E_ARG, "every model must belong to this context");
+    if (models[t]->d != models[0]->d) return fail(MCMCGPU_E_ARG, "Models do not have the same parameter vector size");   // SerialTempMC.jl:39
+    const mcmcgpu_sampler_cfg& sc = samplers[t];
+    if (sc.tuner_on || (sc.kind != MCMCGPU_RWM && sc.kind != MCMCGPU_MALA && sc.kind != MCMCGPU_HMC))
+      return fail(MCMCGPU_E_ARG, "population runners take RWM, MALA or HMC tasks without tuner");
+  }
+  const int64_t d = models[0]->d;
+  for (int t = 0; t < nt; t++) {          // every task is started from its model.init (:44): the samplers' support assertion
+    double lt = 0.0;
+    int rc0 = mcmcgpu_logtarget_grad(models[t], inits + t * d, 1, &lt, nullptr);
+    if (rc0 != MCMCGPU_OK) return rc0;
+    if (!std::isfinite(lt)) return fail(MCMCGPU_E_SUPPORT, "Initial values out of model support, try other values");
+  }
+  CU(use_ctx(c));
+  cudaStream_t st = c->stream;
+  DevBufs B;
+  const int64_t Rp = round_up(nrep, K1_CHAINS), S = steps - burnin;
+  TempMArgs A;
+  A.nt = nt; A.d = (int32_t)d; A.nrep = nrep; A.Rp = Rp; A.rep_offset = rep_offset; A.steps = steps; A.burnin = burnin; A.seed = seed;
+  CU(B.get(&A.state, (size_t)(d * Rp), st)); CU(B.get(&A.pars, (size_t)(d * Rp), st)); CU(B.get(&A.ppars, (size_t)(d * Rp), st));
+  CU(B.get(&A.res_pp, (size_t)(d * Rp), st)); CU(B.get(&A.res_lt0, (size_t)Rp, st)); CU(B.get(&A.logtarget, (size_t)Rp, st));
+  CU(B.get(&A.at, (size_t)Rp, st)); CU(B.get(&A.sel, (size_t)Rp, st));
+  CU(B.get(&A.samples, (size_t)(nrep * S * d), st, false));
+  A.at_out = nullptr;
+  if (out_at) CU(B.get(&A.at_out, (size_t)(nrep * S), st));
+  A.inj_pick = A.inj_swap = nullptr;
+  if (inj) {
+    double *p = nullptr, *w = nullptr;
+    CU(B.up(&p, inj_pick, (size_t)(nrep * (steps + 1)), st)); CU(B.up(&w, inj_swap, (size_t)(nrep * (steps + 1)), st));
+    A.inj_pick = p; A.inj_swap = w;
+  }
+  int64_t launches = 0, nev_total = 0, waves = 0;
+  const int64_t time_eval_saved = c->time_eval;
+  c->time_eval = 0;
+  struct Restore { mcmcgpu_ctx* c; int64_t v; ~Restore() { c->time_eval = v; } } restore{c, time_eval_saved};
+  std::vector<double> zst, ust;
+  // one group: the replicas idx consume task t with the draws of column col, started at A.pars; results -> A.res_pp / A.res_lt0
+  auto group = [&](int t, const std::vector<int64_t>& idx, int64_t col) -> int {
+    const int64_t n = (int64_t)idx.size(), Cp = round_up(n, K1_CHAINS);
+    DevBufs G;
+    int64_t *idx_dev = nullptr, *ids = nullptr;
+    double* start = nullptr;
+    CU(G.up(&idx_dev, idx.data(), (size_t)n, st));
+    CU(G.get(&start, (size_t)(d * Cp), st, false)); CU(G.get(&ids, (size_t)Cp, st, false));
+    CU(launch_temp_gather(A, idx_dev, n, Cp, start, ids, st));
+    mcmcgpu_runner_cfg rc;
+    memset(&rc, 0, sizeof(rc));
+    rc.step = 1; rc.nchains = n; rc.chain_offset = 0; rc.seed = seed; rc.init_per_chain = 1; rc.store_logtarget = 1; rc.engine = MCMCGPU_ENGINE_WAVE;
+    const double *zn = nullptr, *un = nullptr;
+    if (inj) {
+      rc.first = 1; rc.last = 1;
+      zst.assign((size_t)(n * 2 * d), 0.0); ust.assign((size_t)(n * 2), 0.0);
+      for (int64_t k = 0; k < n; k++) {
+        const int64_t r = idx[(size_t)k];
+        memcpy(&zst[(size_t)((k * 2 + 1) * d)], inj_normals + (r * (steps + 2) + col) * d, sizeof(double) * (size_t)d);
+        ust[(size_t)(k * 2 + 1)] = inj_uniforms[r * (steps + 2) + col];
+      }
+      zn = zst.data(); un = ust.data();
+    } else {
+      rc.first = col + 1; rc.last = col + 1;
+    }
+    mcmcgpu_run* R = nullptr;
+    int rcode = run_create_impl(models[t], &samplers[t], &rc, nullptr, start, nullptr, zn, un, &R);
+    if (rcode != MCMCGPU_OK) return rcode;
+    struct RunGuard { mcmcgpu_run* r; ~RunGuard() { mcmcgpu_run_destroy(r); } } guard{R};
+    if (!inj) R->step0 = col;
+    R->chain_ids = ids;
+    mcmcgpu_run_info ri;
+    rcode = execute_impl(R, -1, &ri);
+    if (rcode != MCMCGPU_OK) return rcode;
+    nev_total += ri.n_grad_evals; launches += ri.n_launches + 2; waves += ri.n_waves;
+    CU(launch_temp_scatter(A, idx_dev, n, Cp, R->samples, R->init_lt, st));
+    CU(cudaStreamSynchronize(st));
+    return MCMCGPU_OK;
+  };
+  Events events;
+  cudaEvent_t e0, e1;
+  CU(events.make(&e0)); CU(events.make(&e1));
+  CU(cudaEventRecord(e0, st));
+  std::vector<int64_t> all((size_t)nrep);
+  for (int64_t r = 0; r < nrep; r++) all[(size_t)r] = r;
+  const size_t plane = sizeof(double) * (size_t)(d * Rp);
+  // :44 the first consume of task 1 from its model.init (column 0), :51 its second step from its own state (column 1)
+  for (int64_t j = 0; j < d; j++) CU(launch_fill(A.pars + j * Rp, inits[j], Rp, st));
+  int rcode = group(0, all, 0);
+  if (rcode != MCMCGPU_OK) return rcode;
+  CU(cudaMemcpyAsync(A.state, A.res_pp, plane, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(A.pars, A.state, plane, cudaMemcpyDeviceToDevice, st));
+  rcode = group(0, all, 1);
+  if (rcode != MCMCGPU_OK) return rcode;
+  CU(cudaMemcpyAsync(A.ppars, A.res_pp, plane, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(A.state, A.res_pp, plane, cudaMemcpyDeviceToDevice, st));
+  CU(cudaMemcpyAsync(A.logtarget, A.res_lt0, sizeof(double) * (size_t)Rp, cudaMemcpyDeviceToDevice, st));   // s.logtarget (:53)
+  std::vector<int32_t> sel((size_t)nrep);
+  std::vector<std::vector<int64_t>> groups((size_t)nt);
+  for (int64_t i = 1; i <= steps; i++) {
+    const bool swap_step = (i % swap_period) == 0;                                              // :57
+    CU(launch_temp_plan(A, i, swap_step, st));
+    CU(cudaMemcpyAsync(sel.data(), A.sel, sizeof(int32_t) * (size_t)nrep, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (auto& g : groups) g.clear();
+    for (int64_t r = 0; r < nrep; r++) groups[(size_t)sel[(size_t)r]].push_back(r);
+    for (int t = 0; t < nt; t++) {
+      if (groups[(size_t)t].empty()) continue;
+      rcode = group(t, groups[(size_t)t], i + 1);
+      if (rcode != MCMCGPU_OK) return rcode;
+    }
+    CU(launch_temp_update(A, i, swap_step, st));
+    launches += 2;
+  }
+  CU(cudaEventRecord(e1, st));
+  CU(cudaMemcpyAsync(out_samples, A.samples, sizeof(double) * (size_t)(nrep * S * d), cudaMemcpyDeviceToHost, st));
+  if (out_at) CU(cudaMemcpyAsync(out_at, A.at_out, sizeof(int32_t) * (size_t)(nrep * S), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
   if (info) { info->gpu_ms = ms; info->n_grad_evals = nev_total; info->n_waves = waves; info->n_launches = launches; info->eval_ms = 0; info->comm_ms = 0; }
   return MCMCGPU_OK;
 }

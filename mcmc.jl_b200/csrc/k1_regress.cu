@@ -667,12 +667,14 @@ __global__ void k1_pack_kernel(double* tiles, const double* X, const double* y, 
   }
 }
 
-// supported feature-block counts: every DK up to 13 (d <= 104, 128 registers, two CTAs per SM), then 16, 20, 25
-// (d <= 200, one CTA per SM with up to 255 registers for the 2*DK gradient accumulators per thread)
+// supported feature-block counts: every DK up to 13 (d <= 104, 128 registers, two CTAs per SM), then 14, 15, 16, 20, 25
+// (d <= 200, one CTA per SM with up to 255 registers for the 2*DK gradient accumulators per thread: two CTAs of DK >= 14
+// would need 2 x 119 KB of shared memory).  14 and 15 exist so that 104 < d <= 120 does not execute the dead phase-2 DMMAs
+// of DK = 16 (d = 105: 14 % of them).
 static int k1_round_dk(int64_t d) {
   int dk = (int)((d + 7) / 8);
   if (dk <= K1_MAX_DK_2CTA) return dk;
-  if (dk <= 16) return 16;
+  if (dk <= 16) return dk;
   if (dk <= 20) return 20;
   if (dk <= 25) return 25;
   return -1;
@@ -765,6 +767,8 @@ static cudaError_t launch_f(const K1Args& a, cudaStream_t st) {
     case 11: return launch_fd<FAM, 11>(a, st);
     case 12: return launch_fd<FAM, 12>(a, st);
     case 13: return launch_fd<FAM, 13>(a, st);
+    case 14: return launch_fd<FAM, 14>(a, st);
+    case 15: return launch_fd<FAM, 15>(a, st);
     case 16: return launch_fd<FAM, 16>(a, st);
     case 20: return launch_fd<FAM, 20>(a, st);
     case 25: return launch_fd<FAM, 25>(a, st);

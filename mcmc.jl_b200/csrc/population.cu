@@ -260,15 +260,17 @@ __global__ void __launch_bounds__(128) serialtemp_kernel(const TempArgs A) {
 #pragma unroll
       for (int b = 0; 2 * b < D; b++) {
         double z0 = 0.0, z1 = 0.0;
-        if (2 * b < d) philox_normal_pair(A.seed, (uint64_t)c, (uint32_t)col, (uint32_t)b, z0, z1);
+        if (2 * b < d) philox_normal_pair(A.seed, (uint64_t)c, (uint32_t)(col + 1), (uint32_t)b, z0, z1);   // sampler step = column + 1
         z[2 * b] = z0;
         if (2 * b + 1 < D) z[2 * b + 1] = (2 * b + 1 < d) ? z1 : 0.0;
       }
     }
   };
-  auto uni = [&](const double* inj, int64_t stride, int64_t col, uint32_t block) -> double {
+  // sampler uniforms sit at Philox step column + 1 (the step index of a one-step run, as mcmcgpu_run_serialtemp_models
+  // draws them); the pick / swap uniforms of iteration i at step i in their own blocks
+  auto uni = [&](const double* inj, int64_t stride, int64_t col, uint32_t block, int shift = 0) -> double {
     if (inj) return inj[c * stride + col];
-    u4 o = philox4x32_10((uint32_t)c, (uint32_t)((uint64_t)c >> 32), (uint32_t)col, block, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+    u4 o = philox4x32_10((uint32_t)c, (uint32_t)((uint64_t)c >> 32), (uint32_t)(col + shift), block, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
     return u01(o.x, o.y);
   };
   // every task is started from its model.init (:44); a non-finite start is the samplers' assertion
@@ -287,17 +289,17 @@ __global__ void __launch_bounds__(128) serialtemp_kernel(const TempArgs A) {
   int at = 0;
   double plt, lt0, logtarget;
   normals(0, z);
-  reset_and_step<FAM, D>(T, 0, pars, z, uni(A.inj_uniforms, A.steps + 2, 0, 0xFFFFFFFFu), state, plt, lt0, nev);   // :44
+  reset_and_step<FAM, D>(T, 0, pars, z, uni(A.inj_uniforms, A.steps + 2, 0, 0xFFFFFFFFu, 1), state, plt, lt0, nev);   // :44
 #pragma unroll
   for (int j = 0; j < D; j++) pars[j] = state[j];
   normals(1, z);
-  reset_and_step<FAM, D>(T, 0, pars, z, uni(A.inj_uniforms, A.steps + 2, 1, 0xFFFFFFFFu), ppars, plt, lt0, nev);   // :51
+  reset_and_step<FAM, D>(T, 0, pars, z, uni(A.inj_uniforms, A.steps + 2, 1, 0xFFFFFFFFu, 1), ppars, plt, lt0, nev);   // :51
 #pragma unroll
   for (int j = 0; j < D; j++) state[j] = ppars[j];
   logtarget = lt0;
   for (int64_t i = 1; i <= A.steps; i++) {
     normals(i + 1, z);
-    const double u = uni(A.inj_uniforms, A.steps + 2, i + 1, 0xFFFFFFFFu);
+    const double u = uni(A.inj_uniforms, A.steps + 2, i + 1, 0xFFFFFFFFu, 1);
     if (i % A.swap_period == 0) {                                                 // :57
       int at2 = (int)floor(uni(A.inj_pick, A.steps + 1, i, 0xFFFFFFFDu) * (double)(nt - 1));   // :59
       if (at2 > nt - 2) at2 = nt - 2;
@@ -344,6 +346,88 @@ cudaError_t launch_serialtemp(const TempArgs& A, cudaStream_t st) {
     case MCMCGPU_FAM_ABS_NORMAL: return temp_d<MCMCGPU_FAM_ABS_NORMAL>(A, st);
   }
   return cudaErrorInvalidValue;
+}
+
+// ---- SerialTempMC over arbitrary models: replicas regrouped by the task they consume at this step ----------------------
+// (the mutation itself is a one-step run of the wave engine per task, engine.cu: mcmcgpu_run_serialtemp_models)
+__device__ __forceinline__ double temp_uniform(const TempMArgs& A, const double* inj, int64_t stride, int64_t r, int64_t col, uint32_t block) {
+  if (inj) return inj[r * stride + col];
+  const uint64_t g = (uint64_t)(A.rep_offset + r);
+  u4 o = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)col, block, (uint32_t)A.seed, (uint32_t)(A.seed >> 32));
+  return u01(o.x, o.y);
+}
+
+__global__ void temp_plan_kernel(const TempMArgs A, int64_t i, int swap_step) {
+  // SerialTempMC.jl:57-63 / :68: which task this replica consumes at iteration i, started at s.pars
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.nrep) return;
+  const int at = A.at[r];
+  if (swap_step) {
+    int at2 = (int)floor(temp_uniform(A, A.inj_pick, A.steps + 1, r, i, 0xFFFFFFFDu) * (double)(A.nt - 1));   // :59
+    if (at2 > A.nt - 2) at2 = A.nt - 2;
+    if (at2 >= at) at2 += 1;                                                                                  // :60
+    A.sel[r] = at2;                      // reset to s.pars (unchanged), consume                               // :62-63
+  } else {
+    for (int j = 0; j < A.d; j++) A.pars[j * A.Rp + r] = A.state[j * A.Rp + r];
+    A.sel[r] = at;
+  }
+}
+
+__global__ void temp_gather_kernel(const TempMArgs A, const int64_t* __restrict__ idx, int64_t n, int64_t Cp, double* __restrict__ start,
+                                   int64_t* __restrict__ chain_ids) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Cp) return;
+  const int64_t r = (k < n) ? idx[k] : -1;
+  for (int j = 0; j < A.d; j++) start[j * Cp + k] = (r >= 0) ? A.pars[j * A.Rp + r] : 0.0;
+  chain_ids[k] = (r >= 0) ? A.rep_offset + r : 0;
+}
+
+__global__ void temp_scatter_kernel(const TempMArgs A, const int64_t* __restrict__ idx, int64_t n, int64_t Cp, const double* __restrict__ ppars,
+                                    const double* __restrict__ lt0) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int64_t r = idx[k];
+  for (int j = 0; j < A.d; j++) A.res_pp[j * A.Rp + r] = ppars[j * Cp + k];
+  A.res_lt0[r] = lt0[k];
+}
+
+__global__ void temp_update_kernel(const TempMArgs A, int64_t i, int swap_step) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.nrep) return;
+  const int d = A.d;
+  if (swap_step) {
+    const double lt02 = A.res_lt0[r];
+    if (temp_uniform(A, A.inj_swap, A.steps + 1, r, i, 0xFFFFFFFCu) < exp(A.logtarget[r] - lt02 + 0.0 - 0.0)) {   // :64; logW stays 0 (:48,:70)
+      A.at[r] = A.sel[r];                                                                                         // :65
+      for (int j = 0; j < d; j++) { const double v = A.res_pp[j * A.Rp + r]; A.ppars[j * A.Rp + r] = v; A.state[j * A.Rp + r] = v; }
+      A.logtarget[r] = lt02;
+    }
+  } else {                                                                                                        // :68-71
+    for (int j = 0; j < d; j++) { const double v = A.res_pp[j * A.Rp + r]; A.ppars[j * A.Rp + r] = v; A.state[j * A.Rp + r] = v; }
+    A.logtarget[r] = A.res_lt0[r];
+  }
+  if (i > A.burnin) {                                                                                             // :73-76
+    const int64_t S = A.steps - A.burnin, k = i - A.burnin - 1;
+    for (int j = 0; j < d; j++) A.samples[(r * S + k) * d + j] = A.ppars[j * A.Rp + r];
+    if (A.at_out) A.at_out[r * S + k] = A.at[r];
+  }
+}
+
+cudaError_t launch_temp_plan(const TempMArgs& A, int64_t i, bool swap_step, cudaStream_t st) {
+  temp_plan_kernel<<<(unsigned)((A.nrep + 127) / 128), 128, 0, st>>>(A, i, swap_step ? 1 : 0);
+  return cudaGetLastError();
+}
+cudaError_t launch_temp_gather(const TempMArgs& A, const int64_t* idx, int64_t n, int64_t Cp, double* start, int64_t* chain_ids, cudaStream_t st) {
+  temp_gather_kernel<<<(unsigned)((Cp + 127) / 128), 128, 0, st>>>(A, idx, n, Cp, start, chain_ids);
+  return cudaGetLastError();
+}
+cudaError_t launch_temp_scatter(const TempMArgs& A, const int64_t* idx, int64_t n, int64_t Cp, const double* ppars, const double* lt0, cudaStream_t st) {
+  temp_scatter_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(A, idx, n, Cp, ppars, lt0);
+  return cudaGetLastError();
+}
+cudaError_t launch_temp_update(const TempMArgs& A, int64_t i, bool swap_step, cudaStream_t st) {
+  temp_update_kernel<<<(unsigned)((A.nrep + 127) / 128), 128, 0, st>>>(A, i, swap_step ? 1 : 0);
+  return cudaGetLastError();
 }
 
 bool pop_supported(int family, int64_t d) {

@@ -45,5 +45,24 @@ struct TempArgs {
   unsigned long long* nevals;
 };
 cudaError_t launch_serialtemp(const TempArgs& A, cudaStream_t st);
+
+// SerialTempMC over arbitrary models: per-replica state on the device, replica-minor ([d][Rp])
+struct TempMArgs {
+  int32_t nt, d;
+  int64_t nrep, Rp, rep_offset;      // replicas of this context, pitch, global id of the first one (Philox key)
+  int64_t steps, burnin;
+  uint64_t seed;
+  double *state, *pars, *ppars;      // [d][Rp]: sampler state, s.pars, s.ppars (SerialTempMC.jl:51-71)
+  double *logtarget;                 // [Rp] s.logtarget
+  int32_t *at, *sel;                 // [Rp] current task; task consumed at this step
+  double *res_pp, *res_lt0;          // [d][Rp], [Rp]: the one-step results scattered back by replica
+  const double *inj_pick, *inj_swap; // host layouts (nrep x (steps+1)) on the device, or null
+  double* samples;                   // d x S x nrep (host layout)
+  int32_t* at_out;                   // S x nrep or null
+};
+cudaError_t launch_temp_plan(const TempMArgs& A, int64_t i, bool swap_step, cudaStream_t st);
+cudaError_t launch_temp_gather(const TempMArgs& A, const int64_t* idx, int64_t n, int64_t Cp, double* start, int64_t* chain_ids, cudaStream_t st);
+cudaError_t launch_temp_scatter(const TempMArgs& A, const int64_t* idx, int64_t n, int64_t Cp, const double* ppars, const double* lt0, cudaStream_t st);
+cudaError_t launch_temp_update(const TempMArgs& A, int64_t i, bool swap_step, cudaStream_t st);
 bool pop_supported(int family, int64_t d);
 }  // namespace mg

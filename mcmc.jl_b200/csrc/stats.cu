@@ -18,7 +18,7 @@
 //   pass 2  stats_var_kernel    the centred sum of squares (== lag 0) together with the first NP_WIN Geyer pair sums
 //                               (16 lags) from one register ring (Geyer's scan usually stops inside it: a noise-level
 //                               pair sum is negative with probability 1/2), or the batch-means variance.
-//   Only a series whose pair sums are all still positive goes on, NP_WIN pairs per further pass (stats_more_kernel).
+//   Only a series whose pair sums are all still positive goes on, NP_WIN pairs per further pass (stats_more_warp_kernel / stats_more_lane_kernel).
 // Round 1 made four passes for IMSE (mean, variance, and a 16-lag window pass re-reading x[t] and x[t + lag]) at 120
 // registers per thread (16 warps per SM) and shifted the window through registers (~30 moves per element: issue-bound).
 // The rings below are rotated by unrolling (static register names, no moves), the next chunk's loads are issued before
@@ -87,30 +87,37 @@ __global__ void __launch_bounds__(ST_THREADS) stats_mean_kernel(const double* __
 // stream that trails the first by lag0 + 2 NP elements (L1 / L2 hits for the first window).  FIRST also accumulates
 // a0 = sum v^2 as mul + add: the reference's variance and gamma_0, bit for bit.
 template <int NP, bool FIRST>
-__device__ __forceinline__ void acov_pairs(const double* __restrict__ x, int64_t st, int64_t S, double mu, int64_t lag0, double& a0,
-                                           double (&G)[NP]) {
+__device__ __forceinline__ void acov_pairs(const double* __restrict__ x, int64_t st, int64_t S, double mu, int64_t lag0, int64_t t_begin,
+                                           int64_t t_end, double& a0, double (&G)[NP]) {
+  // sums over t in [t_begin, t_end) (the whole series: [0, S - lag0))
   constexpr int R = 2 * NP;
 #pragma unroll
   for (int j = 0; j < NP; j++) G[j] = 0.0;
   a0 = 0.0;
   double sr[R], nx[R];
   auto cent = [&](int64_t idx) -> double { return (idx < S) ? x[idx * st] - mu : 0.0; };   // beyond the end: exact zeros
-  double vcur = cent(lag0);                    // v at the position whose s is formed next
+  double vcur = cent(t_begin + lag0);          // v at the position whose s is formed next
 #pragma unroll
-  for (int u = 0; u < R; u++) { const double vn = cent(lag0 + u + 1); sr[u] = vcur + vn; vcur = vn; }
-  const int64_t T = S - lag0;                  // t runs over 0 .. T-1
-  for (int64_t t0 = 0; t0 < T; t0 += R) {
-    // the refill values of this chunk are requested before its arithmetic: position t0 + lag0 + R + u + 1 completes the s
-    // that replaces ring entry u
+  for (int u = 0; u < R; u++) { const double vn = cent(t_begin + lag0 + u + 1); sr[u] = vcur + vn; vcur = vn; }
+  // software pipeline: the ring refill values of chunk k + 1 (the DRAM stream) are requested at the top of chunk k and
+  // consumed one iteration later, so a full chunk of arithmetic separates each of these loads from its use (left to itself
+  // the compiler sinks every load next to its use: 2 loads in flight per thread, 1.7 TB/s).  The multipliers v_t were read
+  // 2 NP + lag0 elements earlier as ring values: L1 / L2 hits, loaded in place.
 #pragma unroll
-    for (int u = 0; u < R; u++) nx[u] = cent(t0 + lag0 + R + u + 1);
+  for (int u = 0; u < R; u++) nx[u] = cent(t_begin + lag0 + R + u + 1);
+  for (int64_t t0 = t_begin; t0 < t_end; t0 += R) {
+    double cn[R];
+#pragma unroll
+    for (int u = 0; u < R; u++) cn[u] = nx[u];
+#pragma unroll
+    for (int u = 0; u < R; u++) nx[u] = cent(t0 + R + lag0 + R + u + 1);
 #pragma unroll
     for (int u = 0; u < R; u++) {
-      const double v = (t0 + u < T) ? x[(t0 + u) * st] - mu : 0.0;
+      const double v = (t0 + u < t_end) ? x[(t0 + u) * st] - mu : 0.0;
       if (FIRST) a0 += v * v;                                       // == sum (x - mu)^2 of Base.var, same roundings
 #pragma unroll
       for (int j = 0; j < NP; j++) G[j] = fma(v, sr[(u + 2 * j) % R], G[j]);
-      sr[u] = vcur + nx[u]; vcur = nx[u];
+      sr[u] = vcur + cn[u]; vcur = cn[u];
     }
   }
 }
@@ -133,11 +140,12 @@ __device__ __forceinline__ bool geyer_window(const double (&G)[NP], double n, in
 
 // ---- pass 2 (and the rare further passes): variance / batch means / Geyer ----
 template <int VT>
-__global__ void __launch_bounds__(ST_THREADS) stats_var_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C,
+__global__ void __launch_bounds__(ST_THREADS, 3) stats_var_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C,
                                                                 int64_t Cp, int64_t maxlag, int64_t batchlen,
                                                                 const double* __restrict__ mean_i, const double* __restrict__ bmean_i,
                                                                 double* viid_o, double* var_o, double* ess_o, double* act_o,
-                                                                double* __restrict__ more) {
+                                                                double* __restrict__ more, int32_t* __restrict__ more_list,
+                                                                unsigned int* __restrict__ more_count) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t j = blockIdx.y;
   if (c >= C) return;
@@ -180,15 +188,16 @@ __global__ void __launch_bounds__(ST_THREADS) stats_var_kernel(const double* __r
     bool stop;
     {
       double G[NP_WIN];
-      acov_pairs<NP_WIN, true>(x, st, S, mu, 0, ss, G);
+      acov_pairs<NP_WIN, true>(x, st, S, mu, 0, 0, S, ss, G);
       acv0 = ss / n;                                                // gamma_0 (var.jl:53)
       stop = (k < 0) || geyer_window<NP_WIN>(G, n, k, monotone, jj, gsum, gprev);
     }
-    // a series whose pair sums are still positive goes on in stats_more_kernel (its windows need two load streams and
+    // a series whose pair sums are still positive goes on in the stats_more_* kernels (their windows need two load streams and
     // twice the registers: kept out of this kernel so that the common case runs at full occupancy)
     const int64_t plane = d * Cp;
     more[o] = stop ? 0.0 : 1.0;
     if (!stop) {
+      more_list[atomicAdd(more_count, 1u)] = (int32_t)o;            // compact list of the unfinished series
       more[plane + o] = acv0; more[2 * plane + o] = gsum; more[3 * plane + o] = gprev; more[4 * plane + o] = (double)jj;
       more[5 * plane + o] = (ss / (double)(S - 1)) / n;
       return;
@@ -203,8 +212,56 @@ __global__ void __launch_bounds__(ST_THREADS) stats_var_kernel(const double* __r
   if (act_o) act_o[o] = v / viid;                   // ess.jl:18
 }
 
-// the windows beyond the first NP_WIN pairs, for the series stats_var_kernel left unfinished (slowly mixing chains)
-__global__ void __launch_bounds__(ST_THREADS) stats_more_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C, int64_t Cp,
+// The windows beyond the first NP_WIN pairs, for the series stats_var_kernel left unfinished.
+// Few unfinished series (well-mixing chains: ~2 % survive 8 noise-level pairs): ONE WARP PER SERIES from the compact list, the
+// lanes split the time axis and the partial pair sums are combined by a butterfly (every lane holds the same sum and takes
+// the same decision).  A thread per series would leave the other 31 lanes of almost every warp idle for whole passes.
+__global__ void __launch_bounds__(ST_THREADS) stats_more_warp_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t Cp,
+                                                                      int64_t maxlag, int monotone, const double* __restrict__ mean_i,
+                                                                      const double* __restrict__ more, const int32_t* __restrict__ more_list,
+                                                                      const unsigned int* __restrict__ more_count, double* viid_o,
+                                                                      double* var_o, double* ess_o, double* act_o) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t plane = d * Cp, st = d * Cp, k = (maxlag - 1) / 2;
+  const double n = (double)S;
+  const unsigned int cnt = *more_count;
+  for (int64_t e = warp; e < (int64_t)cnt; e += nwarps) {
+    const int64_t o = more_list[e];
+    const double* x = samples + o;                 // o = j * Cp + c
+    const double mu = mean_i[o];
+    double acv0 = more[plane + o], gsum = more[2 * plane + o], gprev = more[3 * plane + o];
+    int64_t jj = (int64_t)more[4 * plane + o];
+    const double viid = more[5 * plane + o];
+    bool stop = false;
+    for (int64_t lag0 = 2 * NP_WIN; !stop; lag0 += 2 * NP_WIN) {
+      const int64_t T = S - lag0, seg = (T > 0) ? (T + 31) / 32 : 0;
+      const int64_t tb = lane * seg, te = (tb + seg < T) ? tb + seg : T;
+      double G[NP_WIN], unused;
+      if (tb < te) acov_pairs<NP_WIN, false>(x, st, S, mu, lag0, tb, te, unused, G);
+      else {
+#pragma unroll
+        for (int j = 0; j < NP_WIN; j++) G[j] = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < NP_WIN; j++) {
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) G[j] += __shfl_xor_sync(0xffffffffu, G[j], w);
+      }
+      stop = geyer_window<NP_WIN>(G, n, k, monotone != 0, jj, gsum, gprev);
+    }
+    if (lane == 0) {
+      const double v = (-acv0 + 2.0 * gsum) / n;        // var.jl:74
+      if (viid_o) viid_o[o] = viid;
+      if (var_o) var_o[o] = v;
+      if (ess_o) ess_o[o] = n * viid / v;               // ess.jl:9
+      if (act_o) act_o[o] = v / viid;                   // ess.jl:18
+    }
+  }
+}
+
+// Many unfinished series (slowly mixing chains): one thread per series, coalesced across the chains of a warp
+__global__ void __launch_bounds__(ST_THREADS) stats_more_lane_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t C, int64_t Cp,
                                                                  int64_t maxlag, int monotone, const double* __restrict__ mean_i,
                                                                  const double* __restrict__ more, double* viid_o, double* var_o,
                                                                  double* ess_o, double* act_o) {
@@ -223,7 +280,7 @@ __global__ void __launch_bounds__(ST_THREADS) stats_more_kernel(const double* __
   bool stop = false;
   for (int64_t lag0 = 2 * NP_WIN; !stop; lag0 += 2 * NP_WIN) {
     double G[NP_WIN], unused;
-    acov_pairs<NP_WIN, false>(x, st, S, mu, lag0, unused, G);
+    acov_pairs<NP_WIN, false>(x, st, S, mu, lag0, 0, S - lag0, unused, G);
     stop = geyer_window<NP_WIN>(G, n, k, monotone != 0, jj, gsum, gprev);
   }
   const double v = (-acv0 + 2.0 * gsum) / n;        // var.jl:74
@@ -236,8 +293,17 @@ __global__ void __launch_bounds__(ST_THREADS) stats_more_kernel(const double* __
 cudaError_t launch_stats(const double* samples, int64_t S, int64_t d, int64_t C, int64_t Cp, int vtype, int64_t maxlag,
                          int64_t batchlen, double* mean, double* var_iid, double* var, double* ess, double* actime,
                          double* scratch, cudaStream_t st) {
-  // `mean` must be a device buffer [d][Cp] (pass 2 reads it); scratch: [d][Cp] for batch means, [6][d][Cp] for IMSE / IPSE
+  // `mean` must be a device buffer [d][Cp] (pass 2 reads it); scratch: [d][Cp] doubles for batch means,
+  // STATS_SCRATCH_PLANES * d * Cp + 2 for IMSE / IPSE (6 planes of scan state, the list of unfinished series, its length)
   double* bmean_scratch = scratch;
+  const int64_t plane = d * Cp;
+  int32_t* more_list = scratch ? reinterpret_cast<int32_t*>(scratch + 6 * plane) : nullptr;
+  unsigned int* more_count = scratch ? reinterpret_cast<unsigned int*>(scratch + 7 * plane) : nullptr;
+  const bool geyer = (vtype == MCMCGPU_VAR_IMSE || vtype == MCMCGPU_VAR_IPSE);
+  if (geyer) {
+    cudaError_t e0 = cudaMemsetAsync(more_count, 0, sizeof(unsigned int), st);
+    if (e0 != cudaSuccess) return e0;
+  }
   dim3 grid((unsigned)((C + ST_THREADS - 1) / ST_THREADS), (unsigned)d);
   const bool bm = (vtype == MCMCGPU_VAR_BM);
   stats_mean_kernel<<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, batchlen, mean, bm ? bmean_scratch : nullptr);
@@ -245,16 +311,27 @@ cudaError_t launch_stats(const double* samples, int64_t S, int64_t d, int64_t C,
   if (e != cudaSuccess) return e;
   if (!var_iid && !var && !ess && !actime) return cudaSuccess;
   switch (vtype) {
-    case MCMCGPU_VAR_IID: stats_var_kernel<MCMCGPU_VAR_IID><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, nullptr); break;
-    case MCMCGPU_VAR_BM: stats_var_kernel<MCMCGPU_VAR_BM><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, bmean_scratch, var_iid, var, ess, actime, nullptr); break;
-    case MCMCGPU_VAR_IMSE: stats_var_kernel<MCMCGPU_VAR_IMSE><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, scratch); break;
-    case MCMCGPU_VAR_IPSE: stats_var_kernel<MCMCGPU_VAR_IPSE><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, scratch); break;
+    case MCMCGPU_VAR_IID: stats_var_kernel<MCMCGPU_VAR_IID><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, nullptr, nullptr, nullptr); break;
+    case MCMCGPU_VAR_BM: stats_var_kernel<MCMCGPU_VAR_BM><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, bmean_scratch, var_iid, var, ess, actime, nullptr, nullptr, nullptr); break;
+    case MCMCGPU_VAR_IMSE: stats_var_kernel<MCMCGPU_VAR_IMSE><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, scratch, more_list, more_count); break;
+    case MCMCGPU_VAR_IPSE: stats_var_kernel<MCMCGPU_VAR_IPSE><<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, batchlen, mean, nullptr, var_iid, var, ess, actime, scratch, more_list, more_count); break;
     default: return cudaErrorInvalidValue;
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (vtype == MCMCGPU_VAR_IMSE || vtype == MCMCGPU_VAR_IPSE) {
-    stats_more_kernel<<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, vtype == MCMCGPU_VAR_IMSE ? 1 : 0, mean, scratch, var_iid, var, ess, actime);
+  if (geyer) {
+    unsigned int cnt = 0;
+    e = cudaMemcpyAsync(&cnt, more_count, sizeof(cnt), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    const int mono = vtype == MCMCGPU_VAR_IMSE ? 1 : 0;
+    if (cnt == 0) return cudaSuccess;
+    if ((double)cnt > 0.25 * (double)(C * d)) {
+      stats_more_lane_kernel<<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, mono, mean, scratch, var_iid, var, ess, actime);
+    } else {
+      const unsigned blocks = (unsigned)((cnt + 3) / 4 < 148 * 8 ? (cnt + 3) / 4 : 148 * 8);     // 4 warps per block
+      stats_more_warp_kernel<<<blocks, ST_THREADS, 0, st>>>(samples, S, d, Cp, maxlag, mono, mean, scratch, more_list, more_count, var_iid, var, ess, actime);
+    }
     e = cudaGetLastError();
   }
   return e;

@@ -3,7 +3,9 @@
 namespace mg {
 // K3: src/stats over stored draws, one thread per (chain, parameter) series.
 // samples: [S][d][Cp] chain-minor.  Outputs [d][Cp] (any may be null).
-// `mean` is required (the second pass reads it); scratch: [d][Cp] doubles for MCMCGPU_VAR_BM, [6][d][Cp] for IMSE / IPSE.
+// `mean` is required (the second pass reads it); scratch: d * Cp doubles for MCMCGPU_VAR_BM, STATS_SCRATCH_PLANES * d * Cp + 2
+// for IMSE / IPSE.
+constexpr int STATS_SCRATCH_PLANES = 7;
 cudaError_t launch_stats(const double* samples, int64_t S, int64_t d, int64_t C, int64_t Cp, int vtype, int64_t maxlag,
                          int64_t batchlen, double* mean, double* var_iid, double* var, double* ess, double* actime,
                          double* scratch, cudaStream_t st);

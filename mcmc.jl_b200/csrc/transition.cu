@@ -108,7 +108,7 @@ __device__ int transition_chain(const WaveArgs& W, const int64_t c, const bool i
     atomicAdd(W.remaining, 1);
   } else if (ph == PH_PAUSE) return 0;
   const int64_t d = M.d, Cp = R.Cp;
-  const uint64_t gchain = (uint64_t)(R.chain_offset + c);
+  const uint64_t gchain = W.chain_ids ? (uint64_t)W.chain_ids[c] : (uint64_t)(R.chain_offset + c);
   const int64_t burnin = R.first - 1;
   const int kind = S.kind;
   const bool hmc_like = (kind == MCMCGPU_HMC || kind == MCMCGPU_HMCDA);
@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 4) transition_coop_kern
   if (grp == 0) {
     s_acc[lc] = 0; s_begin[lc] = 0; s_k[lc] = -1; s_nl[lc] = 0; s_eps[lc] = 0.0; s_i[lc] = 0;
     if (mode != CM_NONE) {
-      const uint64_t gchain = (uint64_t)(R.chain_offset + c);
+      const uint64_t gchain = W.chain_ids ? (uint64_t)W.chain_ids[c] : (uint64_t)(R.chain_offset + c);
       const int64_t burnin = R.first - 1;
       auto uniform = [&](int64_t step) -> double {
         return W.inj_uniforms ? W.inj_uniforms[step * Cp + c] : philox_uniform(R.seed, gchain, (uint32_t)step);
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 4) transition_coop_kern
     const double eps = s_eps[lc];
     const int64_t inext = s_i[lc];
     const double sq = (kind == MCMCGPU_MALA) ? sqrt(eps) : 0.0;
-    const uint64_t gchain = (uint64_t)(R.chain_offset + c);
+    const uint64_t gchain = (W.chain_ids && c < R.C) ? (uint64_t)W.chain_ids[c] : (uint64_t)(R.chain_offset + c);
     for (int64_t k = grp; k < npairs; k += CO_GROUPS) {
       double z0 = 0.0, z1 = 0.0;
       if (begin) {

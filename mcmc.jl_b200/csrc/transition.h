@@ -46,6 +46,7 @@ struct WaveArgs {
   double* rb;                  // [S][d][Cp] Rao-Blackwell sums (store_rb) or null
   double* rb_acc;              // [d][Cp] running sum_k w_k pars_k of the current trajectory
   double* init_lt;             // [Cp] log-target at the initial point, or null
+  const int64_t* chain_ids;    // [Cp] global chain id of every chain (Philox key), or null = chain_offset + position
 };
 
 cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st);

@@ -35,7 +35,7 @@ def _lt_grad_check(O, capi, ctx, fam, N, d, C, seed, spread=0.3):
 
 @pytest.mark.parametrize("fam", ["linear", "logistic", "probit"])
 @pytest.mark.parametrize("N,d,C", [(1000, 10, 70), (39, 3, 1), (31, 1, 5), (33, 8, 64), (4097, 100, 130), (257, 104, 65), (2048, 20, 129),
-                                   (300, 105, 66), (513, 150, 64), (777, 200, 70)])
+                                   (300, 105, 66), (350, 113, 65), (513, 150, 64), (777, 200, 70)])
 def test_regression_logtarget_gradient(O, capi, ctx, fam, N, d, C):
     # ragged everything: N not a multiple of the 32-row tile, C not a multiple of the 64-chain tile, d = 1 and d = 104
     _lt_grad_check(O, capi, ctx, fam, N, d, C, seed=N + d)

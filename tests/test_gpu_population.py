@@ -147,3 +147,63 @@ def test_seqmc_over_regression_models(O, capi, ctx, fam):
     assert out["info"]["n_grad_evals"] == npart * steps * (2 + 2 + 4)
     for m in dms:
         m.close()
+
+
+def test_serialtemp_models_equals_closed_form_runner(O, capi, ctx):
+    """the model-array SerialTempMC (replicas regrouped by task, one-step runs of the wave engine) reproduces the
+    one-launch closed-form runner and the oracle, with injected draws and with the engine's own Philox draws"""
+    fam, d = "normal_dsl", 3
+    kinds = [("HMC", dict(scale=0.4, nleaps=3)), ("MALA", dict(scale=0.6)), ("RWM", dict(scale=1.5))]
+    hypers = [(0.0, 1.0), (0.0, 2.0), (0.0, 4.0)]
+    models, osmp, gsmp = _ladder(O, capi, fam, d, hypers, kinds)
+    rng = np.random.default_rng(11)
+    nrep, steps, burnin, swap = 70, 60, 10, 3
+    inits = rng.standard_normal((3, d))
+    zn = rng.standard_normal((nrep, steps + 2, d)); un = rng.random((nrep, steps + 2))
+    pk = rng.random((nrep, steps + 1)); sw = rng.random((nrep, steps + 1))
+    dms = [capi.DeviceModel(ctx, fam, d, hyper=h) for h in hypers]
+    out = ctx.run_serialtemp_models(dms, gsmp, steps, burnin, swap, nrep, inits, normals=zn, uniforms=un, pick=pk, swap=sw)
+    visited = set()
+    for c in range(nrep):
+        ref = O.run_serialtemp(models, osmp, steps, burnin, swap, inits, zn[c], un[c], pk[c], sw[c])
+        assert np.array_equal(out["at"][c], ref["at"]) and np.array_equal(out["samples"][c], ref["samples"]), c
+        visited |= set(ref["at"].tolist())
+    assert visited == {0, 1, 2}
+    a = ctx.run_serialtemp(fam, d, hypers, gsmp, steps, burnin, swap, nrep, inits, seed=4)
+    b = ctx.run_serialtemp_models(dms, gsmp, steps, burnin, swap, nrep, inits, seed=4)
+    assert np.array_equal(a["at"], b["at"]) and np.array_equal(a["samples"], b["samples"])
+    # replicas keyed by global id: two shards reproduce the unsharded run
+    lo = ctx.run_serialtemp_models(dms, gsmp, steps, burnin, swap, 30, inits, seed=4)
+    hi = ctx.run_serialtemp_models(dms, gsmp, steps, burnin, swap, 40, inits, seed=4, rep_offset=30)
+    assert np.array_equal(b["samples"][:30], lo["samples"]) and np.array_equal(b["samples"][30:], hi["samples"])
+    for m in dms:
+        m.close()
+
+
+@pytest.mark.parametrize("fam", ["logistic", "probit"])
+def test_serialtemp_over_regression_models(O, capi, ctx, fam):
+    """SerialTempMC with regression models: a ladder of priors over the same data; every replica's visited tasks identical
+    to the oracle's, samples to 1e-9 (the swap test compares log-targets of two models: decided by K1's sums)."""
+    from conftest import make_regression
+    N, d, nrep, steps, burnin, swap = 300, 8, 40, 40, 5, 4
+    X, y, hy, b0 = make_regression(fam, N, d, 41)
+    sds = [1.0, 1.5, 2.5] if fam != "probit" else [10.0, 15.0, 25.0]
+    hys = [(sd,) + tuple(hy[1:]) for sd in sds]
+    kinds = [("HMC", dict(scale=0.05, nleaps=3)), ("MALA", dict(scale=0.004)), ("RWM", dict(scale=0.03))]
+    oms = [O.Model(fam, d, X, y, h) for h in hys]
+    dms = [capi.DeviceModel(ctx, fam, d, X, y, h) for h in hys]
+    osmp = [O.sampler(k, **kw) for k, kw in kinds]; gsmp = [capi.sampler_cfg(k, **kw) for k, kw in kinds]
+    rng = np.random.default_rng(2)
+    inits = b0 + 0.05 * rng.standard_normal((3, d))
+    zn = rng.standard_normal((nrep, steps + 2, d)); un = rng.random((nrep, steps + 2))
+    pk = rng.random((nrep, steps + 1)); sw = rng.random((nrep, steps + 1))
+    out = ctx.run_serialtemp_models(dms, gsmp, steps, burnin, swap, nrep, inits, normals=zn, uniforms=un, pick=pk, swap=sw)
+    visited = set()
+    for c in range(nrep):
+        ref = O.run_serialtemp(oms, osmp, steps, burnin, swap, inits, zn[c], un[c], pk[c], sw[c])
+        assert ref["rc"] == 0 and np.array_equal(out["at"][c], ref["at"]), c
+        assert np.allclose(out["samples"][c], ref["samples"], rtol=1e-9, atol=1e-12), c
+        visited |= set(ref["at"].tolist())
+    assert len(visited) >= 2
+    for m in dms:
+        m.close()
