@@ -964,20 +964,30 @@ static int stats_common(mcmcgpu_ctx* c, const double* samples, const uint8_t* ac
   double* bmean = nullptr;      // scratch of the stats kernels: batch-mean means, or the state of unfinished Geyer scans
   if (vtype == MCMCGPU_VAR_BM) CU(bufs.get(&bmean, (size_t)(d * Cp), st, false));
   else if (vtype != MCMCGPU_VAR_IID) CU(bufs.get(&bmean, (size_t)(STATS_SCRATCH_PLANES * d * Cp + 2), st, false));
-  CU(launch_stats(samples, S, d, C, Cp, vtype, maxlag, batchlen, outs[0], outs[1], outs[2], outs[3], outs[4], bmean, st));
+  unsigned int unfinished = 0;
+  CU(launch_stats(samples, S, d, C, Cp, vtype, maxlag, batchlen, outs[0], outs[1], outs[2], outs[3], outs[4], bmean, &unfinished, st));
+  if (unfinished) {
+    // few unfinished Geyer scans: finish them on a compact time-contiguous copy (one warp per series); many (slowly mixing
+    // chains) or a copy that would not fit comfortably: one thread per series on the strided draws
+    double* gather = nullptr;
+    const double need = (double)unfinished * (double)S * 8.0;
+    if ((double)unfinished <= 0.25 * (double)(C * d) && need <= 8e9) {
+      if (dalloc(&gather, (size_t)unfinished * (size_t)S) == cudaSuccess) bufs.v.push_back(gather); else { gather = nullptr; cudaGetLastError(); }
+    }
+    CU(launch_stats_more(samples, S, d, C, Cp, vtype, maxlag, outs[0], outs[1], outs[2], outs[3], outs[4], bmean, unfinished, gather, st));
+  }
+  // all results are laid out chain-major on the device first, then copied out back to back: one synchronisation
   double* tmp = nullptr;
-  CU(bufs.get(&tmp, (size_t)(C * d), st, false));
+  CU(bufs.get(&tmp, (size_t)(5 * C * d), st, false));
   for (int k = 0; k < 5; k++) if (hosts[k]) {
-    CU(transpose_to_chain_major(outs[k], tmp, 0, C, d, Cp, st));
-    CU(cudaMemcpyAsync(hosts[k], tmp, sizeof(double) * (size_t)(C * d), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(transpose_to_chain_major(outs[k], tmp + (size_t)k * (size_t)(C * d), 0, C, d, Cp, st));
+    CU(cudaMemcpyAsync(hosts[k], tmp + (size_t)k * (size_t)(C * d), sizeof(double) * (size_t)(C * d), cudaMemcpyDeviceToHost, st));
   }
   if (out_accept_rate && accept) {
     double* rate = nullptr;
     CU(bufs.get(&rate, (size_t)Cp, st, false));
     CU(launch_accept_rate(accept, S, C, Cp, rate, st));
     CU(cudaMemcpyAsync(out_accept_rate, rate, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
   }
   CU(cudaStreamSynchronize(st));
   return MCMCGPU_OK;

@@ -32,11 +32,16 @@ constexpr int K1_STAGES = 2;
 constexpr int K1_NR = 4;          // 8-row groups per phase-1 pass (independent DMMA accumulator chains)
 constexpr int PH_IDLE_K1 = 98;  // phases >= PH_PAUSE (98) have no pending evaluation (transition.h)
 constexpr int PH_LEAP_K1 = 3;   // PH_LEAP (transition.h)
-// x / v for the prior gradient, as transition.cu's div_by_var: exact reciprocal when v is a power of two
-__device__ __forceinline__ double k1_div_by_var(double x, double v) {
-  const long long b = __double_as_longlong(v);
-  const bool pow2 = ((b & 0x000FFFFFFFFFFFFFll) == 0) && v > 1e-150 && v < 1e150 && fabs(x) < 1e150 && (fabs(x) > 1e-150 || x == 0.0);
-  return pow2 ? __dmul_rn(x, __ddiv_rn(1.0, v)) : __ddiv_rn(x, v);
+// x / v for the prior gradient, as transition.cu's div_by_var: multiplication by the exact reciprocal when v is a power of
+// two (inv and the test on v are formed once per thread; the per-element test on x is integer work on its exponent)
+__device__ __forceinline__ bool k1_var_is_pow2(double v) {
+  return ((__double_as_longlong(v) & 0x000FFFFFFFFFFFFFll) == 0) && v > 1e-150 && v < 1e150;
+}
+__device__ __forceinline__ double k1_div_by_var(double x, double v, double inv, bool vpow2) {
+  const int ex = (__double2hiint(x) >> 20) & 0x7ff;                 // biased exponent: 2^-498 < |x| < 2^499, or x == 0
+  const bool ok = vpow2 && ((ex > 0x20d && ex < 0x5f2) || (__double_as_longlong(x) << 1) == 0);
+  if (ok) return __dmul_rn(x, inv);
+  return __ddiv_rn(x, v);
 }
 
 // row permutation inside an 8-row group: column n of the phase-1 B fragment reads row PI[n]
@@ -613,7 +618,20 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
       const bool linlog = (FAM == MCMCGPU_FAM_LINEAR || FAM == MCMCGPU_FAM_LOGISTIC);
       const bool oos = linlog && nbad > 0;                 // LLAcc: out of support => zero gradient (modelparser.jl:64-72)
       const double pvar = __dmul_rn(hy[0], hy[0]);
+      const bool vpow2 = k1_var_is_pow2(pvar);
+      const double pinv = vpow2 ? __ddiv_rn(1.0, pvar) : 0.0;
       const double* brow = betas + (warp * 8 + g) * S;
+      // all momentum loads first: the stores below go to the same array as far as the compiler knows, so a load placed after
+      // a store waits for it (one global round trip per element, ~16 us per CTA, when the loop is written element by element)
+      double mo[DK][2];
+#pragma unroll
+      for (int jb = 0; jb < DK; jb++) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int j = 8 * jb + 2 * t + i;
+          mo[jb][i] = (j < d) ? __ldcg(a.mom + (int64_t)j * Cp + mychain) : 0.0;
+        }
+      }
 #pragma unroll
       for (int jb = 0; jb < DK; jb++) {
 #pragma unroll
@@ -623,15 +641,15 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
             const int64_t idx = (int64_t)j * Cp + mychain;
             const double qj = __dmul_rn(bsign, brow[j]);   // beta tile holds sign * q, sign = +-1: exact
             double gj;
-            if (linlog) gj = oos ? 0.0 : __dadd_rn(G[jb][i], k1_div_by_var(__dsub_rn(0.0, qj), pvar));
-            else gj = __dsub_rn(G[jb][i], k1_div_by_var(qj, pvar));
+            if (linlog) gj = oos ? 0.0 : __dadd_rn(G[jb][i], k1_div_by_var(__dsub_rn(0.0, qj), pvar, pinv, vpow2));
+            else gj = __dsub_rn(G[jb][i], k1_div_by_var(qj, pvar, pinv, vpow2));
             const double hg = __dmul_rn(__dmul_rn(0.5, gj), eps);
-            double m = a.mom[idx];
+            double m = mo[jb][i];
             m = __dadd_rn(m, hg);                          // end of this leapfrog      HMC.jl:98
             m = __dadd_rn(m, hg);                          // start of the next one     HMC.jl:95
             const double p = __dadd_rn(qj, __dmul_rn(eps, m));   //                     HMC.jl:96
-            a.mom[idx] = m;
-            a.q_rw[idx] = p;
+            __stcg(a.mom + idx, m);
+            __stcg(a.q_rw + idx, p);
           }
         }
       }

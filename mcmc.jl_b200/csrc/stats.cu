@@ -122,6 +122,39 @@ __device__ __forceinline__ void acov_pairs(const double* __restrict__ x, int64_t
   }
 }
 
+// The first window (lag0 = 0) needs no look-ahead at all: n Gamma_j = sum_u s_u v_{u-2j}, so ONE stream of x suffices --
+// when v_u arrives, s_{u-1} = v_{u-1} + v_u is complete and meets the ring of the last 2 NP values (every other one).
+// a0 = sum v^2 is accumulated as mul + add in the order of the draws: the reference's variance and gamma_0, bit for bit.
+// The raw values of the next chunk are requested one iteration ahead (software pipeline, see acov_pairs).
+template <int NP>
+__device__ __forceinline__ void acov_first(const double* __restrict__ x, int64_t st, int64_t S, double mu, double& a0, double (&G)[NP]) {
+  constexpr int R = 2 * NP;
+#pragma unroll
+  for (int j = 0; j < NP; j++) G[j] = 0.0;
+  a0 = 0.0;
+  double ring[R], nx[R];
+#pragma unroll
+  for (int i = 0; i < R; i++) { ring[i] = 0.0; nx[i] = (i < S) ? x[(int64_t)i * st] : mu; }   // beyond the end: v = 0 exactly
+  double vprev = 0.0;
+  for (int64_t u0 = 0; u0 <= S; u0 += R) {       // u = S closes s_{S-1} = v_{S-1} + 0
+    double cur[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) cur[i] = nx[i];
+#pragma unroll
+    for (int i = 0; i < R; i++) { const int64_t idx = u0 + R + i; nx[i] = (idx < S) ? x[idx * st] : mu; }
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+      const double vu = cur[i] - mu;
+      const double sp = vprev + vu;                                 // s_{u-1}
+      a0 += vu * vu;                                                // == sum (x - mu)^2 of Base.var, same roundings
+#pragma unroll
+      for (int j = 0; j < NP; j++) G[j] = fma(sp, (j == 0) ? vprev : ring[(i - 1 - 2 * j + 2 * R) % R], G[j]);
+      ring[i] = vu;
+      vprev = vu;
+    }
+  }
+}
+
 // Geyer scan over the pairs of one window (var.jl:56-71); returns true when the sequence is truncated
 template <int NP>
 __device__ __forceinline__ bool geyer_window(const double (&G)[NP], double n, int64_t k, bool monotone, int64_t& jj, double& gsum,
@@ -188,7 +221,7 @@ __global__ void __launch_bounds__(ST_THREADS, 3) stats_var_kernel(const double* 
     bool stop;
     {
       double G[NP_WIN];
-      acov_pairs<NP_WIN, true>(x, st, S, mu, 0, 0, S, ss, G);
+      acov_first<NP_WIN>(x, st, S, mu, ss, G);
       acv0 = ss / n;                                                // gamma_0 (var.jl:53)
       stop = (k < 0) || geyer_window<NP_WIN>(G, n, k, monotone, jj, gsum, gprev);
     }
@@ -213,22 +246,41 @@ __global__ void __launch_bounds__(ST_THREADS, 3) stats_var_kernel(const double* 
 }
 
 // The windows beyond the first NP_WIN pairs, for the series stats_var_kernel left unfinished.
-// Few unfinished series (well-mixing chains: ~2 % survive 8 noise-level pairs): ONE WARP PER SERIES from the compact list, the
-// lanes split the time axis and the partial pair sums are combined by a butterfly (every lane holds the same sum and takes
-// the same decision).  A thread per series would leave the other 31 lanes of almost every warp idle for whole passes.
-__global__ void __launch_bounds__(ST_THREADS) stats_more_warp_kernel(const double* __restrict__ samples, int64_t S, int64_t d, int64_t Cp,
+// Few unfinished series (HMC(0.75) on the 3-D Normal: 4.4 % survive the first 8 pairs): they are first copied out of the
+// chain-minor draws into a compact TIME-CONTIGUOUS buffer (a series is strided by d * Cp doubles in the draws: every element
+// costs a whole DRAM sector, paid here once), then ONE WARP PER SERIES walks its copy: the lanes split the time axis, each
+// streaming its own contiguous segment, and the partial pair sums are combined by a butterfly (every lane holds the same
+// sum and takes the same decision).  A thread per series would leave the other 31 lanes of almost every warp idle for whole
+// passes over the strided draws (measured: 7.9 ms and 8 GB of DRAM reads for those windows at 65 536 x 3 series x 9000 draws).
+__global__ void stats_gather_kernel(const double* __restrict__ samples, int64_t S, int64_t st, const int32_t* __restrict__ more_list,
+                                    unsigned int cnt, double* __restrict__ buf) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t e = warp; e < (int64_t)cnt; e += nwarps) {
+    const double* x = samples + more_list[e];
+    double* y = buf + e * S;
+    int64_t t = lane;
+    for (; t + 96 < S; t += 128) {               // 4 independent strided loads per lane in flight
+      const double v0 = x[t * st], v1 = x[(t + 32) * st], v2 = x[(t + 64) * st], v3 = x[(t + 96) * st];
+      y[t] = v0; y[t + 32] = v1; y[t + 64] = v2; y[t + 96] = v3;
+    }
+    for (; t < S; t += 32) y[t] = x[t * st];
+  }
+}
+
+__global__ void __launch_bounds__(ST_THREADS) stats_more_warp_kernel(const double* __restrict__ buf, int64_t S, int64_t d, int64_t Cp,
                                                                       int64_t maxlag, int monotone, const double* __restrict__ mean_i,
                                                                       const double* __restrict__ more, const int32_t* __restrict__ more_list,
                                                                       const unsigned int* __restrict__ more_count, double* viid_o,
                                                                       double* var_o, double* ess_o, double* act_o) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t plane = d * Cp, st = d * Cp, k = (maxlag - 1) / 2;
+  const int64_t plane = d * Cp, st = 1, k = (maxlag - 1) / 2;
   const double n = (double)S;
   const unsigned int cnt = *more_count;
   for (int64_t e = warp; e < (int64_t)cnt; e += nwarps) {
-    const int64_t o = more_list[e];
-    const double* x = samples + o;                 // o = j * Cp + c
+    const int64_t o = more_list[e];                // o = j * Cp + c
+    const double* x = buf + e * S;                 // the series' time-contiguous copy
     const double mu = mean_i[o];
     double acv0 = more[plane + o], gsum = more[2 * plane + o], gprev = more[3 * plane + o];
     int64_t jj = (int64_t)more[4 * plane + o];
@@ -292,7 +344,7 @@ __global__ void __launch_bounds__(ST_THREADS) stats_more_lane_kernel(const doubl
 
 cudaError_t launch_stats(const double* samples, int64_t S, int64_t d, int64_t C, int64_t Cp, int vtype, int64_t maxlag,
                          int64_t batchlen, double* mean, double* var_iid, double* var, double* ess, double* actime,
-                         double* scratch, cudaStream_t st) {
+                         double* scratch, unsigned int* n_unfinished, cudaStream_t st) {
   // `mean` must be a device buffer [d][Cp] (pass 2 reads it); scratch: [d][Cp] doubles for batch means,
   // STATS_SCRATCH_PLANES * d * Cp + 2 for IMSE / IPSE (6 planes of scan state, the list of unfinished series, its length)
   double* bmean_scratch = scratch;
@@ -300,6 +352,7 @@ cudaError_t launch_stats(const double* samples, int64_t S, int64_t d, int64_t C,
   int32_t* more_list = scratch ? reinterpret_cast<int32_t*>(scratch + 6 * plane) : nullptr;
   unsigned int* more_count = scratch ? reinterpret_cast<unsigned int*>(scratch + 7 * plane) : nullptr;
   const bool geyer = (vtype == MCMCGPU_VAR_IMSE || vtype == MCMCGPU_VAR_IPSE);
+  if (n_unfinished) *n_unfinished = 0;
   if (geyer) {
     cudaError_t e0 = cudaMemsetAsync(more_count, 0, sizeof(unsigned int), st);
     if (e0 != cudaSuccess) return e0;
@@ -319,22 +372,32 @@ cudaError_t launch_stats(const double* samples, int64_t S, int64_t d, int64_t C,
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  if (geyer) {
-    unsigned int cnt = 0;
-    e = cudaMemcpyAsync(&cnt, more_count, sizeof(cnt), cudaMemcpyDeviceToHost, st);
+  if (geyer && n_unfinished) {      // how many series go on: the caller sizes the compact copy from it
+    e = cudaMemcpyAsync(n_unfinished, more_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) return e;
-    const int mono = vtype == MCMCGPU_VAR_IMSE ? 1 : 0;
-    if (cnt == 0) return cudaSuccess;
-    if ((double)cnt > 0.25 * (double)(C * d)) {
-      stats_more_lane_kernel<<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, mono, mean, scratch, var_iid, var, ess, actime);
-    } else {
-      const unsigned blocks = (unsigned)((cnt + 3) / 4 < 148 * 8 ? (cnt + 3) / 4 : 148 * 8);     // 4 warps per block
-      stats_more_warp_kernel<<<blocks, ST_THREADS, 0, st>>>(samples, S, d, Cp, maxlag, mono, mean, scratch, more_list, more_count, var_iid, var, ess, actime);
-    }
-    e = cudaGetLastError();
   }
   return e;
+}
+
+cudaError_t launch_stats_more(const double* samples, int64_t S, int64_t d, int64_t C, int64_t Cp, int vtype, int64_t maxlag,
+                              const double* mean, double* var_iid, double* var, double* ess, double* actime, double* scratch,
+                              unsigned int cnt, double* gather, cudaStream_t st) {
+  if (cnt == 0) return cudaSuccess;
+  const int64_t plane = d * Cp;
+  const int32_t* more_list = reinterpret_cast<const int32_t*>(scratch + 6 * plane);
+  const unsigned int* more_count = reinterpret_cast<const unsigned int*>(scratch + 7 * plane);
+  const int mono = vtype == MCMCGPU_VAR_IMSE ? 1 : 0;
+  if (!gather) {
+    dim3 grid((unsigned)((C + ST_THREADS - 1) / ST_THREADS), (unsigned)d);
+    stats_more_lane_kernel<<<grid, ST_THREADS, 0, st>>>(samples, S, d, C, Cp, maxlag, mono, mean, scratch, var_iid, var, ess, actime);
+    return cudaGetLastError();
+  }
+  const unsigned blocks = (unsigned)((cnt + 3) / 4 < 148 * 16 ? (cnt + 3) / 4 : 148 * 16);     // 4 warps per block
+  stats_gather_kernel<<<blocks, ST_THREADS, 0, st>>>(samples, S, d * Cp, more_list, cnt, gather);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  stats_more_warp_kernel<<<blocks, ST_THREADS, 0, st>>>(gather, S, d, Cp, maxlag, mono, mean, scratch, more_list, more_count, var_iid, var, ess, actime);
+  return cudaGetLastError();
 }
 
 __global__ void accept_rate_kernel(const uint8_t* accept, int64_t S, int64_t C, int64_t Cp, double* rate) {

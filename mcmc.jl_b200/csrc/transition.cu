@@ -32,9 +32,12 @@ struct EvalFin {
 // multiplication by the exact reciprocal -- the same double for every x whose quotient is a normal number -- instead of the
 // ~20-instruction IEEE division sequence
 __device__ __forceinline__ double div_by_var(double x, double v) {
-  const long long b = __double_as_longlong(v);
-  const bool pow2 = ((b & 0x000FFFFFFFFFFFFFll) == 0) && v > 1e-150 && v < 1e150 && fabs(x) < 1e150 && (fabs(x) > 1e-150 || x == 0.0);
-  return pow2 ? x * (1.0 / v) : x / v;
+  // the test on v and the reciprocal are loop invariants of every caller (v is a model constant); the test on x is integer
+  // work on its exponent: 2^-498 < |x| < 2^499, or x == 0
+  const bool vpow2 = ((__double_as_longlong(v) & 0x000FFFFFFFFFFFFFll) == 0) && v > 1e-150 && v < 1e150;
+  const int ex = (__double2hiint(x) >> 20) & 0x7ff;
+  if (vpow2 && ((ex > 0x20d && ex < 0x5f2) || (__double_as_longlong(x) << 1) == 0)) return x * (1.0 / v);
+  return x / v;
 }
 
 __device__ __forceinline__ EvalFin finalize_eval(const ModelDev& M, const double* q, const double* part, int nsplit,
