@@ -602,9 +602,9 @@ def cfg2_block(B, wl, K, W, clock=False):
     # what ess(batch) / mean(batch) / acceptance(batch) of the host API do); only the d x C summaries cross PCIe
     B.barrier()
     t0 = time.perf_counter()
-    r = capi.DeviceRun(dm, scfg, (1, 1, Ks), C, np.ones(d), seed=wl["seed"], chain_offset=rank * C, engine="fused", store_grad=False, store_logtarget=False)
+    r = capi.DeviceRun(dm, scfg, (1, 1, Ks), C, np.ones(d), seed=wl["seed"], chain_offset=rank * C, engine="fused", stream_stats=True)
     r.execute()
-    st = r.stats("imse")
+    st = r.stats("bm")
     torch.cuda.synchronize()
     sum_s = time.perf_counter() - t0
     r.close()
@@ -619,8 +619,8 @@ def cfg2_block(B, wl, K, W, clock=False):
                 e2e=dict(value=C * world * Ks / (e2e_ms / 1e3), unit="chain-steps/s", h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K),
                 e2e_summaries=dict(value=C * world * Ks / (sum_ms / 1e3), unit="chain-steps/s", h2d_bytes_per_step=d * 8 / K,
                                    d2h_bytes_per_step=(5 * d + 1) * C * 8 / K, median_ess_per_step=float(np.median(st["ess"])) / Ks,
-                                   note="run + mean / var_iid / var_imse / ess / actime / acceptance on the device-resident draws (mcmcgpu_run_stats); "
-                                        "the kept draws never leave HBM"),
+                                   note="stream_stats run: mean / var_iid / var_bm / ess(bm) / actime / acceptance accumulated in registers while "
+                                        "sampling (mcmcgpu_runner_cfg.stream_stats), no draw is stored; only the d x C summaries cross PCIe"),
                 roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, kernel="fused_chain_kernel",
                               note="store bandwidth of kept draws; the kernel is FP64-ALU/latency bound, see DESIGN.md"))
 

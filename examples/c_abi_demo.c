@@ -22,11 +22,12 @@ int main(int argc, char** argv) {
            offsetof(mcmcgpu_sampler_cfg, step), offsetof(mcmcgpu_sampler_cfg, max_leaps), offsetof(mcmcgpu_sampler_cfg, tuner_on),
            offsetof(mcmcgpu_sampler_cfg, adapt_step), offsetof(mcmcgpu_sampler_cfg, max_step), offsetof(mcmcgpu_sampler_cfg, target_path),
            offsetof(mcmcgpu_sampler_cfg, target_rate));
-    printf("runner_cfg %zu first %zu step %zu last %zu nchains %zu chain_offset %zu seed %zu init_per_chain %zu store_grad %zu store_logtarget %zu engine %zu store_rb %zu\n",
+    printf("runner_cfg %zu first %zu step %zu last %zu nchains %zu chain_offset %zu seed %zu init_per_chain %zu store_grad %zu store_logtarget %zu engine %zu store_rb %zu stream_stats %zu stream_batchlen %zu\n",
            sizeof(mcmcgpu_runner_cfg), offsetof(mcmcgpu_runner_cfg, first), offsetof(mcmcgpu_runner_cfg, step), offsetof(mcmcgpu_runner_cfg, last),
            offsetof(mcmcgpu_runner_cfg, nchains), offsetof(mcmcgpu_runner_cfg, chain_offset), offsetof(mcmcgpu_runner_cfg, seed),
            offsetof(mcmcgpu_runner_cfg, init_per_chain), offsetof(mcmcgpu_runner_cfg, store_grad), offsetof(mcmcgpu_runner_cfg, store_logtarget),
-           offsetof(mcmcgpu_runner_cfg, engine), offsetof(mcmcgpu_runner_cfg, store_rb));
+           offsetof(mcmcgpu_runner_cfg, engine), offsetof(mcmcgpu_runner_cfg, store_rb), offsetof(mcmcgpu_runner_cfg, stream_stats),
+           offsetof(mcmcgpu_runner_cfg, stream_batchlen));
     printf("run_info %zu gpu_ms %zu n_grad_evals %zu n_waves %zu n_launches %zu eval_ms %zu comm_ms %zu\n", sizeof(mcmcgpu_run_info),
            offsetof(mcmcgpu_run_info, gpu_ms), offsetof(mcmcgpu_run_info, n_grad_evals), offsetof(mcmcgpu_run_info, n_waves),
            offsetof(mcmcgpu_run_info, n_launches), offsetof(mcmcgpu_run_info, eval_ms), offsetof(mcmcgpu_run_info, comm_ms));

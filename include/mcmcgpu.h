@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MCMCGPU_ABI_VERSION 2   /* 2: mcmcgpu_run_info.comm_ms */
+#define MCMCGPU_ABI_VERSION 3   /* 2: mcmcgpu_run_info.comm_ms; 3: mcmcgpu_runner_cfg.stream_stats / stream_batchlen */
 
 /* status codes */
 #define MCMCGPU_OK 0
@@ -91,6 +91,13 @@ typedef struct {
   int32_t store_rb;          /* HMC storeLeaps (HMC.jl:145-150): keep, per kept step, the Rao-Blackwell sum of
                                 mean_rb_hmc (src/stats/mean.jl:11-35) accumulated over the leapfrog states on the fly
                                 (the leap states themselves are not stored); fetched with mcmcgpu_run_fetch_rb */
+  int32_t stream_stats;      /* engine FUSED only: do NOT store the draws; instead accumulate, in registers while sampling, what
+                                src/stats needs for mean (mean.jl:6), mcvar_iid (var.jl:7-8), mcvar_bm (var.jl:20-26; batch
+                                length stream_batchlen, 0 = 100), ess / actime of vtype :bm (ess.jl:6-19) and acceptance
+                                (summary.jl:6-15).  mcmcgpu_run_stats(vtype IID or BM) then returns them; fetch is an error.
+                                The mean is the two-pass code's sum bit for bit; the variances are one-pass (shifted by the
+                                first kept draw) and agree with it to ~1e-12. */
+  int32_t stream_batchlen;
 } mcmcgpu_runner_cfg;
 
 typedef struct {

@@ -10,7 +10,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmcmcgpu.so")
+LIB_PATH = os.environ.get("MCMCGPU_LIB") or os.path.join(_HERE, "libmcmcgpu.so")   # MCMCGPU_LIB: A/B timing of two builds (tools/)
 
 OK, E_ARG, E_SUPPORT, E_NOGRAD, E_CUDA, E_COMM, E_STATE = 0, -1, -2, -3, -4, -5, -6
 FAM = dict(normal_fn=0, normal_dsl=1, linear=2, logistic=3, probit=4, ou=5, abs_normal=6)
@@ -37,7 +37,8 @@ class RunnerCfg(C.Structure):
     _fields_ = [("first", C.c_int64), ("step", C.c_int64), ("last", C.c_int64),
                 ("nchains", C.c_int64), ("chain_offset", C.c_int64), ("seed", C.c_uint64),
                 ("init_per_chain", C.c_int32), ("store_grad", C.c_int32),
-                ("store_logtarget", C.c_int32), ("engine", C.c_int32), ("store_rb", C.c_int32)]
+                ("store_logtarget", C.c_int32), ("engine", C.c_int32), ("store_rb", C.c_int32),
+                ("stream_stats", C.c_int32), ("stream_batchlen", C.c_int32)]
 
 
 class RunInfo(C.Structure):
@@ -340,7 +341,7 @@ class DeviceRun(_Owned):
     """Split-form run: inputs resident in HBM after construction; execute() may be timed alone."""
 
     def __init__(self, model, scfg, rng, nchains, init, scale=None, seed=0, chain_offset=0, normals=None, uniforms=None,
-                 store_grad=True, store_logtarget=True, engine="auto", store_rb=False):
+                 store_grad=True, store_logtarget=True, engine="auto", store_rb=False, stream_stats=False, stream_batchlen=0):
         first, step, last = rng
         self.model, self.d = model, model.d
         r = RunnerCfg()
@@ -351,6 +352,10 @@ class DeviceRun(_Owned):
             raise MCMCGPUError(E_ARG, "init must be (d,) or (nchains, d)")
         r.store_grad, r.store_logtarget, r.engine = int(store_grad), int(store_logtarget), ENGINE[engine]
         r.store_rb = int(store_rb)
+        r.stream_stats, r.stream_batchlen = int(stream_stats), int(stream_batchlen)
+        if stream_stats:
+            store_grad = store_logtarget = False
+            r.store_grad = r.store_logtarget = 0
         self.S = 0 if (step < 1 or last < first) else (last - first) // step + 1
         self.C = nchains
         self.store_grad, self.store_logtarget = store_grad, store_logtarget

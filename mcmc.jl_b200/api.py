@@ -336,11 +336,14 @@ class GPUMC(SerialMC):
     """The many-chain runner added beside SerialMC: same range arguments plus
     nchains, seed, shard ("chains": chains split over ranks, no communication), store_gradients, engine."""
 
-    def __init__(self, *args, nchains=1, seed=0, shard="chains", store_gradients=True, engine="auto", **kw):
+    def __init__(self, *args, nchains=1, seed=0, shard="chains", store_gradients=True, engine="auto", store_draws=True, **kw):
         super().__init__(*args, **kw)
         assert nchains >= 1
         assert shard in ("chains", "rows")
         self.nchains, self.seed, self.shard, self.store_gradients, self.engine = int(nchains), int(seed), shard, store_gradients, engine
+        # store_draws=False: the fused engine keeps no draws and accumulates mean / var(:iid, :bm) / ess(:bm) / acceptance while
+        # sampling (closed-form families); the batch then answers mean(), var(vtype="bm"), ess(vtype="bm"), acceptance() only
+        self.store_draws = bool(store_draws)
 
 
 class SeqMC:
@@ -553,10 +556,11 @@ def _run_task(t, init=None, normals=None, uniforms=None, shard_over_ranks=False)
     ini = m.init if init is None else np.asarray(init, dtype=np.float64)
     if ini.ndim == 2:
         ini = ini[offset:offset + nchains]
+    stream = not getattr(r, "store_draws", True)
     drun = capi.DeviceRun(m.device_model(), s._cfg(), (r.r.start, r.r.step, r.r[-1]), nchains, ini, scale=m.scale,
                           seed=r.seed, chain_offset=offset, normals=normals, uniforms=uniforms,
-                          store_grad=bool(r.store_gradients), store_logtarget=True, engine=r.engine,
-                          store_rb=bool(getattr(s, "storeLeaps", False)))
+                          store_grad=bool(r.store_gradients) and not stream, store_logtarget=not stream,
+                          engine="fused" if stream else r.engine, store_rb=bool(getattr(s, "storeLeaps", False)), stream_stats=stream)
     try:
         info = drun.execute()
     except MCMCGPUError as e:

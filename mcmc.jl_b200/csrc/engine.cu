@@ -95,6 +95,7 @@ struct mcmcgpu_run {
   unsigned long long* n_evals = nullptr;
   // wave state
   double *rb = nullptr, *rb_acc = nullptr;
+  double *stream = nullptr, *stream_accept = nullptr;   // streamed summaries (stream_stats) instead of stored draws
   double* init_lt = nullptr;   // log-target at the initial point (the `reset` evaluation of the population runners)
   const int64_t* chain_ids = nullptr;   // per-chain Philox keys (population runners that regroup replicas); not owned
   double *ram_S = nullptr, *ram_al = nullptr;
@@ -531,9 +532,19 @@ static int run_create_impl(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     RCU(cudaStreamSynchronize(st));
   }
   // outputs
-  RCU(R->alloc(&R->samples, (size_t)(S * d * Cp), false));
+  if (r->stream_stats) {
+    if (engine != MCMCGPU_ENGINE_FUSED || r->store_grad || r->store_logtarget || r->store_rb || S < 2) {
+      mcmcgpu_run_destroy(R);
+      return fail(MCMCGPU_E_ARG, "stream_stats needs engine FUSED, at least 2 kept steps and no stored gradients / log-targets / leaps");
+    }
+    if (R->r.stream_batchlen <= 0) R->r.stream_batchlen = 100;
+    RCU(R->alloc(&R->stream, (size_t)(FUSED_STREAM_ROWS * d * Cp)));
+    RCU(R->alloc(&R->stream_accept, (size_t)Cp));
+  } else {
+    RCU(R->alloc(&R->samples, (size_t)(S * d * Cp), false));
+    RCU(R->alloc(&R->accept, (size_t)(S * Cp)));
+  }
   if (r->store_grad) RCU(R->alloc(&R->grads, (size_t)(S * d * Cp), false));
-  RCU(R->alloc(&R->accept, (size_t)(S * Cp)));
   if (r->store_logtarget) RCU(R->alloc(&R->logtarget, (size_t)(S * Cp), false));
   if (r->store_rb) {
     if (s->kind != MCMCGPU_HMC && s->kind != MCMCGPU_HMCDA) { mcmcgpu_run_destroy(R); return fail(MCMCGPU_E_ARG, "storeLeaps applies to HMC / HMCDA"); }
@@ -649,6 +660,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     A.samples = R->samples; A.grads = R->grads; A.accept = R->accept; A.logtarget = R->logtarget;
     A.eps = R->eps; A.nleaps = R->nleaps; A.final_eps = R->final_eps; A.final_pars = nullptr; A.rb = R->rb;
     A.status = R->status; A.n_evals = R->n_evals;
+    A.stream = R->stream; A.stream_accept = R->stream_accept; A.stream_batchlen = R->r.stream_batchlen;
     CU(launch_fused(A, st));
     launches = 1;
     R->started = true;
@@ -888,6 +900,7 @@ static int fetch_chunked(mcmcgpu_run* R, const double* dev, int64_t K, double* h
 int32_t mcmcgpu_run_fetch(mcmcgpu_run* R, double* out_samples, double* out_grads, uint8_t* out_accept, double* out_logtarget) {
   if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
+  if (R->stream) return fail(MCMCGPU_E_STATE, "the run streamed its summaries (stream_stats): no draws were stored; use mcmcgpu_run_stats");
   CU(use_ctx(R->m->ctx));
   cudaStream_t st = R->m->ctx->stream;
   int rc;
@@ -998,6 +1011,28 @@ int32_t mcmcgpu_run_stats(mcmcgpu_run* R, int32_t vtype, int64_t maxlag, int64_t
   if (!R) return fail(MCMCGPU_E_ARG, "run is NULL");
   if (!R->executed) return fail(MCMCGPU_E_STATE, "run has not been executed");
   CU(use_ctx(R->m->ctx));
+  if (R->stream) {      // summaries accumulated while sampling: rows mean, var_iid, var_bm, ess, actime
+    if (vtype != MCMCGPU_VAR_IID && vtype != MCMCGPU_VAR_BM) return fail(MCMCGPU_E_ARG, "a streamed run (stream_stats) offers vtype iid and bm");
+    if ((out_ess || out_actime) && vtype == MCMCGPU_VAR_IID) return fail(MCMCGPU_E_ARG, "Unknown ESS type iid");
+    if (vtype == MCMCGPU_VAR_BM && batchlen > 0 && batchlen != R->r.stream_batchlen)
+      return fail(MCMCGPU_E_ARG, "the batch length of a streamed run is fixed at run creation (stream_batchlen)");
+    if (vtype == MCMCGPU_VAR_BM && R->S / R->r.stream_batchlen <= 1)
+      return fail(MCMCGPU_E_ARG, "Choose batch size such that the number of batches is greather than one");        // var.jl:22
+    cudaStream_t st = R->m->ctx->stream;
+    const int64_t C = R->C, d = R->d, Cp = R->Cp, P = d * Cp;
+    double* hosts[5] = {out_mean, out_var_iid, out_var, out_ess, out_actime};
+    const int rows[5] = {0, 1, vtype == MCMCGPU_VAR_BM ? 2 : 1, 3, 4};
+    DevBufs bufs;
+    double* tmp = nullptr;
+    CU(bufs.get(&tmp, (size_t)(5 * C * d), st, false));
+    for (int k = 0; k < 5; k++) if (hosts[k]) {
+      CU(transpose_to_chain_major(R->stream + rows[k] * P, tmp + (size_t)k * (size_t)(C * d), 0, C, d, Cp, st));
+      CU(cudaMemcpyAsync(hosts[k], tmp + (size_t)k * (size_t)(C * d), sizeof(double) * (size_t)(C * d), cudaMemcpyDeviceToHost, st));
+    }
+    if (out_accept_rate) CU(cudaMemcpyAsync(out_accept_rate, R->stream_accept, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MCMCGPU_OK;
+  }
   return stats_common(R->m->ctx, R->samples, R->accept, R->S, R->d, R->C, R->Cp, vtype, maxlag, batchlen, out_mean, out_var_iid,
                       out_var, out_ess, out_actime, out_accept_rate);
 }

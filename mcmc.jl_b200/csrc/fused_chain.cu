@@ -21,7 +21,7 @@ __device__ __forceinline__ double dotd(const double (&a)[D], int d) {
   return s;
 }
 
-template <int FAM, int D>
+template <int FAM, int D, bool STREAM>
 __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedArgs A) {
   extern __shared__ double sh_series[];
   const ModelDev& M = A.M;
@@ -56,9 +56,44 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
     return A.inj_uniforms ? A.inj_uniforms[i * Cp + c] : philox_uniform(R.seed, gchain, (uint32_t)i);
   };
   int64_t kept = 0;
+  // streamed summaries (stream_stats): per parameter the serial sum of the draws (the mean of src/stats/mean.jl:6, bit for bit),
+  // one-pass sums shifted by the first kept draw for Base.var, and the batch sums of mcvar_bm (var.jl:20-26)
+  // (a template parameter: the 7 D accumulators must not cost the draw-storing kernel its registers)
+  constexpr bool streaming = STREAM;
+  constexpr int DS = STREAM ? D : 1;
+  double st_k[DS], st_sx[DS], st_sy[DS], st_syy[DS], st_bs[DS], st_sb[DS], st_sbb[DS];
+  int64_t st_inb = 0, st_nb = 0, st_acc = 0;
+  const int64_t st_nbmax = streaming ? R.S / A.stream_batchlen : 0;
+#pragma unroll
+  for (int j = 0; j < DS; j++) { st_k[j] = 0.0; st_sx[j] = 0.0; st_sy[j] = 0.0; st_syy[j] = 0.0; st_bs[j] = 0.0; st_sb[j] = 0.0; st_sbb[j] = 0.0; }
   auto store = [&](int64_t i, const double (&pp)[D], double plt, const double (&pg)[D], bool has_grad, bool acc,
                    double eps, int nl) {
     if (!in_range(i, R.first, R.step, R.last)) return;
+    if (streaming) {
+      if (kept == 0) {
+#pragma unroll
+        for (int j = 0; j < DS; j++) st_k[j] = pp[j];
+      }
+      const bool inbatch = st_nb < st_nbmax;
+#pragma unroll
+      for (int j = 0; j < DS; j++) {
+        const double y = pp[j] - st_k[j];
+        st_sx[j] += pp[j];
+        st_sy[j] += y;
+        st_syy[j] += y * y;
+        if (inbatch) st_bs[j] += y;
+      }
+      if (inbatch && ++st_inb == A.stream_batchlen) {
+#pragma unroll
+        for (int j = 0; j < DS; j++) { const double b = st_bs[j] / (double)A.stream_batchlen; st_sb[j] += b; st_sbb[j] += b * b; st_bs[j] = 0.0; }
+        st_inb = 0; st_nb++;
+      }
+      st_acc += acc ? 1 : 0;
+      if (A.eps) A.eps[kept * Cp + c] = eps;
+      if (A.nleaps) A.nleaps[kept * Cp + c] = nl;
+      kept++;
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < D; j++) if (j < d) A.samples[(kept * d + j) * Cp + c] = pp[j];
     if (A.grads) {
@@ -326,6 +361,28 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
     }
     if (A.final_eps) A.final_eps[c] = da ? leapStepDA : (S.tuner_on ? t_step : S.scale);
   }
+  if (streaming && kept >= 2) {
+    const double n = (double)kept, plane = 0.0;
+    (void)plane;
+    const int64_t P = (int64_t)d * Cp;
+#pragma unroll
+    for (int j = 0; j < DS; j++) if (j < d) {
+      const int64_t o = (int64_t)j * Cp + c;
+      const double viid = ((st_syy[j] - st_sy[j] * st_sy[j] / n) / (n - 1.0)) / n;                  // var.jl:7-8
+      double vbm = CUDART_NAN;
+      if (st_nb > 1) {
+        const double nb = (double)st_nb;
+        const double vb = (st_sbb[j] - st_sb[j] * st_sb[j] / nb) / (nb - 1.0);                      // var of the batch means
+        vbm = (double)A.stream_batchlen * vb / (nb * (double)A.stream_batchlen);                    // var.jl:25
+      }
+      A.stream[o] = st_sx[j] / n;                                                                   // mean.jl:6
+      A.stream[P + o] = viid;
+      A.stream[2 * P + o] = vbm;
+      A.stream[3 * P + o] = n * viid / vbm;                                                         // ess.jl:9
+      A.stream[4 * P + o] = vbm / viid;                                                             // ess.jl:18
+    }
+    A.stream_accept[c] = (double)st_acc * 100.0 / n;                                                // summary.jl:13
+  }
   // final state (resume) + evaluation count
   if (A.final_pars) {
 #pragma unroll
@@ -338,11 +395,13 @@ template <int FAM, int D>
 static cudaError_t launch_one(const FusedArgs& A, cudaStream_t st) {
   size_t smem = (FAM == MCMCGPU_FAM_OU) ? sizeof(double) * (size_t)A.M.N : 0;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(fused_chain_kernel<FAM, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(fused_chain_kernel<FAM, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_chain_kernel<FAM, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
   int blocks = (int)((A.R.C + FUSED_THREADS - 1) / FUSED_THREADS);
-  fused_chain_kernel<FAM, D><<<blocks, FUSED_THREADS, smem, st>>>(A);
+  if (A.stream) fused_chain_kernel<FAM, D, true><<<blocks, FUSED_THREADS, smem, st>>>(A);
+  else fused_chain_kernel<FAM, D, false><<<blocks, FUSED_THREADS, smem, st>>>(A);
   return cudaGetLastError();
 }
 

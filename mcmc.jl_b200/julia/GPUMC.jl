@@ -67,6 +67,7 @@ end
 type RunnerCfg    # mirrors mcmcgpu_runner_cfg
   first::Int64; step::Int64; last::Int64; nchains::Int64; chain_offset::Int64; seed::Uint64
   init_per_chain::Int32; store_grad::Int32; store_logtarget::Int32; engine::Int32; store_rb::Int32
+  stream_stats::Int32; stream_batchlen::Int32
 end
 
 tunercfg(t) = isa(t, EmpMCTuner) ? (int32(1), int32(t.adaptStep), int32(t.maxStep), t.targetPath, t.targetRate) :
@@ -91,7 +92,7 @@ function run_gpumc(t::MCMCTask)
   samples = Array(Float64, d, S, C); grads = Array(Float64, d, S, C)
   accept = Array(Uint8, S, C); logtarget = Array(Float64, S, C)
   scfg = samplercfg(t.sampler)
-  rcfg = RunnerCfg(first(r.r), r.r.step, last(r.r), C, 0, r.seed, 0, r.storegradients, 1, 0, 0)
+  rcfg = RunnerCfg(first(r.r), r.r.step, last(r.r), C, 0, r.seed, 0, r.storegradients, 1, 0, 0, 0, 0)
   info = Array(Float64, 5)
   rc = ccall((:mcmcgpu_run_chains, libmcmcgpu), Int32,
              (Ptr{Void}, Ptr{SamplerCfg}, Ptr{RunnerCfg}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},

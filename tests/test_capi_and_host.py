@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol(capi):
     for name in declared:
         assert hasattr(lib, name), f"libmcmcgpu.so does not export {name}"
     assert sorted(capi.EXPORTS) == declared, "ctypes binding and header disagree"
-    assert lib.mcmcgpu_abi_version() == 2
+    assert lib.mcmcgpu_abi_version() == 3
 
 
 def test_no_cpu_fallback(capi):

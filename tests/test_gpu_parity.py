@@ -839,3 +839,29 @@ def test_regression_chain_sharding_invariance(capi, ctx):
     assert np.array_equal(outs[0]["samples"][:72], outs[1]["samples"]) and np.array_equal(outs[0]["samples"][72:], outs[2]["samples"])
     assert np.array_equal(outs[0]["accept"][72:], outs[2]["accept"])
     dm.close()
+
+
+@pytest.mark.parametrize("kind,skw", [("HMC", dict(scale=0.75, nleaps=10)), ("RWM", dict(scale=0.5)), ("MALA", dict(scale=0.4))])
+def test_streamed_summaries_match_the_two_pass_stats(capi, ctx, kind, skw):
+    """stream_stats: the fused kernel keeps no draws and accumulates the summaries while sampling; same chains (same Philox
+    keys) as a draw-storing run, whose src/stats pass is the reference: the mean bit for bit (same serial sum), the one-pass
+    variances, batch-means variance, ESS and IAT to 1e-10, the acceptance rate exactly."""
+    d, C, rngt = 3, 300, (101, 2, 1900)
+    dm = capi.DeviceModel(ctx, "normal_fn", d)
+    cfg = capi.sampler_cfg(kind, **skw)
+    full = capi.DeviceRun(dm, cfg, rngt, C, np.ones(d), seed=21, chain_offset=5, engine="fused"); full.execute()
+    ref = full.stats("bm", batchlen=50)
+    st = capi.DeviceRun(dm, cfg, rngt, C, np.ones(d), seed=21, chain_offset=5, engine="fused", stream_stats=True, stream_batchlen=50); st.execute()
+    out = st.stats("bm", batchlen=50)
+    assert np.array_equal(out["mean"], ref["mean"]) and np.array_equal(out["accept_rate"], ref["accept_rate"])
+    for k in ("var_iid", "var", "ess", "actime"):
+        assert np.allclose(out[k], ref[k], rtol=1e-10, atol=0), k
+    iid = st.stats("iid")
+    assert np.allclose(iid["var"], ref["var_iid"], rtol=1e-10, atol=0)
+    with pytest.raises(capi.MCMCGPUError):
+        st.fetch()                                    # no draws were stored
+    with pytest.raises(capi.MCMCGPUError):
+        st.stats("imse")                              # the Geyer estimators need the draws
+    with pytest.raises(capi.MCMCGPUError):
+        capi.DeviceRun(dm, cfg, rngt, C, np.ones(d), engine="wave", stream_stats=True)
+    full.close(); st.close(); dm.close()
