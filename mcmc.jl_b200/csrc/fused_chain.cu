@@ -21,8 +21,10 @@ __device__ __forceinline__ double dotd(const double (&a)[D], int d) {
   return s;
 }
 
+// (the streaming variant carries 7 D more doubles: capped at the 146 registers that keep 7 CTAs = 14 warps on an SM, the
+//  residency 65 536 chains need for a single round of CTAs)
 template <int FAM, int D, bool STREAM>
-__global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedArgs A) {
+__global__ void __launch_bounds__(FUSED_THREADS, (STREAM && D <= 4) ? 7 : 0) fused_chain_kernel(const FusedArgs A) {
   extern __shared__ double sh_series[];
   const ModelDev& M = A.M;
   const SamplerDev& S = A.S;
@@ -56,6 +58,11 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
     return A.inj_uniforms ? A.inj_uniforms[i * Cp + c] : philox_uniform(R.seed, gchain, (uint32_t)i);
   };
   int64_t kept = 0;
+  // keep / thin bookkeeping without a 64-bit modulo or multiply per step: the step index of the next kept draw and the running
+  // offsets of its slots (i runs 1, 2, ...: `i == next_keep` is in(i, first:step:last), SerialMC.jl:49)
+  int64_t next_keep = R.first;
+  int64_t off_v = c, off_s = c;                 // offsets into the [S][d][Cp] and [S][Cp] arrays
+  const int64_t row_v = (int64_t)d * Cp;
   // streamed summaries (stream_stats): per parameter the serial sum of the draws (the mean of src/stats/mean.jl:6, bit for bit),
   // one-pass sums shifted by the first kept draw for Base.var, and the batch sums of mcvar_bm (var.jl:20-26)
   // (a template parameter: the 7 D accumulators must not cost the draw-storing kernel its registers)
@@ -68,7 +75,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
   for (int j = 0; j < DS; j++) { st_k[j] = 0.0; st_sx[j] = 0.0; st_sy[j] = 0.0; st_syy[j] = 0.0; st_bs[j] = 0.0; st_sb[j] = 0.0; st_sbb[j] = 0.0; }
   auto store = [&](int64_t i, const double (&pp)[D], double plt, const double (&pg)[D], bool has_grad, bool acc,
                    double eps, int nl) {
-    if (!in_range(i, R.first, R.step, R.last)) return;
+    if (i != next_keep || i > R.last) return;
+    next_keep += R.step;
     if (streaming) {
       if (kept == 0) {
 #pragma unroll
@@ -89,22 +97,22 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
         st_inb = 0; st_nb++;
       }
       st_acc += acc ? 1 : 0;
-      if (A.eps) A.eps[kept * Cp + c] = eps;
-      if (A.nleaps) A.nleaps[kept * Cp + c] = nl;
-      kept++;
+      if (A.eps) A.eps[off_s] = eps;
+      if (A.nleaps) A.nleaps[off_s] = nl;
+      kept++; off_s += Cp;
       return;
     }
 #pragma unroll
-    for (int j = 0; j < D; j++) if (j < d) A.samples[(kept * d + j) * Cp + c] = pp[j];
+    for (int j = 0; j < D; j++) if (j < d) A.samples[off_v + (int64_t)j * Cp] = pp[j];
     if (A.grads) {
 #pragma unroll
-      for (int j = 0; j < D; j++) if (j < d) A.grads[(kept * d + j) * Cp + c] = has_grad ? pg[j] : CUDART_NAN;
+      for (int j = 0; j < D; j++) if (j < d) A.grads[off_v + (int64_t)j * Cp] = has_grad ? pg[j] : CUDART_NAN;
     }
-    A.accept[kept * Cp + c] = acc ? 1 : 0;
-    if (A.logtarget) A.logtarget[kept * Cp + c] = plt;
-    if (A.eps) A.eps[kept * Cp + c] = eps;
-    if (A.nleaps) A.nleaps[kept * Cp + c] = nl;
-    kept++;
+    A.accept[off_s] = acc ? 1 : 0;
+    if (A.logtarget) A.logtarget[off_s] = plt;
+    if (A.eps) A.eps[off_s] = eps;
+    if (A.nleaps) A.nleaps[off_s] = nl;
+    kept++; off_v += row_v; off_s += Cp;
   };
 
   double pars[D], grad[D];
@@ -327,9 +335,9 @@ __global__ void __launch_bounds__(FUSED_THREADS) fused_chain_kernel(const FusedA
       bool acc; double pacc = 0.0;
       if (da) { pacc = isnan(e) ? 0.0 : (e < 1.0 ? e : 1.0); acc = u < pacc; }  // HMCDA.jl:120-121 (NaN => 0: documented)
       else acc = u < e;                                                          // HMC.jl:154
-      if (A.rb && in_range(i, R.first, R.step, R.last)) {                       // (sample + sum_k w_k pars_k)/(nleaps+1), mean.jl:24-30
+      if (A.rb && i == next_keep && i <= R.last) {                             // (sample + sum_k w_k pars_k)/(nleaps+1), mean.jl:24-30
 #pragma unroll
-        for (int j = 0; j < D; j++) if (j < d) A.rb[(kept * d + j) * Cp + c] = ((acc ? p[j] : pars[j]) + rbacc[j]) / (double)(nLeaps + 1);
+        for (int j = 0; j < D; j++) if (j < d) A.rb[off_v + (int64_t)j * Cp] = ((acc ? p[j] : pars[j]) + rbacc[j]) / (double)(nLeaps + 1);
       }
       if (acc) {
         store(i, p, plt, g, true, true, eps, (int)nLeaps);
