@@ -49,7 +49,7 @@ extern "C" {
 #define MCMCGPU_MALA 1
 #define MCMCGPU_HMC 2
 #define MCMCGPU_HMCDA 3
-#define MCMCGPU_RAM 4          /* src/samplers/RAM.jl:24-36: scale, rate (robust adaptive Metropolis); d <= 8 fused, d <= 16 wave */
+#define MCMCGPU_RAM 4          /* src/samplers/RAM.jl:24-36: scale, rate (robust adaptive Metropolis); d <= 8 fused, d <= 128 wave */
 
 /* engines */
 #define MCMCGPU_ENGINE_AUTO 0

@@ -98,7 +98,7 @@ struct mcmcgpu_run {
   double *stream = nullptr, *stream_accept = nullptr;   // streamed summaries (stream_stats) instead of stored draws
   double* init_lt = nullptr;   // log-target at the initial point (the `reset` evaluation of the population runners)
   const int64_t* chain_ids = nullptr;   // per-chain Philox keys (population runners that regroup replicas); not owned
-  double *ram_S = nullptr, *ram_al = nullptr;
+  double *ram_S = nullptr, *ram_al = nullptr, *ram_Sb = nullptr, *ram_scratch = nullptr;
   uint8_t* ram_pending = nullptr;
   double *q = nullptr, *part = nullptr, *red = nullptr, *cur_pars = nullptr, *cur_grad = nullptr, *cur_lt = nullptr,
          *mom = nullptr, *H0 = nullptr, *eps_cur = nullptr, *da_leapstep = nullptr, *da_dual = nullptr, *da_dualH = nullptr,
@@ -495,7 +495,7 @@ static int run_create_impl(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   if (engine != MCMCGPU_ENGINE_FUSED && engine != MCMCGPU_ENGINE_WAVE) { delete R; return fail(MCMCGPU_E_ARG, "unknown engine"); }
   R->engine = engine;
   R->has_diag = (s->kind == MCMCGPU_HMCDA) || (s->kind == MCMCGPU_RAM) || s->tuner_on;
-  if (s->kind == MCMCGPU_RAM && engine == MCMCGPU_ENGINE_WAVE && d > RAM_WAVE_MAX_D) { delete R; return fail(MCMCGPU_E_ARG, "RAM supports d <= 16"); }
+  if (s->kind == MCMCGPU_RAM && engine == MCMCGPU_ENGINE_WAVE && d > RAM_BIG_MAX_D) { delete R; return fail(MCMCGPU_E_ARG, "RAM supports d <= 128"); }
 #define RCU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { std::string msg = std::string("CUDA: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__); mcmcgpu_run_destroy(R); return fail(MCMCGPU_E_CUDA, msg); } } while (0)
   // inputs
   if (init_dev_cm) {
@@ -584,7 +584,12 @@ static int run_create_impl(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     RCU(R->alloc(&R->need_ll, (size_t)Cp));
     RCU(R->alloc(&R->init_lt, (size_t)Cp));
     if (r->store_rb) RCU(R->alloc(&R->rb_acc, (size_t)(d * Cp)));
-    if (s->kind == MCMCGPU_RAM) {
+    if (s->kind == MCMCGPU_RAM && d > RAM_WAVE_MAX_D) {      // one CTA per chain: chain-major factor + 3 work matrices per chain
+      RCU(R->alloc(&R->ram_Sb, (size_t)(C * d * d)));
+      RCU(R->alloc(&R->ram_scratch, (size_t)(3 * C * d * d), false));
+      RCU(R->alloc(&R->ram_al, (size_t)Cp));
+      RCU(R->alloc(&R->ram_pending, (size_t)Cp));
+    } else if (s->kind == MCMCGPU_RAM) {
       RCU(R->alloc(&R->ram_S, (size_t)(d * d * Cp)));
       RCU(R->alloc(&R->ram_al, (size_t)Cp));
       RCU(R->alloc(&R->ram_pending, (size_t)Cp));
@@ -675,7 +680,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     W.phase = R->phase; W.leap = R->leap; W.nleaps_cur = R->nleaps_cur; W.istep = R->istep; W.kept = R->kept;
     W.eps_cur = R->eps_cur; W.da_leapstep = R->da_leapstep; W.da_dual = R->da_dual; W.da_dualH = R->da_dualH;
     W.tn_step = R->tn_step; W.tn_nleaps = R->tn_nleaps; W.tn_acc = R->tn_acc; W.tn_prop = R->tn_prop;
-    W.ram_S = R->ram_S; W.ram_al = R->ram_al; W.ram_pending = R->ram_pending;
+    W.ram_S = R->ram_S; W.ram_al = R->ram_al; W.ram_pending = R->ram_pending; W.ram_Sb = R->ram_Sb; W.ram_scratch = R->ram_scratch;
     W.need_ll = R->need_ll; W.status = R->status; W.remaining = R->remaining; W.n_evals = R->n_evals;
     W.init = R->init; W.scale = R->scale; W.inj_normals = R->inj_normals; W.inj_uniforms = R->inj_uniforms;
     W.samples = R->samples; W.grads = R->grads; W.accept = R->accept; W.logtarget = R->logtarget;

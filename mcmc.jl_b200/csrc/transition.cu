@@ -177,7 +177,8 @@ __device__ int transition_chain(const WaveArgs& W, const int64_t c, const bool i
     double diag = CUDART_NAN;
     if (kind == MCMCGPU_RAM) {
       diag = 0.0;
-      for (int64_t j = 0; j < d; j++) diag += W.ram_S[(j * d + j) * Cp + c];     // "scale" => trace(S) (RAM.jl:65,69)
+      if (W.ram_Sb) { for (int64_t j = 0; j < d; j++) diag += W.ram_Sb[(c * d + j) * d + j]; }
+      else for (int64_t j = 0; j < d; j++) diag += W.ram_S[(j * d + j) * Cp + c];     // "scale" => trace(S) (RAM.jl:65,69)
       const double er = exp(ratio);
       W.ram_al[c] = isnan(er) ? 0.0 : (er < 1.0 ? er : 1.0);                     // min(1, exp(ratio)) (RAM.jl:76); NaN => 0
       W.ram_pending[c] = 1;
@@ -845,8 +846,115 @@ __global__ void __launch_bounds__(128) ram_kernel(const WaveArgs W, int init) {
   W.phase[c] = PH_RWM;
 }
 
+// RAM for d > RAM_WAVE_MAX_D: one CTA per chain; the factor and three d x d work matrices live in global memory (L2).
+// Every matrix element is formed by ONE thread with the reference's serial sum over k (RAM.jl:76-78 restated literally:
+// A = I + eta (alpha - rate) z z'/|z|^2, B = S A, M = B S', S = chol(M)' column by column), so the result does not depend
+// on the thread count and equals the one-thread kernel's -- and the oracle's -- operation for operation.
+constexpr int RAMB_THREADS = 256;
+__global__ void __launch_bounds__(RAMB_THREADS) ram_big_kernel(const WaveArgs W, int init) {
+  const int64_t c = blockIdx.x;
+  const RunnerDev& R = W.R;
+  const int d = (int)W.M.d, tid = threadIdx.x;
+  const int64_t Cp = R.Cp, dd = (int64_t)d * d;
+  double* S = W.ram_Sb + c * dd;
+  double* A = W.ram_scratch + c * 3 * dd;
+  double* B = A + dd;
+  double* Mx = B + dd;
+  __shared__ double z[RAM_BIG_MAX_D];
+  __shared__ double s_scal[2];
+  if (init) {                                                   // RAM.jl:50,55: S = diag(model.scale * sampler.scale)
+    for (int64_t e = tid; e < dd; e += RAMB_THREADS) { const int a = (int)(e / d), b = (int)(e % d); S[e] = (a == b) ? W.scale[a] * W.S.scale : 0.0; }
+    if (tid == 0) W.ram_pending[c] = 0;
+    return;
+  }
+  const int ph = W.phase[c];
+  const bool pending = W.ram_pending[c] != 0;
+  if (!pending && ph != PH_RAM_BEGIN) return;
+  if (pending) {                                                // RAM.jl:73-78 for the step just decided
+    for (int a = tid; a < d; a += RAMB_THREADS) z[a] = W.mom[(int64_t)a * Cp + c];
+    __syncthreads();
+    if (tid == 0) {
+      const int64_t i = W.istep[c] - 1;
+      double eta = (double)d * pow((double)i, -2.0 / 3.0);
+      if (!(eta < 1.0)) eta = 1.0;
+      double zz = 0.0;
+      for (int a = 0; a < d; a++) zz += z[a] * z[a];
+      s_scal[0] = zz; s_scal[1] = eta * (W.ram_al[c] - W.S.rate);
+    }
+    __syncthreads();
+    const double zz = s_scal[0];
+    const int64_t ii = W.istep[c] - 1;
+    double eta = (double)d * pow((double)ii, -2.0 / 3.0);
+    if (!(eta < 1.0)) eta = 1.0;
+    const double dal = W.ram_al[c] - W.S.rate;
+    for (int64_t e = tid; e < dd; e += RAMB_THREADS) {
+      const int a = (int)(e / d), b = (int)(e % d);
+      A[e] = ((a == b) ? 1.0 : 0.0) + (z[a] * z[b]) / zz * eta * dal;
+    }
+    __syncthreads();
+    for (int64_t e = tid; e < dd; e += RAMB_THREADS) {          // B = S * A
+      const int a = (int)(e / d), b = (int)(e % d);
+      double s2 = 0.0;
+      for (int k = 0; k < d; k++) s2 += S[a * d + k] * A[k * d + b];
+      B[e] = s2;
+    }
+    __syncthreads();
+    for (int64_t e = tid; e < dd; e += RAMB_THREADS) {          // M = B * S'
+      const int a = (int)(e / d), b = (int)(e % d);
+      double s2 = 0.0;
+      for (int k = 0; k < d; k++) s2 += B[a * d + k] * S[b * d + k];
+      Mx[e] = s2;
+    }
+    __syncthreads();
+    // S = chol(M)' (lower factor), column by column: the diagonal first, then the rows below it in parallel; each element is
+    // M[a][b] - sum_{k<b} S[a][k] S[b][k] in the reference's order
+    for (int b = 0; b < d; b++) {
+      if (tid == 0) {
+        double s2 = Mx[b * d + b];
+        for (int k = 0; k < b; k++) s2 -= S[b * d + k] * S[b * d + k];
+        S[b * d + b] = sqrt(s2);
+      }
+      __syncthreads();
+      const double dg = S[b * d + b];
+      for (int a = b + 1 + tid; a < d; a += RAMB_THREADS) {
+        double s2 = Mx[a * d + b];
+        for (int k = 0; k < b; k++) s2 -= S[a * d + k] * S[b * d + k];
+        S[a * d + b] = s2 / dg;
+      }
+      for (int a = tid; a < b; a += RAMB_THREADS) S[a * d + b] = 0.0;     // upper part (b > a)
+      __syncthreads();
+    }
+    if (tid == 0) W.ram_pending[c] = 0;
+  }
+  if (ph != PH_RAM_BEGIN) return;
+  // RAM.jl:59-60: rvec = randn(d); proposedPars = pars + S * rvec
+  const int64_t i = W.istep[c];
+  const uint64_t gchain = W.chain_ids ? (uint64_t)W.chain_ids[c] : (uint64_t)(R.chain_offset + c);
+  __syncthreads();
+  for (int k = tid; 2 * k < d; k += RAMB_THREADS) {
+    double z0, z1 = 0.0;
+    if (W.inj_normals) {
+      z0 = W.inj_normals[(i * d + 2 * k) * Cp + c];
+      if (2 * k + 1 < d) z1 = W.inj_normals[(i * d + 2 * k + 1) * Cp + c];
+    } else {
+      philox_normal_pair(R.seed, gchain, (uint32_t)i, (uint32_t)k, z0, z1);
+    }
+    z[2 * k] = z0;
+    if (2 * k + 1 < d) z[2 * k + 1] = z1;
+  }
+  __syncthreads();
+  for (int a = tid; a < d; a += RAMB_THREADS) {
+    double acc = 0.0;
+    for (int b = 0; b < d; b++) acc += S[a * d + b] * z[b];
+    W.q[(int64_t)a * Cp + c] = W.cur_pars[(int64_t)a * Cp + c] + acc;
+    W.mom[(int64_t)a * Cp + c] = z[a];
+  }
+  if (tid == 0) { W.need_ll[c] = 1; W.eps_cur[c] = W.S.scale; W.phase[c] = PH_RWM; }
+}
+
 cudaError_t launch_ram(const WaveArgs& W, bool init, cudaStream_t st) {
-  ram_kernel<<<(unsigned)((W.R.C + 127) / 128), 128, 0, st>>>(W, init ? 1 : 0);
+  if (W.ram_Sb) ram_big_kernel<<<(unsigned)W.R.C, RAMB_THREADS, 0, st>>>(W, init ? 1 : 0);
+  else ram_kernel<<<(unsigned)((W.R.C + 127) / 128), 128, 0, st>>>(W, init ? 1 : 0);
   return cudaGetLastError();
 }
 

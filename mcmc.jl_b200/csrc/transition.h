@@ -31,7 +31,9 @@ struct WaveArgs {
   double *eps_cur;
   double *da_leapstep, *da_dual, *da_dualH;
   double *tn_step; int64_t *tn_nleaps, *tn_acc, *tn_prop;
-  double* ram_S;               // RAM: [d*d][Cp] lower-triangular proposal factor (row-major index a*d+b)
+  double* ram_S;               // RAM: [d*d][Cp] lower-triangular proposal factor (row-major index a*d+b), d <= RAM_WAVE_MAX_D
+  double* ram_Sb;              // RAM, d > RAM_WAVE_MAX_D: [C][d*d] chain-major factor (one CTA per chain), else null
+  double* ram_scratch;         // RAM, d > RAM_WAVE_MAX_D: [C][3][d*d] work matrices
   double* ram_al;              // RAM: min(1, exp(ratio)) of the step just decided
   uint8_t* ram_pending;        // RAM: factor update pending for that step
   uint8_t* need_ll;
@@ -50,7 +52,8 @@ struct WaveArgs {
 };
 
 cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st);
-constexpr int RAM_WAVE_MAX_D = 16;
+constexpr int RAM_WAVE_MAX_D = 16;    // one thread per chain, factor in local memory; larger d: one CTA per chain (ram_big_kernel)
+constexpr int RAM_BIG_MAX_D = 128;
 cudaError_t launch_ram(const WaveArgs& W, bool init, cudaStream_t st);   // RAM.jl:50-60,73-78 for the wave engine
 // closed-form families through the wave engine: writes part[0][(d+2)][Cp] directly (final lt / grad)
 cudaError_t launch_eval_closed(const ModelDev& M, const double* q, double* part, int64_t C, int64_t Cp,

@@ -865,3 +865,23 @@ def test_streamed_summaries_match_the_two_pass_stats(capi, ctx, kind, skw):
     with pytest.raises(capi.MCMCGPUError):
         capi.DeviceRun(dm, cfg, rngt, C, np.ones(d), engine="wave", stream_stats=True)
     full.close(); st.close(); dm.close()
+
+
+@pytest.mark.parametrize("fam,d,N", [("normal_dsl", 20, 0), ("logistic", 40, 600), ("linear", 128, 500)])
+def test_ram_large_d(O, capi, ctx, fam, d, N):
+    """RAM beyond 16 parameters (RAM.jl:41-80 has no size limit): one CTA per chain, every matrix element summed by one
+    thread in the reference's order -- same arithmetic as the one-thread kernel, so the same tolerance (pow's last bit)."""
+    C, rngt = 12, (1, 1, 60)
+    if N:
+        X, y, hy, b0 = make_regression(fam, N, d, 9)
+        init = b0
+    else:
+        X, y, hy, init = None, None, (0.5, 2.0), np.ones(d)
+    out, diag, refs, _ = _run_both(O, capi, ctx, fam, d, X, y, hy, "RAM", dict(scale=0.02 if N else 1.0, rate=0.234), rngt, C, init, "wave")
+    for c in range(C):
+        assert np.array_equal(refs[c]["accept"], out["accept"][c]), c
+        assert np.allclose(refs[c]["samples"], out["samples"][c], rtol=1e-8, atol=1e-11), c
+        assert np.allclose(diag[0][c], refs[c]["eps"], rtol=1e-8), c
+    assert 0 < out["accept"].mean() < 1
+    with pytest.raises(capi.MCMCGPUError):
+        capi.DeviceRun(capi.DeviceModel(ctx, "normal_dsl", 129, hyper=(0.0, 1.0)), capi.sampler_cfg("RAM", scale=1.0, rate=0.234), (1, 1, 5), 2, np.ones(129), engine="wave")
