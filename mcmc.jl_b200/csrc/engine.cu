@@ -105,7 +105,7 @@ struct mcmcgpu_run {
          *tn_step = nullptr;
   int32_t *phase = nullptr, *leap = nullptr, *nleaps_cur = nullptr, *remaining = nullptr;
   int64_t *istep = nullptr, *kept = nullptr, *tn_nleaps = nullptr, *tn_acc = nullptr, *tn_prop = nullptr;
-  uint8_t* need_ll = nullptr;
+  uint8_t *need_ll = nullptr, *k1_done = nullptr;
   int nsplit = 1;
   std::vector<void*> owned, owned_big;
   template <typename T>
@@ -358,8 +358,10 @@ static int eval_wave(mcmcgpu_model* m, const double* q, double* part, double* re
     a.q = q; a.part = part; a.Cp = Cp; a.nsplit = nsplit; a.need_grad = need_grad ? 1 : 0;
     a.need_ll = need_ll; a.phase = phase; a.remaining = remaining; a.debug = (int32_t)m->ctx->k1_debug;
     a.fuse_leap = 0; a.leap = nullptr; a.nleaps_cur = nullptr; a.eps_cur = nullptr; a.mom = nullptr; a.q_rw = nullptr;
+    a.need_ll_rw = nullptr; a.k1_done = nullptr; a.n_evals = nullptr;
     if (fuse) {      // interior leapfrogs made by the likelihood kernel itself (run_fuses_leap)
       a.fuse_leap = 1; a.leap = fuse->leap; a.nleaps_cur = fuse->nleaps_cur; a.eps_cur = fuse->eps_cur; a.mom = fuse->mom; a.q_rw = fuse->q;
+      a.need_ll_rw = fuse->need_ll; a.k1_done = fuse->k1_done; a.n_evals = fuse->n_evals;
     }
     CU(k1_launch(a, st));
     if (ev_k1_done) CU(cudaEventRecord(ev_k1_done, st));   // what follows (split fold, all-reduce) is timed apart: run_info.comm_ms
@@ -582,6 +584,7 @@ static int run_create_impl(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
     RCU(R->alloc(&R->tn_acc, (size_t)Cp));
     RCU(R->alloc(&R->tn_prop, (size_t)Cp));
     RCU(R->alloc(&R->need_ll, (size_t)Cp));
+    RCU(R->alloc(&R->k1_done, (size_t)Cp));
     RCU(R->alloc(&R->init_lt, (size_t)Cp));
     if (r->store_rb) RCU(R->alloc(&R->rb_acc, (size_t)(d * Cp)));
     if (s->kind == MCMCGPU_RAM && d > RAM_WAVE_MAX_D) {      // one CTA per chain: chain-major factor + 3 work matrices per chain
@@ -673,7 +676,12 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
     WaveArgs W;
     W.M = m->dev(); W.S = sampler_dev(R); W.R = runner_dev(R);
     const mcmcgpu_run* fuse = run_fuses_leap(R) ? R : nullptr;
-    W.fused_interior = fuse ? 1 : 0;
+    W.fused_interior = fuse ? 1 : 0; W.k1_done = R->k1_done;
+    // fixed-length HMC with the fused interior leapfrog: all chains of a run move in lockstep (they pause only between
+    // steps), so on the waves that evaluate an interior leapfrog -- all but every nleaps-th -- the likelihood kernel does
+    // everything and the transition kernel is not launched at all
+    const bool lockstep = fuse && R->s.kind == MCMCGPU_HMC && !R->s.tuner_on;
+    int64_t leap_pos = 0;                    // evaluations already made in the current step (0 .. nleaps-1)
     W.nsplit = R->nsplit; W.resume = 0; W.restore_da = R->restore_da ? 1 : 0; W.step0 = R->step0; W.step_limit = upto;
     W.q = R->q; W.part = R->part;
     W.cur_pars = R->cur_pars; W.cur_grad = R->cur_grad; W.cur_lt = R->cur_lt; W.mom = R->mom; W.H0 = R->H0;
@@ -755,6 +763,7 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
             for (int64_t rp = 0; rp < reps; rp++) CU(cudaGraphLaunch(gexec, st));
             waves += reps * GW;
             launches += reps * GW * per_wave;
+            if (lockstep) leap_pos = (leap_pos + reps * GW) % (int64_t)R->s.nleaps;   // the replayed waves ran the transition kernel every time
             CU(cudaStreamSynchronize(st));
           } else {
             for (;;) {
@@ -777,9 +786,11 @@ static int execute_impl(mcmcgpu_run* R, int64_t nsteps, mcmcgpu_run_info* info) 
       if (rc != MCMCGPU_OK) return rc;
       if (c->time_eval) { CU(cudaEventRecord(a1, st)); evs.push_back(a0); evs.push_back(am); evs.push_back(a1); }
       W.part = pp; W.nsplit = ns;
-      CU(launch_transition(W, st));
+      bool interior_wave = false;
+      if (lockstep && !first) { interior_wave = (leap_pos + 1 < (int64_t)R->s.nleaps); leap_pos = (leap_pos + 1) % (int64_t)R->s.nleaps; }
+      if (!interior_wave) { CU(launch_transition(W, st)); launches++; }
       if (is_ram) { CU(launch_ram(W, false, st)); launches++; }
-      launches += 2 + (m->row_sharded ? 1 : 0);
+      launches += 1 + (m->row_sharded ? 1 : 0);
       waves++;
       first = false;
       if (known >= 0) { if (waves >= known) break; }

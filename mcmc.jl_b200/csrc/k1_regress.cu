@@ -612,7 +612,17 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
     // round-to-nearest intrinsics: this translation unit allows multiply-add contraction and the update must round as
     // the transition kernel's does (HMC.jl:95-98: (0.5 g) eps, m += ., p += eps m).
     bool fused = false;
-    if (a.fuse_leap) fused = (a.phase[mychain] == PH_LEAP_K1) && (a.leap[mychain] + 2 <= a.nleaps_cur[mychain]);
+    int lp = 0, nlc = 0;
+    if (a.fuse_leap) { lp = a.leap[mychain]; nlc = a.nleaps_cur[mychain]; fused = (a.phase[mychain] == PH_LEAP_K1) && (lp + 2 <= nlc); }
+    if (a.fuse_leap) {     // the chain's counters too: on a wave of interior leapfrogs the transition kernel need not run at all
+      const unsigned done = __ballot_sync(0xffffffffu, fused && t == 0);
+      if (t == 0) a.k1_done[mychain] = fused ? 1 : 0;      // written for every evaluated chain, every wave: never stale
+      if (fused && t == 0) {
+        a.leap[mychain] = lp + 1;
+        a.need_ll_rw[mychain] = (lp + 2 == nlc) ? 1 : 0;
+      }
+      if (lane == 0 && done) atomicAdd(a.n_evals, (unsigned long long)__popc(done));
+    }
     if (fused) {
       const double eps = a.eps_cur[mychain];
       const bool linlog = (FAM == MCMCGPU_FAM_LINEAR || FAM == MCMCGPU_FAM_LOGISTIC);

@@ -41,7 +41,10 @@ struct K1Args {
   // leapfrog and the start of the next one (HMC.jl:98,95,96) right here instead of a round trip of X'r through `part`
   // and a pass of the transition kernel over mom / q; the transition kernel then only advances the chain's counters.
   int32_t fuse_leap;
-  const int32_t* leap;       // [Cp]
+  int32_t* leap;             // [Cp]  advanced here for the chains whose leapfrog this kernel completes
+  uint8_t* need_ll_rw;       // [Cp]  their flag for the NEXT evaluation (the trajectory's last one needs the value)
+  uint8_t* k1_done;          // [Cp]  set for those chains: the transition kernel has nothing left to do for them this wave
+  unsigned long long* n_evals;   // evaluation counter of the run (one per such chain is added here)
   const int32_t* nleaps_cur; // [Cp]
   const double* eps_cur;     // [Cp]
   double* mom;               // [d][Cp]

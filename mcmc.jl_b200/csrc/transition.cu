@@ -469,6 +469,8 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 4) transition_coop_kern
     else if (ph == PH_RWM) mode = CM_RWM;
     else if (ph == PH_MALA) mode = CM_MALA;
     else if (ph == PH_LEAP) mode = (W.leap[c] + 2 <= W.nleaps_cur[c]) ? CM_INTERIOR : CM_FINAL;
+    // interior leapfrog completed (state and counters) by the likelihood kernel: nothing to do for this chain
+    if (W.fused_interior && !W.resume && W.k1_done[c]) mode = CM_NONE;
   }
   const double eps_cur = (mode == CM_INTERIOR || mode == CM_FINAL || mode == CM_MALA) ? W.eps_cur[c] : 0.0;
   EvalFin F; F.fam = M.family; F.lt = CUDART_NAN; F.oos = false; F.ginv = 0.0;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 4) transition_coop_kern
   __syncthreads();
 
   // ---- stage A: interior leapfrogs ----
-  if (mode == CM_INTERIOR && !W.fused_interior) {
+  if (mode == CM_INTERIOR) {
     // CO_UNROLL elements per pass, all loads first (the stores to q / mom could alias them as far as the compiler knows)
     for (int64_t j0 = grp; j0 < d; j0 += CO_GROUPS * CO_UNROLL) {
       double gj[CO_UNROLL], m[CO_UNROLL], p[CO_UNROLL];

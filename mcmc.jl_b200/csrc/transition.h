@@ -21,6 +21,8 @@ struct WaveArgs {
   int64_t step0;               // chains start at step step0 + 1
   int64_t step_limit;          // chains pause before starting a step > step_limit
   int32_t fused_interior;      // 1: the likelihood kernel has already made the interior leapfrog updates (K1Args::fuse_leap)
+  uint8_t* k1_done;            // [Cp] with fused_interior: 1 for the chains the likelihood kernel has fully advanced this wave
+                               // (it writes the flag of every chain it evaluates, every wave)
   // evaluation in/out
   double* q;                   // [d][Cp]
   const double* part;          // [nsplit][d+2][Cp]

@@ -885,3 +885,60 @@ def test_ram_large_d(O, capi, ctx, fam, d, N):
     assert 0 < out["accept"].mean() < 1
     with pytest.raises(capi.MCMCGPUError):
         capi.DeviceRun(capi.DeviceModel(ctx, "normal_dsl", 129, hyper=(0.0, 1.0)), capi.sampler_cfg("RAM", scale=1.0, rate=0.234), (1, 1, 5), 2, np.ones(129), engine="wave")
+
+
+@pytest.mark.parametrize("fam", ["logistic", "probit", "linear"])
+@pytest.mark.parametrize("kind,skw,rngt", [("HMC", dict(scale=0.02, nleaps=5), (11, 1, 60)),
+                                           ("HMC", dict(scale=0.02, nleaps=1), (1, 1, 40)),
+                                           ("HMC", dict(scale=0.02, nleaps=3, tuner=dict(target_rate=0.8, adapt_step=10)), (31, 2, 70)),
+                                           ("HMCDA", dict(len=0.1, max_leaps=64), (1, 1, 40)),
+                                           ("MALA", dict(scale=0.001), (1, 1, 40))])
+def test_unsplit_likelihood_fuses_the_leapfrog(O, capi, ctx, fam, kind, skw, rngt):
+    """one row split (the launch-bound small-N regime; forced here): the likelihood kernel makes the interior leapfrog
+    updates and advances the chains' counters itself, the transition kernel is skipped on those waves (fixed-length HMC)
+    or ignores those chains (HMCDA, tuned HMC).  Draw-matched against the oracle, stepwise == one call, evaluation counts."""
+    N, d, C = 700, 10, 70
+    X, y, hy, _ = make_regression(fam, N, d, 6)
+    ctx.set_option("force_splits", 1)
+    try:
+        kw = dict(skw)
+        if kind == "HMCDA":                      # realistic restored step sizes (the adaptation from eps = 1 is chaotic)
+            rng = np.random.default_rng(1)
+            eps = rng.uniform(0.01, 0.03, size=C)
+            om = O.Model(fam, d, X, y, hy); dm = capi.DeviceModel(ctx, fam, d, X, y, hy)
+            last = rngt[2]
+            zn = rng.standard_normal((C, last + 1, d)); un = rng.random((C, last + 1))
+            run = capi.DeviceRun(dm, capi.sampler_cfg(kind, **kw), rngt, C, np.zeros(d), normals=zn, uniforms=un, engine="wave")
+            run.set_state(0, eps, eps, np.zeros(C))
+            info = run.execute(); out = run.fetch(); geps, gnl = run.fetch_diag(); run.close(); dm.close()
+            refs = [O.run_chain(om, O.sampler(kind, da_state=[eps[c], eps[c], 0.0], **kw), rngt, np.zeros(d), None, zn[c], un[c]) for c in range(C)]
+            assert info["n_grad_evals"] == C + gnl.sum() and len(np.unique(gnl)) >= 3
+        else:
+            out, diag, refs, info = _run_both(O, capi, ctx, fam, d, X, y, hy, kind, kw, rngt, C, np.zeros(d), "wave")
+            if kind == "HMC" and "tuner" not in kw:
+                assert info["n_grad_evals"] == C * (1 + rngt[2] * kw["nleaps"])
+                assert info["n_launches"] < 2 * info["n_waves"] or kw["nleaps"] == 1      # no transition launch on interior waves
+        gs = np.abs(X).sum(0)
+        for c in range(C):
+            assert np.array_equal(refs[c]["accept"], out["accept"][c]), (fam, kind, c)
+            assert np.allclose(refs[c]["samples"], out["samples"][c], rtol=1e-9, atol=1e-12)
+            assert np.allclose(refs[c]["logtarget"], out["logtarget"][c], rtol=1e-11, atol=0)
+            assert np.all(np.abs(refs[c]["grads"] - out["grads"][c]) <= 1e-9 * gs)
+        assert 0.2 < out["accept"].mean() <= 1.0
+        if kind == "HMC" and "tuner" not in kw:   # stepwise execution (pauses between steps) gives the same chains
+            dm = capi.DeviceModel(ctx, fam, d, X, y, hy)
+            a = capi.DeviceRun(dm, capi.sampler_cfg(kind, **kw), rngt, C, np.zeros(d), seed=3, engine="wave"); a.execute(); fa = a.fetch()
+            b = capi.DeviceRun(dm, capi.sampler_cfg(kind, **kw), rngt, C, np.zeros(d), seed=3, engine="wave")
+            for n in (3, 1, 20, 100):
+                b.execute_steps(n)
+            fb = b.fetch()
+            assert np.array_equal(fa["samples"], fb["samples"]) and np.array_equal(fa["accept"], fb["accept"])
+            ctx.set_option("fuse_leap", 0)     # and the unfused path (transition kernel does the update) gives the same bits
+            try:
+                u = capi.DeviceRun(dm, capi.sampler_cfg(kind, **kw), rngt, C, np.zeros(d), seed=3, engine="wave"); u.execute(); fu = u.fetch(); u.close()
+            finally:
+                ctx.set_option("fuse_leap", 1)
+            assert np.array_equal(fa["samples"], fu["samples"]) and np.array_equal(fa["accept"], fu["accept"])
+            a.close(); b.close(); dm.close()
+    finally:
+        ctx.set_option("force_splits", 0)
