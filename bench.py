@@ -563,12 +563,17 @@ def wave_block(B, name, wl, K, W, clock=False):
     B.ctx.set_option("time_eval", 1)
     ms_max, e2e_ms = B.max_over_ranks(ms, e2e_s * 1e3)
     (evals,) = B.sum_over_ranks(float(info["n_grad_evals"]))
+    ess = None
+    if rank == 0 and not B.args.no_ess:      # min-ESS per chain-step of this sampler on this target (pilot of the same chains)
+        sweep, sample = ess_pilot(B, dm, wl, init_state, set_state, rank * C, (None,), ce=min(256, C))
+        ess = dict(value=sweep[0]["ess_per_chain_step"] * C * world * K / (ms_max / 1e3), unit="min-ESS/s (min over parameters, summed over chains)",
+                   **{k: v for k, v in sweep[0].items() if k not in ("len", "nleaps", "min_ess_per_grad")}, sample=sample)
     dm.close()
     rf = B.k1_roofline(wl, C, info_t, ms_t)
     rf["share_of_step"] = info_t["eval_ms"] / ms                   # share of the (graph-replayed) step
     return dict(description=wl["desc"], N=wl["N"], d=d, chains_per_gpu=C, sampler=wl["sampler"], steps=K, warmup=W,
                 value=C * world * K / (ms_max / 1e3), unit="chain-steps/s", ms_per_step=ms_max / K,
-                grad_evals_per_s=evals / (ms_max / 1e3), accept_rate=acc, gpu_launches=int(info["n_launches"]), clocks=clocks,
+                grad_evals_per_s=evals / (ms_max / 1e3), accept_rate=acc, gpu_launches=int(info["n_launches"]), clocks=clocks, min_ess_per_s=ess,
                 e2e=dict(value=C * world * K / (e2e_ms / 1e3), unit="chain-steps/s", h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K),
                 roofline=dict(bound="tensor", achieved=rf["achieved"], peak=rf["peak"], unit="TFLOP/s", frac=rf["frac"],
                               ms_per_launch=rf["ms_per_launch"], share_of_step=rf["share_of_step"]))
@@ -619,6 +624,8 @@ def cfg2_block(B, wl, K, W, clock=False):
                 e2e=dict(value=C * world * Ks / (e2e_ms / 1e3), unit="chain-steps/s", h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K),
                 e2e_summaries=dict(value=C * world * Ks / (sum_ms / 1e3), unit="chain-steps/s", h2d_bytes_per_step=d * 8 / K,
                                    d2h_bytes_per_step=(5 * d + 1) * C * 8 / K, median_ess_per_step=float(np.median(st["ess"])) / Ks,
+                                   min_ess_per_s=float(np.median(st["ess"].min(axis=1))) / Ks * C * world * Ks / (ms_max / 1e3),
+                                   min_ess_note="median over chains of min over parameters of ess(vtype=:bm, batch length 100) per step x the device-timed chain-steps/s",
                                    note="stream_stats run: mean / var_iid / var_bm / ess(bm) / actime / acceptance accumulated in registers while "
                                         "sampling (mcmcgpu_runner_cfg.stream_stats), no draw is stored; only the d x C summaries cross PCIe"),
                 roofline=dict(bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm, traffic=None, kernel="fused_chain_kernel",

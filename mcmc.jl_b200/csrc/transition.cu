@@ -698,18 +698,29 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 4) transition_coop_kern
           philox_normal_pair(R.seed, gchain, (uint32_t)inext, (uint32_t)k, z0, z1);
         }
       }
+      // both elements of the pair: every load first, then every store (the stores go to arrays the loads read from as far
+      // as the compiler knows: interleaved, each load is issued only after the preceding store, four round trips per pair)
+      double pjv[2] = {0.0, 0.0}, gjv[2] = {0.0, 0.0};
 #pragma unroll
       for (int t2 = 0; t2 < 2; t2++) {
         const int64_t j = 2 * k + t2;
         if (j >= d) break;
-        double pj, gj = 0.0;
         if (acc) {
-          pj = q[j * Cp + c];
-          W.cur_pars[j * Cp + c] = pj;
-          if (need_grad_state) { gj = fin_grad(F, M, q, part, ns, Cp, c, j); W.cur_grad[j * Cp + c] = gj; }
+          pjv[t2] = q[j * Cp + c];
+          if (need_grad_state) gjv[t2] = fin_grad(F, M, q, part, ns, Cp, c, j);
         } else {
-          pj = W.cur_pars[j * Cp + c];
-          if (need_grad_state) gj = W.cur_grad[j * Cp + c];
+          pjv[t2] = W.cur_pars[j * Cp + c];
+          if (need_grad_state) gjv[t2] = W.cur_grad[j * Cp + c];
+        }
+      }
+#pragma unroll
+      for (int t2 = 0; t2 < 2; t2++) {
+        const int64_t j = 2 * k + t2;
+        if (j >= d) break;
+        const double pj = pjv[t2], gj = gjv[t2];
+        if (acc) {
+          W.cur_pars[j * Cp + c] = pj;
+          if (need_grad_state) W.cur_grad[j * Cp + c] = gj;
         }
         if (kk >= 0) {                    // the post-decision state is what is kept (SerialMC.jl:49-53)
           W.samples[(kk * d + j) * Cp + c] = pj;
