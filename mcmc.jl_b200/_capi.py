@@ -353,6 +353,7 @@ class DeviceRun(_Owned):
         r.store_grad, r.store_logtarget, r.engine = int(store_grad), int(store_logtarget), ENGINE[engine]
         r.store_rb = int(store_rb)
         r.stream_stats, r.stream_batchlen = int(stream_stats), int(stream_batchlen)
+        self.streaming = bool(stream_stats)
         if stream_stats:
             store_grad = store_logtarget = False
             r.store_grad = r.store_logtarget = 0

@@ -742,6 +742,10 @@ def actime(c, pars=None, vtype="imse", **kw):                              # ess
 
 
 def acceptance(c, lags=None, reject=False):                                # summary.jl:6-15
+    if isinstance(c, MCMCChainBatch) and c._run.streaming:        # GPUMC(store_draws=False): the rate was accumulated while sampling
+        assert lags is None, "a streamed run keeps no per-step accept flags"
+        rate = c.stats("iid")["accept_rate"]
+        return 100.0 - rate if reject else rate
     if isinstance(c, MCMCChainBatch):
         acc = c.arrays()["accept"].astype(np.float64)
     else:

@@ -207,3 +207,27 @@ def test_serialtemp_over_regression_models(O, capi, ctx, fam):
     assert len(visited) >= 2
     for m in dms:
         m.close()
+
+
+def test_host_api_population_and_streaming(O):
+    """the Python mirror drives the new paths: SeqMC / SerialTempMC over regression models (dispatch on family / size),
+    GPUMC(store_draws=False)"""
+    import mcmc_jl_b200 as mj
+    from conftest import make_regression
+    X, y, hy, b0 = make_regression("logistic", 300, 6, 51)
+    mods = [mj.model("logistic", X=X, Y=y, vars=b0, prior_sd=sd) for sd in (4.0, 2.0, 1.0)]
+    targets = [mods[i] * mj.RWM(0.05) * mj.SeqMC(steps=4, burnin=1) for i in range(3)]
+    parts = b0 + 0.1 * np.random.default_rng(0).standard_normal((150, 6))
+    chain = mj.run(targets, particles=list(parts), seed=2)
+    assert chain.samples.shape == (3 * 150, 6) and np.all(np.isfinite(chain.diagnostics["weigths"])) and chain.info["n_grad_evals"] == 150 * 4 * 3 * 2
+    temps = [mods[i] * mj.HMC(3, 0.05) * mj.SerialTempMC(steps=30, burnin=5, swapPeriod=3) for i in range(3)]
+    chains = mj.run(temps, nreplicas=8, seed=3)
+    assert len(chains) == 8 and chains[0].samples.shape == (25, 6) and set(np.unique(np.concatenate([c.diagnostics["task"] for c in chains]))) <= {1, 2, 3}
+    m = mj.model("normal", init=np.ones(3))
+    full = mj.run(m * mj.HMC(0.75) * mj.GPUMC(steps=1200, burnin=200, nchains=256, seed=5))
+    st = mj.run(m * mj.HMC(0.75) * mj.GPUMC(steps=1200, burnin=200, nchains=256, seed=5, store_draws=False))
+    assert np.array_equal(mj.mean(st), mj.mean(full)) and np.array_equal(mj.acceptance(st), mj.acceptance(full))
+    assert np.allclose(mj.var(st, vtype="bm"), mj.var(full, vtype="bm"), rtol=1e-10) and np.allclose(mj.ess(st, vtype="bm"), mj.ess(full, vtype="bm"), rtol=1e-10)
+    with pytest.raises(mj.MCMCGPUError):
+        st.arrays()
+    full.close(); st.close()
