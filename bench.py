@@ -33,6 +33,8 @@ Sub-blocks of the default (cfg4) run, each a driver-timed number for another BAS
              of the (d+2) x C partials per leapfrog; K1 ms/launch and fold+all-reduce ms/leapfrog from CUDA events; at
              N > 1 a sharded-vs-unsharded parity check runs first (`parity`).
 `strong`     (N > 1) cfg4 with 10 000 chains in TOTAL, chain-sharded: strong scaling of the headline.
+`population` (N > 1) SeqMC over regression models sharded over the GPUs (ncclAllGather per target) and SerialTempMC replicas sharded by
+             replica id, each checked against the single-GPU run of the same population (`*_sharded_parity`).
 """
 import argparse
 import json
@@ -526,6 +528,8 @@ def main():
             sh = max(1, args.shrink)
             line["row_sharded"] = row_sharded_block(B, dict(WORKLOADS["cfg5"], N=WORKLOADS["cfg5"]["N"] // sh), 3, 3, parity=world > 1)
             line["row_sharded"].pop("clocks", None)
+            if world > 1:
+                line["population"] = population_block(B)
             cfgs = {}
             w3 = dict(WORKLOADS["cfg3"]); w3["N"] //= sh; w3["chains"] //= sh
             cfgs["cfg3"] = wave_block(B, "cfg3", w3, 5, 3); cfgs["cfg3"].pop("clocks")
@@ -716,6 +720,51 @@ def row_shard_parity(B):
     full.close(); shard.close()
     return ("ok" if int(ok.item()) == 1 else "FAILED"), dict(max_rel_err_logtarget=err_lt, max_rel_err_gradient=err_g,
                                                               accept_rate=float(outs[1]["accept"].mean()))
+
+
+def population_block(B):
+    """population runners over GPUs (N > 1): a SeqMC population of regression models sharded over the ranks (one ncclAllGather of
+    particle states and weights per target, every rank resampling its slots from the global weights) and SerialTempMC replicas
+    sharded by global replica id (no communication) must reproduce the single-GPU run of the same population."""
+    capi, torch, dist, rank, world = B.capi, B.torch, B.dist, B.rank, B.world
+    N, d, npl, nrl = 600, 8, 128, 64
+    X, y, b0 = _small_regression(N, d, 7)
+    hys = [(4.0, -1.0), (2.0, -1.0), (1.0, -1.0)]
+    smp = [capi.sampler_cfg("RWM", scale=0.03), capi.sampler_cfg("MALA", scale=0.002), capi.sampler_cfg("HMC", scale=0.04, nleaps=3)]
+    solo = capi.Context(B.local)                      # no communicator: the whole population on this GPU
+    out = {}
+    try:
+        shard_m = [capi.DeviceModel(B.ctx, "logistic", d, X, y, h) for h in hys]
+        solo_m = [capi.DeviceModel(solo, "logistic", d, X, y, h) for h in hys]
+        rng = np.random.default_rng(13)
+        gp = npl * world
+        parts = b0 + 0.1 * rng.standard_normal((gp, d))
+        steps, burnin = 4, 1
+        trig = 1e300                                   # resample after every target: the all-gathered weights decide every slot
+        t0 = time.perf_counter()
+        sh = B.ctx.run_seqmc_models(shard_m, smp, steps, burnin, trig, parts[rank * npl:(rank + 1) * npl], seed=5)
+        t_sh = time.perf_counter() - t0
+        ref = solo.run_seqmc_models(solo_m, smp, steps, burnin, trig, parts, seed=5)
+        rs = ref["samples"].reshape(steps - burnin, gp, d)[:, rank * npl:(rank + 1) * npl].reshape(-1, d)
+        rw = ref["weights"].reshape(steps - burnin, gp)[:, rank * npl:(rank + 1) * npl].reshape(-1)
+        ok_seq = sh["n_resamples"] == ref["n_resamples"] and np.allclose(sh["samples"], rs, rtol=1e-9, atol=1e-12) and np.allclose(sh["weights"], rw, rtol=1e-7)
+        inits = b0 + 0.05 * rng.standard_normal((3, d))
+        tsteps, tburn, swap = 30, 5, 3
+        a = B.ctx.run_serialtemp_models(shard_m, smp, tsteps, tburn, swap, nrl, inits, seed=6, rep_offset=rank * nrl)
+        b = solo.run_serialtemp_models(solo_m, smp, tsteps, tburn, swap, nrl * world, inits, seed=6)
+        ok_tmp = np.array_equal(a["at"], b["at"][rank * nrl:(rank + 1) * nrl]) and np.allclose(a["samples"], b["samples"][rank * nrl:(rank + 1) * nrl], rtol=1e-9, atol=1e-12)
+        flags = torch.tensor([int(ok_seq), int(ok_tmp)], device="cuda")
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        out = dict(seqmc_sharded_parity="ok" if int(flags[0]) else "FAILED", serialtemp_sharded_parity="ok" if int(flags[1]) else "FAILED",
+                   models="3 logistic regressions N=600 d=8 (prior sd 4, 2, 1), tasks RWM / MALA / HMC(3 leapfrogs)",
+                   seqmc=dict(particles_total=gp, targets=3, iterations=steps, n_resamples=int(sh["n_resamples"]), seconds=t_sh,
+                              allgather_bytes_per_target=(d + 2) * ((npl + 63) // 64 * 64) * 8 * world),
+                   serialtemp=dict(replicas_total=nrl * world, steps=tsteps, swap_period=swap, tasks_visited=sorted(set(int(v) for v in np.unique(a["at"])))))
+        for m in shard_m + solo_m:
+            m.close()
+    finally:
+        solo.close()
+    return out
 
 
 def row_sharded_block(B, wl, K, W, parity):
