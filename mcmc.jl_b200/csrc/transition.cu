@@ -437,10 +437,10 @@ __global__ void __launch_bounds__(TR_CHAINS * TR_GROUPS) transition_kernel(const
 //   B4 initial Hamiltonian / phase of the step just started
 // (one thread per chain walking all d parameters took 1.01 ms per decision wave at 102 400 chains x d = 100: every
 // Box-Muller pair, division and store of a chain in sequence.)
-constexpr int CO_CHAINS = 64, CO_GROUPS = 4, CO_UNROLL = 5;
+constexpr int CO_CHAINS = 64, CO_GROUPS = 8, CO_UNROLL = 3;
 enum { CM_NONE = 0, CM_INTERIOR, CM_FINAL, CM_MALA, CM_RWM, CM_INIT, CM_RESUME };
 
-__global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 4) transition_coop_kernel(const WaveArgs W) {
+__global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kernel(const WaveArgs W) {
   __shared__ double s_sum[CO_GROUPS][3][CO_CHAINS];      // partial sums [group][slot][chain]
   __shared__ double s_eps[CO_CHAINS];                    // step size of the step being started
   __shared__ long long s_k[CO_CHAINS], s_i[CO_CHAINS];   // kept index of the step just decided (-1: not kept); step being started
