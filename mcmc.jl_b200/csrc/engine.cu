@@ -397,7 +397,7 @@ int32_t mcmcgpu_logtarget_grad(mcmcgpu_model* m, const double* B, int64_t C, dou
   CU(use_ctx(c));
   cudaStream_t st = c->stream;
   const int64_t d = m->d, Cp = round_up(C, K1_CHAINS);
-  int nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp)) : 1;
+  int nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp, -1, m->family)) : 1;
   double *hB = nullptr, *q = nullptr, *part = nullptr, *red = nullptr, *lt = nullptr, *grad = nullptr, *gout = nullptr;
   struct Freer { double** p[7]; ~Freer() { for (auto pp : p) if (*pp) { dfree(*pp); *pp = nullptr; } } } freer{{&hB, &q, &part, &red, &lt, &grad, &gout}};
   CU(dalloc(&hB, (size_t)(C * d)));
@@ -560,7 +560,7 @@ static int run_create_impl(mcmcgpu_model* m, const mcmcgpu_sampler_cfg* s, const
   RCU(R->alloc(&R->status, (size_t)Cp));
   RCU(R->alloc(&R->n_evals, 1));
   if (engine == MCMCGPU_ENGINE_WAVE) {
-    R->nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp)) : 1;
+    R->nsplit = m->is_regression ? (c->force_splits > 0 ? (int)c->force_splits : k1_choose_splits(m->pack, Cp, -1, m->family)) : 1;
     RCU(R->alloc(&R->q, (size_t)(d * Cp)));
     RCU(R->alloc(&R->part, (size_t)(R->nsplit * (d + 2) * Cp)));
     if (m->row_sharded || R->nsplit > 4) RCU(R->alloc(&R->red, (size_t)((d + 2) * Cp)));

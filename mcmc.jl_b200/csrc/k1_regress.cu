@@ -29,6 +29,15 @@
 namespace mg {
 
 constexpr int K1_STAGES = 2;
+// probit at d <= 32: two resident CTAs (128 registers: no spills in the link, room for the whole central table |z| < 8) and
+// a 4-deep ring (a tile lasts ~1300 cycles there, the refill of a slot starts when the SLOWEST warp leaves it); measured on
+// cfg3's MALA wave: 3 CTAs x 2 stages 7.42 ms, 3 x 3 7.20, 2 x 3 7.10, 2 x 4 7.03
+#ifndef K1_PROBIT_SMALL_STAGES
+#define K1_PROBIT_SMALL_STAGES 4
+#endif
+#ifndef K1_PROBIT_SMALL_CTAS
+#define K1_PROBIT_SMALL_CTAS 2
+#endif
 constexpr int K1_NR = 4;          // 8-row groups per phase-1 pass (independent DMMA accumulator chains)
 constexpr int PH_IDLE_K1 = 98;  // phases >= PH_PAUSE (98) have no pending evaluation (transition.h)
 constexpr int PH_LEAP_K1 = 3;   // PH_LEAP (transition.h)
@@ -101,50 +110,65 @@ __device__ __forceinline__ double erfcx_fast(double u) {       // requires 0 <= 
   return p;
 }
 
-// ---- probit link from tables: F(z) = log Phi(z), W(z) = phi(z)/Phi(z), |z| < 36.9 (tools/gen_probit_table.py) ----
-// one round-to-nearest index (magic-number add, no conversions) and a degree-9 Horner per function: ~13 FP64
-// instructions each instead of erfcx + exp + reciprocal + log (~70); relative error 2e-16 for z < 0, absolute 1e-16 for z >= 0
-__device__ const double probit_F_tab[(PROBIT_DEG + 1) * PROBIT_NINT] = {PROBIT_F_VALUES};
-__device__ const double probit_W_tab[(PROBIT_DEG + 1) * PROBIT_NINT] = {PROBIT_W_VALUES};
-// joint table: one degree-10 polynomial J per interval with J' = the W interpolant and J(0) = F(centre); the simultaneous
-// Horner scheme gives log Phi and phi/Phi from ONE set of coefficient loads (the kernel is load/store-unit bound at small d)
-__device__ const double probit_J_tab[(PROBIT_DEG + 2) * PROBIT_NINT] = {PROBIT_J_VALUES};
-// The tables sit in global memory (L1-resident).  At small d the kernel is bound by the load/store unit (ncu on the MALA
-// wave of cfg3: LSU wavefronts 83 % of peak, one wavefront per distinct 32-byte sector of every gather), so when the CTA has
-// room the central part |z| < 8 -- where practically every element falls -- is copied to shared memory, where a gather costs
-// one wavefront per group of lanes that hit one bank at different addresses.  The copies hold the same coefficients and the
+// ---- probit link: F(z) = log Phi(z), W(z) = phi(z)/Phi(z), |z| < 36.9 (tools/gen_probit_table.py) ----------------------
+// Round 1 evaluated degree-9/10 piecewise polynomials: 11 table gathers and 25 FP64 instructions per element for value +
+// derivative, and at small d the kernel was bound by the load/store unit (ncu, cfg3: LSU wavefronts 89 % of peak).  Behind
+// the LSU sits the math dispatch port: a DMMA keeps it busy for ~12 of its 16 cycles (tools/fp64_probe3.cu: 64 FFMAs next to
+// 8 DMMAs cost 33 extra cycles, 16 conversion pairs cost 2), so every FP64 (2 cycles), FP32 and integer instruction of the
+// link adds to the DMMA time, while conversions and loads overlap with it.  Round 2: the table holds, per grid point
+// c = k/128, only F(c) and W(c) in double and a FLOAT pair (e3, e4) -- three gathers --; between grid points, t = z - c:
+//   s = c + W, W1 = -W s, W2 = -W1 (s + W) - W                      from W' = -W (z + W), in double (enter with t, t^2)
+//   W(c+t) = W + t (W1 + t/2 (W2 + t Tp2)),            Tp2 = e3 + e4 t            in float (enters with t^3 <= 2^-24)
+//   F(c+t) = F + t (W + t/2 (W1 + t/3 (W2 + t Tv6))),  Tv6 = 0.75 e3 + 0.6 e4 t = 0.6 Tp2 + 0.15 e3
+// 14 FP64 + 6 FP32 instructions for value + derivative (the grid index is float work too), 9 + 3 for the derivative alone.  Error against mpmath (emulated
+// operation by operation in the generator): F 2.1e-16 relative (z < 0) / 1.1e-16 absolute (z >= 0), W 7.6e-16 / 1.8e-15.
+__device__ const unsigned long long probit_tab[3 * PROBIT_NINT] = {PROBIT_TAB_WORDS};   // [F | W | E], 8-byte words
+// The tables sit in global memory (L1-resident); when the CTA has room the central part |z| < H (H = 8, else 4) -- where
+// practically every element falls -- is copied to shared memory, where a gather costs one wavefront per group of lanes that
+// hit one bank at different addresses instead of one per distinct 32-byte sector.  The copies hold the same numbers and the
 // arithmetic is the same, so which copy a warp reads never changes a number.
-constexpr int PS_K0 = (PROBIT_ZMAX - 8) * PROBIT_INV_W - 1;      // first interval of the shared-memory copy
-constexpr int PS_N = 16 * PROBIT_INV_W + 3;                       // intervals -8 - 1/8 .. 8 + 1/8
-constexpr int PS_DOUBLES = PS_N * (3 * PROBIT_DEG + 4);           // J (DEG+2 rows), W and F (DEG+1 rows each)
-// shared-memory bytes of a CTA without the probit tables, and whether the resident CTA count of the DK class survives them
+__host__ __device__ constexpr int ps_k0(int H) { return (PROBIT_ZMAX - H) * PROBIT_INV_W - 1; }   // first grid point of the copy
+__host__ __device__ constexpr int ps_n(int H) { return 2 * H * PROBIT_INV_W + 3; }                // grid points -H - 1/128 .. H + 1/128
+__host__ __device__ constexpr size_t ps_bytes(int H) { return (size_t)ps_n(H) * 24; }             // F, W (double), E (float2)
+// shared-memory bytes of a CTA without the probit tables, and the half-width of the copy the resident CTA count leaves room for
 __host__ __device__ constexpr size_t k1_smem_base(int DK, int WARPS, int STAGES) {
   return sizeof(double) * ((size_t)(8 * WARPS) * (8 * DK + 4) + (size_t)STAGES * (K1_ROWS * (8 * DK + 4) + K1_ROWS)) +
          2 * STAGES * sizeof(uint64_t) + (EXP_NTAB + 2 * LOG_NINT) * sizeof(double);
 }
-__host__ __device__ constexpr bool k1_probit_smem(int DK, int WARPS, int STAGES, int CTAS) {
-  return (size_t)CTAS * (k1_smem_base(DK, WARPS, STAGES) + PS_DOUBLES * sizeof(double) + 1024) <= 233472;   // 228 KB per SM
+__host__ __device__ constexpr int k1_probit_half(int DK, int WARPS, int STAGES, int CTAS) {
+  return ((size_t)CTAS * (k1_smem_base(DK, WARPS, STAGES) + ps_bytes(8) + 1024) <= 233472) ? 8      // 228 KB per SM
+       : ((size_t)CTAS * (k1_smem_base(DK, WARPS, STAGES) + ps_bytes(4) + 1024) <= 233472) ? 4 : 0;
 }
 template <bool SM>
-__device__ __forceinline__ double tab_ld(const double* p) { return SM ? *p : __ldg(p); }
-template <bool SM>
-__device__ __forceinline__ void probit_eval_joint(const double* c, int stride, double t, double& f, double& w) {
-  double p = tab_ld<SM>(c + (PROBIT_DEG + 1) * stride), dp = 0.0;
-#pragma unroll
-  for (int j = PROBIT_DEG; j >= 0; j--) { dp = fma(dp, t, p); p = fma(p, t, tab_ld<SM>(c + j * stride)); }
-  f = p; w = dp;
-}
-__device__ __forceinline__ void probit_index(double z, int& k, double& t) {
-  const double m = fma(z, (double)PROBIT_INV_W, 6755399441055744.0 + (double)(PROBIT_ZMAX * PROBIT_INV_W));
-  k = __double2loint(m);
-  t = fma(m - (6755399441055744.0 + (double)(PROBIT_ZMAX * PROBIT_INV_W)), -1.0 / PROBIT_INV_W, z);
-}
-template <bool SM>
-__device__ __forceinline__ double probit_eval(const double* c, int stride, double t) {
-  double p = tab_ld<SM>(c + PROBIT_DEG * stride);
-#pragma unroll
-  for (int j = PROBIT_DEG - 1; j >= 0; j--) p = fma(p, t, tab_ld<SM>(c + j * stride));
-  return p;
+__device__ __forceinline__ unsigned long long tab_ld(const unsigned long long* p) { return SM ? *p : __ldg(p); }
+// T: the table, rows F | W | E of STRIDE 8-byte words each, positioned so that T[k] is F at grid point k (one address per
+// element, the rows at compile-time offsets).  WANT_F / WANT_W: which of the two functions the caller uses (the other
+// one's instructions are not generated)
+template <bool SM, int STRIDE, bool WANT_F, bool WANT_W>
+__device__ __forceinline__ void probit_eval(const unsigned long long* T, double z, double& f, double& w) {
+  // grid index in FLOAT (conversions and FP32 instructions are cheaper than FP64 ones here): k = rint(128 z) from the low
+  // mantissa bits of 1.5 * 2^23 + 128 z; t = z - k/128 is exact in double whichever neighbour a tie-near z picks
+  const float mf = fmaf((float)z, (float)PROBIT_INV_W, 12582912.0f);
+  const int k = __float_as_int(mf) - 0x4B400000 + PROBIT_ZMAX * PROBIT_INV_W;
+  const double kd = (double)(mf - 12582912.0f);                  // 128 c, exact
+  const double t = fma(kd, -1.0 / PROBIT_INV_W, z);               // exact
+  const unsigned long long* Tk = T + k;
+  const double W0 = __longlong_as_double((long long)tab_ld<SM>(Tk + STRIDE));
+  const unsigned long long eb = tab_ld<SM>(Tk + 2 * STRIDE);
+  const float e3 = __uint_as_float((unsigned)eb), e4 = __uint_as_float((unsigned)(eb >> 32));
+  const double s = fma(kd, 1.0 / PROBIT_INV_W, W0);               // c + W
+  const double W1 = -__dmul_rn(W0, s);
+  const double W2 = fma(-W1, __dadd_rn(s, W0), -W0);              // -W1 s - W (1 + W1) = -W1 (s + W) - W
+  const double th = 0.5 * t;
+  const float tf = (float)t;
+  const float Tp2 = fmaf(e4, tf, e3);
+  if (WANT_W) w = fma(t, fma(th, fma(t, (double)Tp2, W2), W1), W0);
+  if (WANT_F) {
+    const double F0 = __longlong_as_double((long long)tab_ld<SM>(Tk));
+    const double t3 = t * (1.0 / 3.0);
+    const float Tv6 = fmaf(0.15f, e3, 0.6f * Tp2);                // 0.75 e3 + 0.6 e4 t
+    f = fma(t, fma(th, fma(t3, fma(t, (double)Tv6, W2), W1), W0), F0);
+  }
 }
 
 // ---- logistic link: exp from a 64-entry table of 2^(j/64) held in shared memory (tools/gen_exp_table.py) ---------------
@@ -294,10 +318,13 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
   unsigned int* released = reinterpret_cast<unsigned int*>(full + K1_STAGES);   // warps that have finished with a slot
   double* etab = reinterpret_cast<double*>(full + 2 * K1_STAGES);               // 2^(j/64) (logistic link)
   double2* ltab = reinterpret_cast<double2*>(etab + EXP_NTAB);                  // (1/c_j, log c_j) (logistic link)
-  constexpr bool PSM = (FAM == MCMCGPU_FAM_PROBIT) && k1_probit_smem(DK, WARPS, STAGES, CTAS);
-  double* ptab = reinterpret_cast<double*>(ltab + LOG_NINT);                    // central part of the probit tables
+  constexpr int PSH = (FAM == MCMCGPU_FAM_PROBIT) ? k1_probit_half(DK, WARPS, STAGES, CTAS) : 0;   // |z| < PSH sits in shared memory
+  constexpr bool PSM = PSH > 0;
+  constexpr int PS_N = ps_n(PSH), PS_K0 = ps_k0(PSH);
+  unsigned long long* ptab = reinterpret_cast<unsigned long long*>(ltab + LOG_NINT);   // central part of the probit table: F | W | E
 
   if (a.remaining && *a.remaining == 0) return;
+  const bool ybin = (FAM == MCMCGPU_FAM_PROBIT) && a.P.ynb != nullptr && (*a.P.ynb == 0u);   // every response is 0.0 or 1.0
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int64_t chain0 = (int64_t)blockIdx.x * K1_CHAINS;
@@ -334,12 +361,9 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
     betas[c * S + j] = (j < d && chain0 + c < Cp) ? bsign * a.q[(int64_t)j * Cp + chain0 + c] : 0.0;
   }
   if (PSM) {
-    for (int idx = tid; idx < PS_DOUBLES; idx += K1_THREADS) {
-      const int row = idx / PS_N, i = idx - row * PS_N;       // rows: J[0..DEG+1], W[0..DEG], F[0..DEG]
-      const double* src = (row < PROBIT_DEG + 2) ? probit_J_tab + row * PROBIT_NINT
-                        : (row < 2 * PROBIT_DEG + 3) ? probit_W_tab + (row - (PROBIT_DEG + 2)) * PROBIT_NINT
-                                                     : probit_F_tab + (row - (2 * PROBIT_DEG + 3)) * PROBIT_NINT;
-      ptab[idx] = src[PS_K0 + i];
+    for (int idx = tid; idx < 3 * PS_N; idx += K1_THREADS) {
+      const int row = idx / PS_N, i = idx - row * PS_N;
+      ptab[idx] = probit_tab[row * PROBIT_NINT + PS_K0 + i];
     }
   }
   if (FAM == MCMCGPU_FAM_LOGISTIC) {
@@ -459,64 +483,60 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
       }
       if (FAM == MCMCGPU_FAM_PROBIT && a.debug == 0) {
         // binary responses with |eta| < 36.9 (the only case met in practice): log Phi(z) and phi(z)/Phi(z), z = +-eta, from
-        // the tables, stage by stage over the 2*NR elements; log Phi is skipped when no chain of the warp needs the value.
-        // Response tests, range tests and sign flips are integer work on the bit patterns (the FP64 pipe is DMMA's).
-        double zv[2 * NR], tv[2 * NR];
-        int kv[2 * NR];
-        unsigned y1mask = 0u;
-        bool fast = true, central = true;
+        // the table; log Phi is skipped when no chain of the warp needs the value.  Response tests, range tests and sign
+        // flips are integer work on the bit patterns, and as little of it as possible (every math instruction of the link
+        // adds to the DMMA time): one running maximum of |z| instead of two compares per element, y in {0, 1} checked once when the
+        // design matrix is packed, the y == 0 flags shifted
+        // into one register, ONE log-likelihood accumulator (the two dot products of probit_regression.jl:29 are added at the
+        // end anyway), and the padded rows of the last tile masked on a warp-uniform path of their own.
+        double zv[2 * NR];
+        unsigned neg = 0u, amax = 0u;                 // neg bit (2 NR - 1 - i): y_i == 0, so z = -eta and r = -w
 #pragma unroll
         for (int n = 0; n < NR; n++)
 #pragma unroll
           for (int s = 0; s < 2; s++) {
             const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-            const long long yb = __double_as_longlong(ys[lr]);
-            const bool y1 = (yb == 0x3FF0000000000000ll);
-            y1mask |= y1 ? (1u << i) : 0u;
-            const int zh = __double2hiint(acc[n][s]) ^ (y1 ? 0 : (int)0x80000000);          // z = y ? eta : -eta
-            zv[i] = __hiloint2double(zh, __double2loint(acc[n][s]));
-            fast = fast && (y1 || yb == 0ll) && ((zh & 0x7fffffff) < 0x40427333);            // |z| < 36.9 and not NaN
-            central = central && ((zh & 0x7fffffff) < 0x40200000);                           // |z| < 8
+            const unsigned yh = (unsigned)__double2hiint(ys[lr]);                            // 0x3FF00000 or 0 (ybin, checked by k1_pack)
+            const unsigned sg = ~(yh << 2) & 0x80000000u;                                    // y == 1: 0; y == 0: the sign bit
+            neg = __funnelshift_l(sg, neg, 1);
+            const unsigned zh = (unsigned)__double2hiint(acc[n][s]) ^ sg;                    // z = y ? eta : -eta
+            zv[i] = __hiloint2double((int)zh, __double2loint(acc[n][s]));
+            amax = max(amax, zh & 0x7fffffffu);
           }
-        // the shared-memory copies only when every element of the warp is central (warp-uniform choice of the code path;
-        // same coefficients, same arithmetic: the choice never changes a number)
-        const bool insm = PSM && __all_sync(0xffffffffu, fast && central);
+        const bool fast = ybin && (amax < 0x40427333u);                                      // |z| < 36.9 and not NaN
+        // the shared-memory copies only when every element of the warp is central, |z| < PSH (warp-uniform choice of the
+        // code path; same numbers, same arithmetic: the choice never changes a result)
+        const bool insm = PSM && __all_sync(0xffffffffu, fast && (amax < (PSH == 8 ? 0x40200000u : 0x40100000u)));
         if (fast) {
-#pragma unroll
-          for (int i = 0; i < 2 * NR; i++) probit_index(zv[i], kv[i], tv[i]);
-          auto stages = [&](auto sm_tag) {
-            constexpr bool SM = decltype(sm_tag)::value;
-            constexpr int stride = SM ? PS_N : PROBIT_NINT;
-            const double* TJ = SM ? ptab : probit_J_tab;
-            const double* TW = SM ? ptab + (PROBIT_DEG + 2) * PS_N : probit_W_tab;
-            const double* TF = SM ? ptab + (2 * PROBIT_DEG + 3) * PS_N : probit_F_tab;
-            constexpr int k0 = SM ? PS_K0 : 0;
+          auto stages = [&](auto sm_tag, auto mask_tag) {
+            constexpr bool SM = decltype(sm_tag)::value, MASK = decltype(mask_tag)::value;
+            constexpr int STR = SM ? PS_N : PROBIT_NINT;
+            const unsigned long long* T = SM ? ptab - PS_K0 : probit_tab;
             if (a.need_ll == nullptr && a.need_grad) {
-              // every chain needs value and gradient on every wave of this run (MALA; the first wave of any run):
-              // both from the joint table, one set of coefficient loads
+              // every chain needs value and gradient on every wave of this run (MALA; the first wave of any run)
 #pragma unroll
               for (int n = 0; n < NR; n++)
 #pragma unroll
                 for (int s = 0; s < 2; s++) {
                   const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
                   double l, w;
-                  probit_eval_joint<SM>(TJ + (kv[i] - k0), stride, tv[i], l, w);
-                  const bool y1 = (y1mask >> i) & 1u;
-                  acc[n][s] = __hiloint2double(__double2hiint(w) ^ (y1 ? 0 : (int)0x80000000), __double2loint(w));   // r = y ? w : -w
-                  if ((rowbase + lr) >= N) l = 0.0;
-                  const double sum = (y1 ? ll1 : ll2) + l;      // dot(log Phi(eta), y) and dot(log Phi(-eta), 1 - y) kept apart
-                  ll1 = y1 ? sum : ll1;
-                  ll2 = y1 ? ll2 : sum;
+                  probit_eval<SM, STR, true, true>(T, zv[i], l, w);
+                  acc[n][s] = __hiloint2double(__double2hiint(w) ^ (int)((neg << (32 - 2 * NR + i)) & 0x80000000u), __double2loint(w));   // r = y ? w : -w
+                  if (MASK && (rowbase + lr) >= N) l = 0.0;
+                  ll1 += l;
                 }
             } else {
+              // the same instructions produce w whether or not the value is wanted (need_ll is a per-WARP flag: a chain's
+              // numbers must not depend on the phase of its neighbours)
               if (a.need_grad) {
 #pragma unroll
                 for (int n = 0; n < NR; n++)
 #pragma unroll
                   for (int s = 0; s < 2; s++) {
                     const int i = 2 * n + s;
-                    const double w = probit_eval<SM>(TW + (kv[i] - k0), stride, tv[i]);
-                    acc[n][s] = __hiloint2double(__double2hiint(w) ^ (((y1mask >> i) & 1u) ? 0 : (int)0x80000000), __double2loint(w));
+                    double l, w;
+                    probit_eval<SM, STR, false, true>(T, zv[i], l, w);
+                    acc[n][s] = __hiloint2double(__double2hiint(w) ^ (int)((neg << (32 - 2 * NR + i)) & 0x80000000u), __double2loint(w));
                   }
               }
               if (need_ll) {
@@ -525,16 +545,19 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
 #pragma unroll
                   for (int s = 0; s < 2; s++) {
                     const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-                    const double l = ((rowbase + lr) < N) ? probit_eval<SM>(TF + (kv[i] - k0), stride, tv[i]) : 0.0;
-                    const bool y1 = (y1mask >> i) & 1u;
-                    const double sum = (y1 ? ll1 : ll2) + l;
-                    ll1 = y1 ? sum : ll1;
-                    ll2 = y1 ? ll2 : sum;
+                    double l, w;
+                    probit_eval<SM, STR, true, false>(T, zv[i], l, w);
+                    if (MASK && (rowbase + lr) >= N) l = 0.0;
+                    ll1 += l;
                   }
               }
             }
           };
-          if (insm) stages(std::true_type{}); else stages(std::false_type{});
+          if (rowbase + K1_ROWS <= N) {
+            if (insm) stages(std::true_type{}, std::false_type{}); else stages(std::false_type{}, std::false_type{});
+          } else {
+            if (insm) stages(std::true_type{}, std::true_type{}); else stages(std::false_type{}, std::true_type{});
+          }
           done = true;
         }
       }
@@ -678,7 +701,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
 
 // ---- packing kernel: column-major X -> tile images -------------------------------------------
 __global__ void k1_pack_kernel(double* tiles, const double* X, const double* y, int64_t N, int64_t d, int S,
-                               int64_t tile_doubles, int64_t ntiles) {
+                               int64_t tile_doubles, int64_t ntiles, unsigned int* ynb) {
   // one block per tile; threads stride over (row, col)
   const int64_t tl = blockIdx.x;
   double* T = tiles + tl * tile_doubles;
@@ -691,7 +714,10 @@ __global__ void k1_pack_kernel(double* tiles, const double* X, const double* y, 
   }
   for (int r = threadIdx.x; r < K1_ROWS; r += blockDim.x) {
     int64_t row = row0 + r;
-    T[K1_ROWS * S + r] = (row < N) ? y[row] : 0.0;
+    const double yv = (row < N) ? y[row] : 0.0;
+    T[K1_ROWS * S + r] = yv;
+    const long long yb = __double_as_longlong(yv);
+    if (yb != 0ll && yb != 0x3FF0000000000000ll) atomicOr(ynb, 1u);     // the probit link tests this word once instead of every y
   }
 }
 
@@ -715,21 +741,26 @@ cudaError_t k1_pack(K1Pack& P, const double* dX, const double* dy, int64_t N, in
   P.S = 8 * P.DK + 4;
   P.ntiles = (N + K1_ROWS - 1) / K1_ROWS;
   P.tile_doubles = (int64_t)K1_ROWS * P.S + K1_ROWS;
-  cudaError_t e = cudaMalloc(&P.tiles, sizeof(double) * (size_t)(P.ntiles * P.tile_doubles));
+  cudaError_t e = cudaMalloc(&P.tiles, sizeof(double) * (size_t)(P.ntiles * P.tile_doubles + 2));
   if (e != cudaSuccess) return e;
-  k1_pack_kernel<<<(unsigned)P.ntiles, 256, 0, st>>>(P.tiles, dX, dy, N, d, P.S, P.tile_doubles, P.ntiles);
+  unsigned int* ynb = reinterpret_cast<unsigned int*>(P.tiles + P.ntiles * P.tile_doubles);
+  P.ynb = ynb;
+  e = cudaMemsetAsync(ynb, 0, 2 * sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  k1_pack_kernel<<<(unsigned)P.ntiles, 256, 0, st>>>(P.tiles, dX, dy, N, d, P.S, P.tile_doubles, P.ntiles, ynb);
   return cudaGetLastError();
 }
 void k1_free(K1Pack& P) { if (P.tiles) cudaFree(P.tiles); P.tiles = nullptr; }
 
-int k1_choose_splits(const K1Pack& P, int64_t Cp, int device) {
+int k1_choose_splits(const K1Pack& P, int64_t Cp, int device, int family) {
   // Row splits: enough CTAs to fill the machine, and a CTA count whose last wave is nearly full
   // (two resident CTAs per SM).  Every split keeps >= 8 tiles so the prologue stays amortised.
   const int64_t ctiles = Cp / K1_CHAINS;
   int sms = 148;
   if (device < 0) cudaGetDevice(&device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int64_t slots = (P.DK <= K1_MAX_DK_3CTA ? 3LL : (P.DK <= K1_MAX_DK_2CTA ? 2LL : 1LL)) * sms;
+  const int64_t small_ctas = (family == MCMCGPU_FAM_PROBIT) ? K1_PROBIT_SMALL_CTAS : 3;
+  const int64_t slots = (P.DK <= K1_MAX_DK_3CTA ? small_ctas : (P.DK <= K1_MAX_DK_2CTA ? 2LL : 1LL)) * sms;
   int64_t maxs = P.ntiles / 8;
   if (maxs < 1) maxs = 1;
   if (maxs > 512) maxs = 512;
@@ -755,7 +786,7 @@ template <int FAM, int DK, int WARPS, int STAGES, int CTAS>
 static cudaError_t launch_shape(const K1Args& a, cudaStream_t st) {
   constexpr int NR = K1_NR;
   constexpr size_t smem = k1_smem_base(DK, WARPS, STAGES) +
-                          ((FAM == MCMCGPU_FAM_PROBIT && k1_probit_smem(DK, WARPS, STAGES, CTAS)) ? PS_DOUBLES * sizeof(double) : 0);
+                          ((FAM == MCMCGPU_FAM_PROBIT && k1_probit_half(DK, WARPS, STAGES, CTAS) > 0) ? ps_bytes(k1_probit_half(DK, WARPS, STAGES, CTAS)) : 0);
   static_assert(smem <= 232448, "one CTA must fit the 227 KB of dynamic shared memory");
   static bool attr_done[64] = {false};      // the attribute is per device
   int dev = 0;
@@ -775,16 +806,19 @@ static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
   // 8 warps x 64 chains, 2-deep ring; 3 / 2 / 1 resident CTAs by register and shared-memory budget.  (Measured and dropped:
   // one 16-warp x 128-chain CTA per SM with a 4-deep ring for 32 < d <= 104 -- same warps per SM, half the X-tile traffic,
   // three tiles of slack between the fastest and the slowest warp -- 35.0 vs 35.1 ms per wave: the ring is not the limiter.)
-  constexpr int CTAS = (DK <= K1_MAX_DK_3CTA) ? 3 : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1);
-  return launch_shape<FAM, DK, K1_WARPS, K1_STAGES, CTAS>(a, st);
+  constexpr bool SMALL = (DK <= K1_MAX_DK_3CTA);
+  constexpr bool PSMALL = SMALL && (FAM == MCMCGPU_FAM_PROBIT);
+  constexpr int CTAS = PSMALL ? K1_PROBIT_SMALL_CTAS : (SMALL ? 3 : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1));
+  return launch_shape<FAM, DK, K1_WARPS, PSMALL ? K1_PROBIT_SMALL_STAGES : K1_STAGES, CTAS>(a, st);
 }
 
 template <int FAM>
 static cudaError_t launch_f(const K1Args& a, cudaStream_t st) {
   switch (a.P.DK) {
+    case 3: return launch_fd<FAM, 3>(a, st);
+#ifndef K1_ONLY_DK3
     case 1: return launch_fd<FAM, 1>(a, st);
     case 2: return launch_fd<FAM, 2>(a, st);
-    case 3: return launch_fd<FAM, 3>(a, st);
     case 4: return launch_fd<FAM, 4>(a, st);
     case 5: return launch_fd<FAM, 5>(a, st);
     case 6: return launch_fd<FAM, 6>(a, st);
@@ -800,6 +834,7 @@ static cudaError_t launch_f(const K1Args& a, cudaStream_t st) {
     case 16: return launch_fd<FAM, 16>(a, st);
     case 20: return launch_fd<FAM, 20>(a, st);
     case 25: return launch_fd<FAM, 25>(a, st);
+#endif
   }
   return cudaErrorInvalidValue;
 }

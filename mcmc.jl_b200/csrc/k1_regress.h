@@ -21,6 +21,7 @@ struct K1Pack {
   int S = 0;         // row stride in doubles
   int64_t ntiles = 0;
   int64_t tile_doubles = 0;
+  const unsigned int* ynb = nullptr;   // device word behind the tiles: nonzero iff some response is neither 0.0 nor 1.0
 };
 
 struct K1Args {
@@ -54,7 +55,7 @@ struct K1Args {
 cudaError_t k1_pack(K1Pack& P, const double* dX /* N x d col-major, device */, const double* dy, int64_t N, int64_t d,
                     cudaStream_t st);
 void k1_free(K1Pack& P);
-int k1_choose_splits(const K1Pack& P, int64_t Cp, int device = -1);   // device < 0: the current device
+int k1_choose_splits(const K1Pack& P, int64_t Cp, int device = -1, int family = -1);   // device < 0: the current device; the resident CTA count of the small-d class depends on the family
 cudaError_t k1_launch(const K1Args& a, cudaStream_t st);
 bool k1_supported(int64_t d);
 
