@@ -35,7 +35,10 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__inst_executed.sum', 'dram__bytes_write.sum.per_second',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__pipe_shared_cycles_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum', 'smsp__inst_executed.sum', 'dram__bytes_write.sum.per_second',
         'dram__bytes_read.sum.per_second', 'launch__shared_mem_per_block_dynamic', 'smsp__inst_executed_op_shared_ld.sum', 'sm__sass_inst_executed_op_global_ld.sum']
 
 
@@ -61,7 +64,7 @@ full = "ncu --set full --clock-control none -k regex:%s -s %d -c %d <cmd>; expor
 summarize('k1_full_r02', dict(command=full % ("k1_kernel", 25, 1), cmd="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-ess --no-extras",
                              kernel="mg::k1_kernel<3 (logistic), 13 (d<=104), 4, 8, 2, 2>", workload="cfg4 N=1e6 d=100 C=10000, interior leapfrog wave"))
 summarize('k1_probit_r02', dict(command=full % ("k1_kernel", 8, 1), cmd="python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu-baseline --no-ess",
-                               kernel="mg::k1_kernel<4 (probit), 3 (d<=24), 4, 8, 2, 3>", workload="cfg3 N=1e5 d=20 C=16384, MALA wave (value + gradient)"))
+                               kernel="mg::k1_kernel<4 (probit), 3 (d<=24), 4, 8, 4 (ring), 2 (CTAs/SM)>", workload="cfg3 N=1e5 d=20 C=16384, MALA wave (value + gradient)"))
 summarize('fused_full_r02', dict(command=full % ("fused_chain", 1, 1), cmd="python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu-baseline --no-ess",
                                 kernel="mg::fused_chain_kernel<0 (normal_fn), 3, false>", workload="cfg2 65536 chains HMC(0.75), 400-step timed launch"))
 summarize('k1_smalln_r02', dict(command=full % ("k1_kernel", 12, 1), cmd="python tools/smalln_probe.py 4 94720",
