@@ -684,6 +684,42 @@ def test_logistic_link_elementwise(capi, ctx, sign):
         capi.DeviceModel(ctx, "logistic", 1, np.ones((1, 1)), np.array([1.0]), (1.0, -2.0))     # sign must be +-1
 
 
+def test_probit_link_elementwise(capi, ctx):
+    """log Phi(+-eta) and r = +-phi/Phi of the probit link, element by element (N = 1, X = [1], one chain per eta), against
+    mpmath: the two-doubles-and-a-float-pair table of K1's fast path (tools/gen_probit_table.py: W', W'' from
+    W' = -W (z + W) in double, the cubic / quartic tail in float, the grid index in float) must keep the accuracy the
+    generator's emulation states -- relative for z < 0, absolute for z >= 0 -- over the whole fast range incl. grid points,
+    interval edges and the shared-memory / global-memory table boundary at |z| = 8; the libm path takes over at 36.9
+    (examples/probit_regression.jl:29,39-40)."""
+    import mpmath as mp
+    mp.mp.dps = 40
+    rng = np.random.default_rng(12)
+    grid = np.arange(-1100, 1100) / 128.0
+    eta = np.concatenate([np.linspace(-36.8, 36.8, 1200), rng.uniform(-6, 6, 1500), grid[::7], grid[::11] + 0.99 / 256, grid[::13] - 0.99 / 256,
+                          [0.0, 1e-300, -1e-17, 7.999, 8.001, -7.999, -8.001, 36.89, -36.89, 36.95, -36.95, 39.0, -39.0]])
+    sd = 1e6
+    prior = lambda b: -0.5 * (mp.log(2 * mp.pi) + 2 * mp.log(sd)) - mp.mpf(float(b)) ** 2 / (2 * mp.mpf(sd) ** 2)
+    for yval in (1.0, 0.0):
+        dm = capi.DeviceModel(ctx, "probit", 1, np.ones((1, 1)), np.array([yval]), (sd,))
+        lt, g = dm.logtarget_grad(eta.reshape(-1, 1))
+        for c, b in enumerate(eta):
+            z = mp.mpf(float(b)) if yval == 1.0 else -mp.mpf(float(b))
+            F = mp.log(mp.ncdf(z))
+            W = mp.npdf(z) / mp.ncdf(z)
+            r = W if yval == 1.0 else -W
+            tol_f = 1e-15 * abs(F) + 4e-16 + 3e-16 * abs(prior(b))
+            tol_w = (5e-15 * abs(W) if z < 0 else 6e-15) + 1e-16 * abs(float(b)) / (sd * sd)
+            assert abs(mp.mpf(float(lt[c])) - (F + prior(b))) <= tol_f, (yval, b, lt[c], F + prior(b))
+            assert abs(mp.mpf(float(g[c, 0])) - (r - mp.mpf(float(b)) / (sd * sd))) <= tol_w, (yval, b, g[c, 0], r)
+        dm.close()
+    # a response that is neither 0 nor 1 sends the whole model down the general path (the table path tests y once, at pack time)
+    dm = capi.DeviceModel(ctx, "probit", 1, np.ones((2, 1)), np.array([1.0, 0.5]), (sd,))
+    lt, g = dm.logtarget_grad(np.array([[0.3]]))
+    truth = mp.log(mp.ncdf(0.3)) + 0.5 * mp.log(mp.ncdf(0.3)) + 0.5 * mp.log(mp.ncdf(-0.3)) + prior(0.3)
+    assert abs(mp.mpf(float(lt[0])) - truth) <= 1e-14 * abs(truth)
+    dm.close()
+
+
 def test_readme_snippet():
     """the usage example of README.md runs as written"""
     import mcmc_jl_b200 as mj
