@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, (STREAM && D <= 4) ? 7 : 0) fus
   const ModelDev& M = A.M;
   const SamplerDev& S = A.S;
   const RunnerDev& R = A.R;
-  const int d = (int)M.d;
+  constexpr int d = D;            // launch_d instantiates every d up to FUSED_MAX_D: no runtime dimension tests in the step loop
   if (FAM == MCMCGPU_FAM_OU) {
     for (int64_t t = threadIdx.x; t < M.N; t += blockDim.x) sh_series[t] = M.series[t];
     __syncthreads();
@@ -100,19 +100,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, (STREAM && D <= 4) ? 7 : 0) fus
       if (A.eps) A.eps[off_s] = eps;
       if (A.nleaps) A.nleaps[off_s] = nl;
       kept++; off_s += Cp;
-      return;
-    }
+    } else {
 #pragma unroll
-    for (int j = 0; j < D; j++) if (j < d) A.samples[off_v + (int64_t)j * Cp] = pp[j];
-    if (A.grads) {
+      for (int j = 0; j < D; j++) if (j < d) A.samples[off_v + (int64_t)j * Cp] = pp[j];
+      if (A.grads) {
 #pragma unroll
-      for (int j = 0; j < D; j++) if (j < d) A.grads[off_v + (int64_t)j * Cp] = has_grad ? pg[j] : CUDART_NAN;
+        for (int j = 0; j < D; j++) if (j < d) A.grads[off_v + (int64_t)j * Cp] = has_grad ? pg[j] : CUDART_NAN;
+      }
+      A.accept[off_s] = acc ? 1 : 0;
+      if (A.logtarget) A.logtarget[off_s] = plt;
+      if (A.eps) A.eps[off_s] = eps;
+      if (A.nleaps) A.nleaps[off_s] = nl;
+      kept++; off_v += row_v; off_s += Cp;
     }
-    A.accept[off_s] = acc ? 1 : 0;
-    if (A.logtarget) A.logtarget[off_s] = plt;
-    if (A.eps) A.eps[off_s] = eps;
-    if (A.nleaps) A.nleaps[off_s] = nl;
-    kept++; off_v += row_v; off_s += Cp;
   };
 
   double pars[D], grad[D];
@@ -420,7 +420,9 @@ static cudaError_t launch_d(const FusedArgs& A, cudaStream_t st) {
   if (d <= 2) return launch_one<FAM, 2>(A, st);
   if (d <= 3) return launch_one<FAM, 3>(A, st);
   if (d <= 4) return launch_one<FAM, 4>(A, st);
+  if (d <= 5) return launch_one<FAM, 5>(A, st);
   if (d <= 6) return launch_one<FAM, 6>(A, st);
+  if (d <= 7) return launch_one<FAM, 7>(A, st);
   if (d <= 8) return launch_one<FAM, 8>(A, st);
   return cudaErrorInvalidValue;
 }
