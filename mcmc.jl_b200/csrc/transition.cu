@@ -448,7 +448,6 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
   const RunnerDev& R = W.R;
   const SamplerDev& S = W.S;
   const ModelDev& M = W.M;
-  if (!W.resume && *W.remaining == 0) return;
   const int lc = threadIdx.x % CO_CHAINS, grp = threadIdx.x / CO_CHAINS;
   const int64_t c = (int64_t)blockIdx.x * CO_CHAINS + lc;
   const int64_t d = M.d, Cp = R.Cp;
@@ -461,21 +460,42 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
   const int64_t npairs = (d + 1) / 2;
 
   // ---- stage 0: classify (every group reads the chain's counters; nobody has advanced them yet) ----
+  // Every per-chain scalar the kernel will need is loaded HERE, unconditionally and side by side: at small shapes the kernel
+  // is a chain of dependent global round trips (remaining -> phase -> leap -> eps -> support flag -> ... : 9 us for an
+  // interior wave of 96 chains, 25 us for a decision wave), and the values a later stage needs depend on nothing but c.
+  // The arrays are allocated for every run (size Cp), so the speculative reads are in bounds whatever the sampler.
+  const bool live = c < R.C;
+  const int rem = W.resume ? 1 : *W.remaining;
+  int ph = PH_DONE, lp = 0, nlc = 0;
+  bool k1d = false;
+  double eps_ld = 0.0, oos_sum = 0.0;
+  long long istep_ld = 0, kept_ld = 0;              // group 0 only: what stage B2 / B4 consume
+  double cur_lt_ld = 0.0, H0_ld = 0.0, ll_ld = 0.0, da_ls_ld = 0.0, da_dual_ld = 0.0, da_dualH_ld = 0.0;
+  if (live) {
+    ph = W.phase[c]; lp = W.leap[c]; nlc = W.nleaps_cur[c]; eps_ld = W.eps_cur[c];
+    if (W.fused_interior) k1d = W.k1_done[c] != 0;
+    if (linlog && ns == 1) oos_sum = sum_part(part, ns, d + 1, d, Cp, c);
+    if (grp == 0) {
+      istep_ld = W.istep[c]; kept_ld = W.kept[c]; cur_lt_ld = W.cur_lt[c]; H0_ld = W.H0[c];
+      if (ns == 1) ll_ld = sum_part(part, ns, d, d, Cp, c);
+      if (kind == MCMCGPU_HMCDA) { da_ls_ld = W.da_leapstep[c]; da_dual_ld = W.da_dual[c]; da_dualH_ld = W.da_dualH[c]; }
+    }
+  }
+  if (rem == 0) return;                             // uniform over the grid
   int mode = CM_NONE;
-  if (c < R.C) {
-    const int ph = W.phase[c];
+  if (live) {
     if (W.resume) mode = (ph == PH_PAUSE) ? CM_RESUME : CM_NONE;
     else if (ph == PH_INIT) mode = CM_INIT;
     else if (ph == PH_RWM) mode = CM_RWM;
     else if (ph == PH_MALA) mode = CM_MALA;
-    else if (ph == PH_LEAP) mode = (W.leap[c] + 2 <= W.nleaps_cur[c]) ? CM_INTERIOR : CM_FINAL;
+    else if (ph == PH_LEAP) mode = (lp + 2 <= nlc) ? CM_INTERIOR : CM_FINAL;
     // interior leapfrog completed (state and counters) by the likelihood kernel: nothing to do for this chain
-    if (W.fused_interior && !W.resume && W.k1_done[c]) mode = CM_NONE;
+    if (W.fused_interior && !W.resume && k1d) mode = CM_NONE;
   }
-  const double eps_cur = (mode == CM_INTERIOR || mode == CM_FINAL || mode == CM_MALA) ? W.eps_cur[c] : 0.0;
+  const double eps_cur = (mode == CM_INTERIOR || mode == CM_FINAL || mode == CM_MALA) ? eps_ld : 0.0;
   EvalFin F; F.fam = M.family; F.lt = CUDART_NAN; F.oos = false; F.ginv = 0.0;
   if (mode != CM_NONE && mode != CM_RESUME) {
-    if (linlog) F.oos = sum_part(part, ns, d + 1, d, Cp, c) > 0.0;    // LLAcc: a non-finite likelihood term => zero gradient
+    if (linlog) F.oos = ((ns == 1) ? oos_sum : sum_part(part, ns, d + 1, d, Cp, c)) > 0.0;    // LLAcc: a non-finite likelihood term => zero gradient
     else F.ginv = M.hyper[0] * M.hyper[0];
   }
   __syncthreads();
@@ -540,6 +560,7 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
 
   // ---- stage B2: the decision (group 0, one thread per chain) ----
   int nev = 0;
+  double cur_lt_now = cur_lt_ld;            // the chain's log-target after this wave's decision (group 0; stage B4 reads it)
   if (grp == 0) {
     s_acc[lc] = 0; s_begin[lc] = 0; s_k[lc] = -1; s_nl[lc] = 0; s_eps[lc] = 0.0; s_i[lc] = 0;
     if (mode != CM_NONE) {
@@ -549,13 +570,14 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
         return W.inj_uniforms ? W.inj_uniforms[step * Cp + c] : philox_uniform(R.seed, gchain, (uint32_t)step);
       };
       nev = (mode == CM_RESUME) ? 0 : 1;
-      int64_t i = W.istep[c];
+      int64_t i = istep_ld;
       bool begin = false, acc = false;
+      cur_lt_now = cur_lt_ld;
       double lt_q = CUDART_NAN;
       if (decide) {            // the model-side finish of the evaluation (finalize_eval), from the partial sums
         double pr = 0.0;
         for (int g = 0; g < CO_GROUPS; g++) pr += s_sum[g][1][lc];
-        const double ll = sum_part(part, ns, d, d, Cp, c);
+        const double ll = (ns == 1) ? ll_ld : sum_part(part, ns, d, d, Cp, c);
         if (linlog) {
           bool oos = F.oos;
           const double a1 = 0.0 + pr;
@@ -573,65 +595,68 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
         atomicAdd(W.remaining, 1);
         begin = true;
       } else if (mode == CM_INTERIOR) {
-        const int leap = W.leap[c] + 1;
+        const int leap = lp + 1;
         W.leap[c] = leap;
-        W.need_ll[c] = (leap + 1 == W.nleaps_cur[c]) ? 1 : 0;
+        W.need_ll[c] = (leap + 1 == nlc) ? 1 : 0;
       } else if (mode == CM_INIT) {
         if (!isfinite(lt_q)) {     // "Initial values out of model support" RWM.jl:55 MALA.jl:85 HMC.jl:121 HMCDA.jl:88
           W.status[c] = 1; W.phase[c] = PH_DONE; atomicSub(W.remaining, 1);
         } else {
           W.status[c] = 0;
-          W.cur_lt[c] = lt_q;
+          W.cur_lt[c] = lt_q; cur_lt_now = lt_q;
           if (W.init_lt) W.init_lt[c] = lt_q;
           acc = true;              // "accept" the initial point: stage B3 copies q (and its gradient) into the state
-          if (kind == MCMCGPU_HMCDA && !W.restore_da) { W.da_leapstep[c] = 1.0; W.da_dual[c] = 1.0; W.da_dualH[c] = 0.0; }   // HMCDA.jl:90-94
+          if (kind == MCMCGPU_HMCDA && !W.restore_da) {                      // HMCDA.jl:90-94
+            W.da_leapstep[c] = 1.0; W.da_dual[c] = 1.0; W.da_dualH[c] = 0.0;
+            da_ls_ld = 1.0; da_dual_ld = 1.0; da_dualH_ld = 0.0;
+          }
           if (S.tuner_on) { W.tn_step[c] = S.scale; W.tn_nleaps[c] = S.nleaps; W.tn_acc[c] = 0; W.tn_prop[c] = 0; }
           i = W.step0 + 1;
           begin = true;
         }
       } else if (mode == CM_RWM) {                                       // RWM.jl:62-70
-        const double ratio = lt_q - W.cur_lt[c];
+        const double ratio = lt_q - cur_lt_ld;
         acc = ratio > 0 || ratio > log_lean_normal(uniform(i));
-        if (acc) W.cur_lt[c] = lt_q;
+        if (acc) { W.cur_lt[c] = lt_q; cur_lt_now = lt_q; }
         stored = true; st_eps = CUDART_NAN; st_nl = 0;
       } else if (mode == CM_MALA) {                                      // MALA.jl:103-118
         double qno = 0.0, qon = 0.0;
         for (int g = 0; g < CO_GROUPS; g++) { qno += s_sum[g][0][lc]; qon += s_sum[g][2][lc]; }
-        const double ratio = lt_q + qon - W.cur_lt[c] - qno;             // :107
+        const double ratio = lt_q + qon - cur_lt_ld - qno;               // :107
         acc = ratio > 0 || ratio > log_lean_normal(uniform(i));          // :108
-        if (acc) { W.cur_lt[c] = lt_q; if (S.tuner_on) W.tn_acc[c] += 1; }
+        if (acc) { W.cur_lt[c] = lt_q; cur_lt_now = lt_q; if (S.tuner_on) W.tn_acc[c] += 1; }
         stored = true; st_eps = eps_cur; st_nl = 0;
       } else if (mode == CM_FINAL) {                                     // HMC.jl:154 / HMCDA.jl:120-121
         double mm = 0.0;
         for (int g = 0; g < CO_GROUPS; g++) mm += s_sum[g][0][lc];
         const double H = -lt_q + 0.5 * mm;                               // update! HMC.jl:91
-        const double e = exp(W.H0[c] - H);
+        const double e = exp(H0_ld - H);
         const double u = uniform(i);
         double pacc = 0.0;
         if (kind == MCMCGPU_HMCDA) { pacc = isnan(e) ? 0.0 : (e < 1.0 ? e : 1.0); acc = u < pacc; }
         else acc = u < e;
-        if (acc) { W.cur_lt[c] = lt_q; if (S.tuner_on) W.tn_acc[c] += 1; }
-        stored = true; st_eps = eps_cur; st_nl = W.nleaps_cur[c];
+        if (acc) { W.cur_lt[c] = lt_q; cur_lt_now = lt_q; if (S.tuner_on) W.tn_acc[c] += 1; }
+        stored = true; st_eps = eps_cur; st_nl = nlc;
         if (kind == MCMCGPU_HMCDA) {
           if (i < burnin) {                                               // HMCDA.jl:133-138
             const double fi = (double)i;
             double eta = 1.0 / (fi + S.t0);
-            const double dualH = (1.0 - eta) * W.da_dualH[c] + eta * (S.rate - pacc);
+            const double dualH = (1.0 - eta) * da_dualH_ld + eta * (S.rate - pacc);
             const double ls = exp(log(10.0 * 1.0) - sqrt(fi) * dualH / S.shrinkage);
             eta = pow(fi, -S.step);
-            W.da_dual[c] = exp((1.0 - eta) * log(W.da_dual[c]) + eta * log(ls));
-            W.da_dualH[c] = dualH; W.da_leapstep[c] = ls;
+            W.da_dual[c] = exp((1.0 - eta) * log(da_dual_ld) + eta * log(ls));
+            W.da_dualH[c] = dualH; W.da_leapstep[c] = ls; da_ls_ld = ls;
           } else {
-            W.da_leapstep[c] = W.da_dual[c];                              // :140
+            W.da_leapstep[c] = da_dual_ld; da_ls_ld = da_dual_ld;         // :140
           }
         }
       }
       if (stored) {
         if (in_range(i, R.first, R.step, R.last)) {                       // SerialMC.jl:49-66
-          const int64_t k = W.kept[c];
+          const int64_t k = kept_ld;
           s_k[lc] = k;
           W.accept[k * Cp + c] = acc ? 1 : 0;
-          if (W.logtarget) W.logtarget[k * Cp + c] = W.cur_lt[c];
+          if (W.logtarget) W.logtarget[k * Cp + c] = cur_lt_now;
           if (W.eps) W.eps[k * Cp + c] = st_eps;
           if (W.nleaps) W.nleaps[k * Cp + c] = st_nl;
           W.kept[c] = k + 1;
@@ -653,7 +678,7 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
         W.istep[c] = i;
         if (i > R.last) {
           W.phase[c] = PH_DONE;
-          if (W.final_eps) W.final_eps[c] = (kind == MCMCGPU_HMCDA) ? W.da_leapstep[c] : (S.tuner_on ? W.tn_step[c] : S.scale);
+          if (W.final_eps) W.final_eps[c] = (kind == MCMCGPU_HMCDA) ? da_ls_ld : (S.tuner_on ? W.tn_step[c] : S.scale);
           atomicSub(W.remaining, 1);
         } else if (i > W.step_limit) {
           W.phase[c] = PH_PAUSE;
@@ -661,7 +686,7 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
         } else {
           double eps = S.scale; int nl = 0;
           if (kind == MCMCGPU_HMCDA) {
-            eps = W.da_leapstep[c];
+            eps = da_ls_ld;
             double r = round(S.len / eps);                                // HMCDA.jl:104
             if (!(r >= 1.0)) r = 1.0;
             if (r > (double)S.max_leaps) r = (double)S.max_leaps;
@@ -754,7 +779,7 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
     if (hmc_like) {
       double mm = 0.0;
       for (int g = 0; g < CO_GROUPS; g++) mm += s_sum[g][0][lc];
-      W.H0[c] = -W.cur_lt[c] + 0.5 * mm;                                 // update! HMC.jl:91
+      W.H0[c] = -cur_lt_now + 0.5 * mm;                                  // update! HMC.jl:91 (cur_lt_now: this thread's stage B2)
       W.leap[c] = 0; W.nleaps_cur[c] = s_nl[lc];
       W.need_ll[c] = (s_nl[lc] == 1) ? 1 : 0;
       W.phase[c] = PH_LEAP;
