@@ -512,8 +512,11 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
             constexpr bool SM = decltype(sm_tag)::value, MASK = decltype(mask_tag)::value;
             constexpr int STR = SM ? PS_N : PROBIT_NINT;
             const unsigned long long* T = SM ? ptab - PS_K0 : probit_tab;
-            if (a.need_ll == nullptr && a.need_grad) {
-              // every chain needs value and gradient on every wave of this run (MALA; the first wave of any run)
+            if (a.need_grad && need_ll) {
+              // value and gradient (MALA; the first wave of any run; the last leapfrog of a trajectory for the warps that hold
+              // such a chain).  need_ll is a per-WARP flag and a chain's numbers must not depend on the phase of its
+              // neighbours: w comes out of the same instruction sequence here and in the gradient-only branch below
+              // (test_regression_chain_sharding_invariance, test_unsplit_likelihood_fuses_the_leapfrog compare bit for bit)
 #pragma unroll
               for (int n = 0; n < NR; n++)
 #pragma unroll
@@ -525,32 +528,27 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
                   if (MASK && (rowbase + lr) >= N) l = 0.0;
                   ll1 += l;
                 }
-            } else {
-              // the same instructions produce w whether or not the value is wanted (need_ll is a per-WARP flag: a chain's
-              // numbers must not depend on the phase of its neighbours)
-              if (a.need_grad) {
+            } else if (a.need_grad) {
 #pragma unroll
-                for (int n = 0; n < NR; n++)
+              for (int n = 0; n < NR; n++)
 #pragma unroll
-                  for (int s = 0; s < 2; s++) {
-                    const int i = 2 * n + s;
-                    double l, w;
-                    probit_eval<SM, STR, false, true>(T, zv[i], l, w);
-                    acc[n][s] = __hiloint2double(__double2hiint(w) ^ (int)((neg << (32 - 2 * NR + i)) & 0x80000000u), __double2loint(w));
-                  }
-              }
-              if (need_ll) {
+                for (int s = 0; s < 2; s++) {
+                  const int i = 2 * n + s;
+                  double l, w;
+                  probit_eval<SM, STR, false, true>(T, zv[i], l, w);
+                  acc[n][s] = __hiloint2double(__double2hiint(w) ^ (int)((neg << (32 - 2 * NR + i)) & 0x80000000u), __double2loint(w));
+                }
+            } else if (need_ll) {
 #pragma unroll
-                for (int n = 0; n < NR; n++)
+              for (int n = 0; n < NR; n++)
 #pragma unroll
-                  for (int s = 0; s < 2; s++) {
-                    const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-                    double l, w;
-                    probit_eval<SM, STR, true, false>(T, zv[i], l, w);
-                    if (MASK && (rowbase + lr) >= N) l = 0.0;
-                    ll1 += l;
-                  }
-              }
+                for (int s = 0; s < 2; s++) {
+                  const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+                  double l, w;
+                  probit_eval<SM, STR, true, false>(T, zv[i], l, w);
+                  if (MASK && (rowbase + lr) >= N) l = 0.0;
+                  ll1 += l;
+                }
             }
           };
           if (rowbase + K1_ROWS <= N) {
