@@ -386,6 +386,12 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
   for (int jb = 0; jb < DK; jb++) { G[jb][0] = 0.0; G[jb][1] = 0.0; }
   double ll1 = 0.0, ll2 = 0.0;
   int nbad = 0;
+  // linear family: sum of squared standardised residuals and the number of real rows this lane has seen; the constant
+  // -(ln sqrt(2 pi) + log sd) per row is added once at the end
+  double lin_s2 = 0.0;
+  int lin_rows = 0;
+  const double lin_inv_sd = (FAM == MCMCGPU_FAM_LINEAR) ? 1.0 / a.hyper[1] : 0.0;
+  const double lin_inv_var = (FAM == MCMCGPU_FAM_LINEAR) ? 1.0 / (a.hyper[1] * a.hyper[1]) : 0.0;
   const double hy[4] = {a.hyper[0], a.hyper[1], a.hyper[2], a.hyper[3]};
   const int64_t N = a.P.N;
 
@@ -427,6 +433,31 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
       }
       // ---- epilogue: link function on this lane's 2*NR (row, chain) elements ----
       bool done = false;
+      if (FAM == MCMCGPU_FAM_LINEAR && a.debug == 0) {
+        // examples/linear_regression.jl:16-17: resid = Y - X*vars; resid ~ Normal(0, sd).  Four FP64 instructions per
+        // element (every math instruction of the link adds to the DMMA time, see the probit link): the two divisions by sd
+        // and sd^2 are multiplications by reciprocals formed once per thread (<= 2 ulp from the quotients; the sums of this
+        // kernel are compared with the reference within a tolerance by construction), the log-likelihood is carried as
+        // sum z^2 plus a row count, and padded rows (y = 0, X = 0) contribute exact zeros to both sums.
+#pragma unroll
+        for (int n = 0; n < NR; n++)
+#pragma unroll
+          for (int s = 0; s < 2; s++) {
+            const int lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+            const double resid = ys[lr] - acc[n][s];
+            const double z = resid * lin_inv_sd;
+            lin_s2 = fma(z, z, lin_s2);
+            acc[n][s] = resid * lin_inv_var;                 // MCMCDerivRules.jl:57 through resid = Y - X*vars
+          }
+        if (rowbase + K1_ROWS <= N) lin_rows += 2 * NR;
+        else {
+#pragma unroll
+          for (int n = 0; n < NR; n++)
+#pragma unroll
+            for (int s = 0; s < 2; s++) lin_rows += ((rowbase + rg * 8 * NR + 8 * n + (s ? row2b : row2a)) < N) ? 1 : 0;
+        }
+        done = true;
+      }
       if (FAM == MCMCGPU_FAM_LOGISTIC && a.debug == 0) {
         // all 2*NR elements stage by stage, so their dependency chains interleave.  The same arithmetic is used whether
         // or not the log-likelihood is wanted (need_ll is a per-WARP flag: a chain's numbers must not depend on the
@@ -617,6 +648,10 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
     }
   }
 
+  if (FAM == MCMCGPU_FAM_LINEAR && a.debug == 0) {
+    ll1 = -fma(0.5, lin_s2, (double)lin_rows * (MG_LN_SQRT_2PI + a.hyper[3]));     // hyper[3] = log(noise_sd)
+    nbad = isfinite(lin_s2) ? 0 : 1;                   // a non-finite term anywhere makes the sum of squares non-finite
+  }
   // ---- write this split's partial sums ----
   // quad reduction of the scalar sums (the 4 lanes of a quad hold different rows of the same chain)
   ll1 += __shfl_xor_sync(0xffffffffu, ll1, 1); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 2);
