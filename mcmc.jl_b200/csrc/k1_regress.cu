@@ -464,12 +464,15 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
         // phase of its neighbours, or sharding / stepwise execution would change the draws).  acc holds x = sign * eta
         // (sign folded into beta).  15 FP64 instructions per element on a gradient wave: exp 10, 1 + e, reciprocal 3,
         // e * p; the response test, the support test and the sign of r are integer work on the bit patterns.
-        bool fast = true;
+        // (Integer work is kept to a minimum as well -- every math instruction of the link adds to the DMMA time: one running
+        // maximum of |x| serves the range test and tells whether any element can be out of support at all; the padded rows of
+        // the last tile are masked on a path of their own.)
+        unsigned amax = 0u;
 #pragma unroll
         for (int n = 0; n < NR; n++)
 #pragma unroll
-          for (int s = 0; s < 2; s++)
-            fast = fast && ((__double2hiint(acc[n][s]) & 0x7fffffff) < 0x4085E000);   // |x| < 700 and not NaN
+          for (int s = 0; s < 2; s++) amax = max(amax, (unsigned)__double2hiint(acc[n][s]) & 0x7fffffffu);
+        const bool fast = amax < 0x4085E000u;                                         // |x| < 700 and not NaN
         if (fast) {
           double ev[2 * NR], pv[2 * NR];
 #pragma unroll
@@ -480,6 +483,18 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
           for (int i = 0; i < 2 * NR; i++) pv[i] = rcp_cubic(1.0 + ev[i]);
           const int sbit = __double2hiint(hy[1]) & 0x80000000;      // sign bit of the link's sign convention
           unsigned y1mask = 0u;
+          // support: log(p) is finite for |x| < 700; log(1 - p) is finite unless 1 + e rounds to 1, i.e.
+          // x <= ln 2^-53 = -36.736800569677101 (padded rows have x = 0): only looked for when some |x| is that large
+          if (amax >= 0x40425E4Fu) {
+#pragma unroll
+            for (int n = 0; n < NR; n++)
+#pragma unroll
+              for (int s = 0; s < 2; s++) {
+                const int lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+                const bool y1 = (__double_as_longlong(ys[lr]) << 1) != 0;
+                nbad += (!y1 && (unsigned long long)__double_as_longlong(acc[n][s]) >= 0xC0425E4F7B2737FAull) ? 1 : 0;
+              }
+          }
 #pragma unroll
           for (int n = 0; n < NR; n++)
 #pragma unroll
@@ -487,9 +502,6 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
               const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
               const long long yb = __double_as_longlong(ys[lr]);
               const bool y1 = (yb << 1) != 0;                        // y != 0.0 (NaN counts as a success, as != does)
-              // support: log(p) is finite for |x| < 700; log(1 - p) is finite unless 1 + e rounds to 1, i.e.
-              // x <= ln 2^-53 = -36.736800569677101 (padded rows have x = 0)
-              nbad += (!y1 && (unsigned long long)__double_as_longlong(acc[n][s]) >= 0xC0425E4F7B2737FAull) ? 1 : 0;
               y1mask |= y1 ? (1u << i) : 0u;
               // r = y ? (-sign) (e p) : sign p  (the reference's AD chain in closed form, see link<>): magnitude, then sign bit
               const double ep = ev[i] * pv[i];
@@ -498,16 +510,21 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) k1_kernel(const K1Args a) {
               acc[n][s] = __hiloint2double(__double2hiint(mag) ^ flip, __double2loint(mag));
             }
           if (need_ll) {                                                        // warp-uniform; kept out of the straight-line code above
+            auto loglik = [&](auto mask_tag) {
+              constexpr bool MASK = decltype(mask_tag)::value;
 #pragma unroll
-            for (int n = 0; n < NR; n++)
+              for (int n = 0; n < NR; n++)
 #pragma unroll
-              for (int s = 0; s < 2; s++) {
-                const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
-                const bool y1 = (y1mask >> i) & 1u;
-                const double arg = y1 ? pv[i] : 1.0 - pv[i];                    // Bernoulli: p1, or p0 = 1 - p1 by subtraction
-                const double lg = log_tab129(arg, ltab);
-                ll1 += ((rowbase + lr) < N) ? lg : 0.0;                         // padded rows contribute an exact zero
-              }
+                for (int s = 0; s < 2; s++) {
+                  const int i = 2 * n + s, lr = rg * 8 * NR + 8 * n + (s ? row2b : row2a);
+                  const bool y1 = (y1mask >> i) & 1u;
+                  const double arg = y1 ? pv[i] : 1.0 - pv[i];                  // Bernoulli: p1, or p0 = 1 - p1 by subtraction
+                  const double lg = log_tab129(arg, ltab);
+                  if (MASK) ll1 += ((rowbase + lr) < N) ? lg : 0.0;             // padded rows contribute an exact zero
+                  else ll1 += lg;
+                }
+            };
+            if (rowbase + K1_ROWS <= N) loglik(std::false_type{}); else loglik(std::true_type{});
           }
           done = true;
         }
