@@ -38,6 +38,12 @@ constexpr int K1_STAGES = 2;
 #ifndef K1_PROBIT_SMALL_CTAS
 #define K1_PROBIT_SMALL_CTAS 2
 #endif
+#ifndef K1_OTHER_SMALL_CTAS
+#define K1_OTHER_SMALL_CTAS 3      // linear, logistic at d <= 32
+#endif
+#ifndef K1_OTHER_SMALL_STAGES
+#define K1_OTHER_SMALL_STAGES 2
+#endif
 constexpr int K1_NR = 4;          // 8-row groups per phase-1 pass (independent DMMA accumulator chains)
 constexpr int PH_IDLE_K1 = 98;  // phases >= PH_PAUSE (98) have no pending evaluation (transition.h)
 constexpr int PH_LEAP_K1 = 3;   // PH_LEAP (transition.h)
@@ -809,7 +815,7 @@ int k1_choose_splits(const K1Pack& P, int64_t Cp, int device, int family) {
   int sms = 148;
   if (device < 0) cudaGetDevice(&device);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  const int64_t small_ctas = (family == MCMCGPU_FAM_PROBIT) ? K1_PROBIT_SMALL_CTAS : 3;
+  const int64_t small_ctas = (family == MCMCGPU_FAM_PROBIT) ? K1_PROBIT_SMALL_CTAS : K1_OTHER_SMALL_CTAS;
   const int64_t slots = (P.DK <= K1_MAX_DK_3CTA ? small_ctas : (P.DK <= K1_MAX_DK_2CTA ? 2LL : 1LL)) * sms;
   int64_t maxs = P.ntiles / 8;
   if (maxs < 1) maxs = 1;
@@ -858,8 +864,8 @@ static cudaError_t launch_fd(const K1Args& a, cudaStream_t st) {
   // three tiles of slack between the fastest and the slowest warp -- 35.0 vs 35.1 ms per wave: the ring is not the limiter.)
   constexpr bool SMALL = (DK <= K1_MAX_DK_3CTA);
   constexpr bool PSMALL = SMALL && (FAM == MCMCGPU_FAM_PROBIT);
-  constexpr int CTAS = PSMALL ? K1_PROBIT_SMALL_CTAS : (SMALL ? 3 : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1));
-  return launch_shape<FAM, DK, K1_WARPS, PSMALL ? K1_PROBIT_SMALL_STAGES : K1_STAGES, CTAS>(a, st);
+  constexpr int CTAS = PSMALL ? K1_PROBIT_SMALL_CTAS : (SMALL ? K1_OTHER_SMALL_CTAS : ((DK <= K1_MAX_DK_2CTA) ? 2 : 1));
+  return launch_shape<FAM, DK, K1_WARPS, PSMALL ? K1_PROBIT_SMALL_STAGES : (SMALL ? K1_OTHER_SMALL_STAGES : K1_STAGES), CTAS>(a, st);
 }
 
 template <int FAM>
