@@ -208,6 +208,49 @@ def test_generated_link_tables_are_reproducible():
         assert abs(mp.mpf(gl.log_dev(float(x), R, L)) - ref) <= mp.mpf(3e-16) * abs(ref) + mp.mpf(3e-18)
 
 
+def test_probit_table_is_reproducible():
+    """csrc/probit_table.h holds what tools/gen_probit_table.py computes (log Phi and phi/Phi at the grid points in double,
+    the float pair of the cubic / quartic tail), and the generator's operation-by-operation replay of K1's probit link
+    (probit_eval, k1_regress.cu: grid index in float, W', W'' from W' = -W (z + W) in double, tail in float) is accurate to
+    the figures its header states: relative for z < 0, absolute for z >= 0."""
+    import importlib.util
+    import re
+    import struct
+    import mpmath as mp
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_probit_table", os.path.join(root, "tools", "gen_probit_table.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    txt = open(os.path.join(root, "mcmc.jl_b200", "csrc", "probit_table.h")).read()
+    assert f"#define PROBIT_INV_W {g.INV_W}" in txt and f"#define PROBIT_ZMAX {g.ZMAX}" in txt
+    words = [int(w, 16) for w in re.findall(r"0x([0-9a-f]{16})ull", txt)]
+    nint = 2 * g.ZMAX * g.INV_W + 1
+    assert len(words) == 3 * nint
+    as_double = lambda w: struct.unpack("<d", struct.pack("<Q", w))[0]
+    as_floats = lambda w: struct.unpack("<ff", struct.pack("<Q", w))
+    rng = np.random.default_rng(3)
+    ks = np.concatenate([[0, 1, nint // 2, nint - 1], rng.integers(0, nint, 40)])
+    tab = {}
+    for k in ks:
+        k = int(k)
+        e = g.entry(k)
+        assert (as_double(words[k]), as_double(words[nint + k])) == e[:2], k
+        assert as_floats(words[2 * nint + k]) == (np.float32(e[2]), np.float32(e[3])), k
+        tab[k] = e
+    # the replay on the header's own numbers, at points of the checked intervals
+    for k, e in tab.items():
+        c = -g.ZMAX + k / g.INV_W
+        for t in (0.0, 0.2 / g.INV_W, -0.49 / g.INV_W, 0.4999 / g.INV_W):
+            z = c + t
+            if not (-36.9 < z < 36.9) or int(np.rint(np.float32(z) * np.float32(g.INV_W))) + g.ZMAX * g.INV_W != k:
+                continue
+            f, w = g.device_eval(tab, z)
+            rf, rw = g.F(mp.mpf(z)), g.W(mp.mpf(z))
+            if z < 0:
+                assert abs((mp.mpf(f) - rf) / rf) < 4e-16 and abs((mp.mpf(w) - rw) / rw) < 2e-15, (z, f, w)
+            else:
+                assert abs(mp.mpf(f) - rf) < 3e-16 and abs(mp.mpf(w) - rw) < 3e-15, (z, f, w)
+
+
 def test_handle_lifetimes_children_first(capi, monkeypatch):
     """runs, models and contexts are released children-first -- by close(), by `with`, and by garbage
     collection -- and a closed parent leaves no dangling child handle (checked against a recording fake of the library)."""
