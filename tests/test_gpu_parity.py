@@ -69,6 +69,16 @@ def test_out_of_support_semantics(O, capi, ctx):
     lt, g = dm.logtarget_grad(np.array([[-1.0, 1, 1], [5, 2.5, 1], [5, 1, 21], [20, 0.1, 10]]))
     assert np.all(lt[:3] == -np.inf) and np.all(g[:3] == 0) and np.isfinite(lt[3])
     dm.close()
+    # linear: the four-instruction link carries sum z^2 and a row count; a non-finite residual anywhere must still give (-Inf, zeros)
+    Xl, yl, hyl, _ = make_regression("linear", 70, 3, 4)             # 70 rows: a ragged last tile
+    om, dm = O.Model("linear", 3, Xl, yl, hyl), capi.DeviceModel(ctx, "linear", 3, Xl, yl, hyl)
+    Bl = np.array([[np.nan, 0.0, 0.0], [1e200, 0.0, 0.0], [0.0, np.inf, 0.0], [0.3, -0.2, 0.1]])
+    lt, g = dm.logtarget_grad(Bl)
+    assert np.all(lt[:3] == -np.inf) and np.all(g[:3] == 0) and np.isfinite(lt[3]) and np.all(np.isfinite(g[3]))
+    for c in range(4):
+        olt, og = om.evalallg(Bl[c])
+        assert (olt == lt[c] or abs(olt - lt[c]) <= 1e-12 * abs(olt)) and np.allclose(og, g[c], rtol=1e-12, atol=0), c
+    dm.close()
     Xp, yp, hyp, _ = make_regression("probit", 30, 2, 2)
     dm = capi.DeviceModel(ctx, "probit", 2, Xp, yp, hyp)
     lt, _ = dm.logtarget_grad(np.array([[1e200, 1e200]]))
