@@ -872,7 +872,7 @@ template <int FAM>
 static cudaError_t launch_f(const K1Args& a, cudaStream_t st) {
   switch (a.P.DK) {
     case 3: return launch_fd<FAM, 3>(a, st);
-#ifndef K1_ONLY_DK3
+#ifndef K1_ONLY_DK3        // experiments: -DK1_ONLY_DK3 builds the d <= 24 kernels only (seconds instead of minutes per variant)
     case 1: return launch_fd<FAM, 1>(a, st);
     case 2: return launch_fd<FAM, 2>(a, st);
     case 4: return launch_fd<FAM, 4>(a, st);
