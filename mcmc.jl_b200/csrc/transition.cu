@@ -97,22 +97,6 @@ __device__ __forceinline__ double fin_grad(const EvalFin& f, const ModelDev& M, 
   return part[j * Cp + c];
 }
 
-// fin_grad from values already at hand (one split): qj = q[j][c], pj = part[j][c]; the same operations in the same order
-__device__ __forceinline__ double fin_grad_of(const EvalFin& f, const ModelDev& M, double qj, double pj) {
-  if (f.fam == MCMCGPU_FAM_LINEAR || f.fam == MCMCGPU_FAM_LOGISTIC) {
-    if (f.oos) return 0.0;
-    double psd = M.hyper[0];
-    return pj + div_by_var(0.0 - qj, psd * psd);
-  } else if (f.fam == MCMCGPU_FAM_PROBIT) {
-    return pj - div_by_var(qj, f.ginv);
-  }
-  return pj;
-}
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gmem_src) : "memory");
-}
-
 // One chain's share of a wave.  Returns the number of evaluations it consumed (0 or 1).  `interior_done`: the chain is in the
 // middle of a trajectory and its momentum / position update has already been made element-parallel by the caller
 // (transition_kernel, stage A); only the per-chain counters are left.
@@ -454,8 +438,6 @@ __global__ void __launch_bounds__(TR_CHAINS * TR_GROUPS) transition_kernel(const
 // (one thread per chain walking all d parameters took 1.01 ms per decision wave at 102 400 chains x d = 100: every
 // Box-Muller pair, division and store of a chain in sequence.)
 constexpr int CO_CHAINS = 64, CO_GROUPS = 8, CO_UNROLL = 3;
-constexpr int CO_NPB = 2;                                   // pairs per cp.async chunk of stage B3 (two chunks in flight)
-constexpr size_t CO_STAGE_BYTES = (size_t)2 * CO_NPB * 4 * CO_CHAINS * CO_GROUPS * sizeof(double);
 enum { CM_NONE = 0, CM_INTERIOR, CM_FINAL, CM_MALA, CM_RWM, CM_INIT, CM_RESUME };
 
 __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kernel(const WaveArgs W) {
@@ -463,7 +445,6 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
   __shared__ double s_eps[CO_CHAINS];                    // step size of the step being started
   __shared__ long long s_k[CO_CHAINS], s_i[CO_CHAINS];   // kept index of the step just decided (-1: not kept); step being started
   __shared__ int s_acc[CO_CHAINS], s_begin[CO_CHAINS], s_nl[CO_CHAINS];
-  extern __shared__ __align__(16) double co_stage[];    // stage B3: [2 chunks][CO_NPB pairs][4 values][thread]
   const RunnerDev& R = W.R;
   const SamplerDev& S = W.S;
   const ModelDev& M = W.M;
@@ -732,104 +713,59 @@ __global__ void __launch_bounds__(CO_CHAINS * CO_GROUPS, 2) transition_coop_kern
     const int64_t inext = s_i[lc];
     const double sq = (kind == MCMCGPU_MALA) ? sqrt(eps) : 0.0;
     const uint64_t gchain = (W.chain_ids && c < R.C) ? (uint64_t)W.chain_ids[c] : (uint64_t)(R.chain_offset + c);
-    // The state this stage reads -- (q, X'r) of an accepted proposal or (cur_pars, cur_grad) of a rejected one -- is brought
-    // in by cp.async, CO_NPB pairs per chunk and one chunk ahead of its use, into slots of shared memory private to the
-    // thread: as plain loads the compiler must issue each pair's loads after the previous pair's stores (q is read and
-    // written), one dependent round trip per pair with four loads in flight per thread.  Different pairs touch different
-    // elements, so reading a later pair early is safe.  (ns > 1: the partial sums are spread over splits; plain loads.)
-    const bool pre = (ns == 1);
-    const double* srcA = acc ? q : W.cur_pars;
-    const double* srcB = acc ? part : W.cur_grad;
-    const int64_t nmine = (npairs > grp) ? (npairs - grp + CO_GROUPS - 1) / CO_GROUPS : 0;     // pairs of this thread
-    const int64_t nchunks = (nmine + CO_NPB - 1) / CO_NPB;
-    auto slot = [&](int buf, int u, int v) -> double* {                                          // v: 0,1 = A of both elements; 2,3 = B
-      return co_stage + ((size_t)((buf * CO_NPB + u) * 4 + v) * (CO_CHAINS * CO_GROUPS) + threadIdx.x);
-    };
-    auto issue = [&](int64_t ch) {
-      if (pre) {
-        const int buf = (int)(ch & 1);
-#pragma unroll
-        for (int u = 0; u < CO_NPB; u++) {
-          const int64_t k = grp + (ch * CO_NPB + u) * CO_GROUPS;
-#pragma unroll
-          for (int t2 = 0; t2 < 2; t2++) {
-            const int64_t j = 2 * k + t2;
-            if (k < npairs && j < d) {
-              cp_async8(slot(buf, u, t2), srcA + j * Cp + c);
-              if (need_grad_state) cp_async8(slot(buf, u, 2 + t2), srcB + j * Cp + c);
-            }
-          }
+    for (int64_t k = grp; k < npairs; k += CO_GROUPS) {
+      double z0 = 0.0, z1 = 0.0;
+      if (begin) {
+        if (W.inj_normals) {
+          z0 = W.inj_normals[(inext * d + 2 * k) * Cp + c];
+          if (2 * k + 1 < d) z1 = W.inj_normals[(inext * d + 2 * k + 1) * Cp + c];
+        } else {
+          philox_normal_pair(R.seed, gchain, (uint32_t)inext, (uint32_t)k, z0, z1);
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (nchunks > 0) issue(0);
-    for (int64_t ch = 0; ch < nchunks; ch++) {
-      if (ch + 1 < nchunks) { issue(ch + 1); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-      else asm volatile("cp.async.wait_group 0;" ::: "memory");
-      const int buf = (int)(ch & 1);
+      // both elements of the pair: every load first, then every store (the stores go to arrays the loads read from as far
+      // as the compiler knows: interleaved, each load is issued only after the preceding store, four round trips per pair)
+      double pjv[2] = {0.0, 0.0}, gjv[2] = {0.0, 0.0};
 #pragma unroll
-      for (int u = 0; u < CO_NPB; u++) {
-        const int64_t k = grp + (ch * CO_NPB + u) * CO_GROUPS;
-        if (k >= npairs) break;
-        double z0 = 0.0, z1 = 0.0;
+      for (int t2 = 0; t2 < 2; t2++) {
+        const int64_t j = 2 * k + t2;
+        if (j >= d) break;
+        if (acc) {
+          pjv[t2] = q[j * Cp + c];
+          if (need_grad_state) gjv[t2] = fin_grad(F, M, q, part, ns, Cp, c, j);
+        } else {
+          pjv[t2] = W.cur_pars[j * Cp + c];
+          if (need_grad_state) gjv[t2] = W.cur_grad[j * Cp + c];
+        }
+      }
+#pragma unroll
+      for (int t2 = 0; t2 < 2; t2++) {
+        const int64_t j = 2 * k + t2;
+        if (j >= d) break;
+        const double pj = pjv[t2], gj = gjv[t2];
+        if (acc) {
+          W.cur_pars[j * Cp + c] = pj;
+          if (need_grad_state) W.cur_grad[j * Cp + c] = gj;
+        }
+        if (kk >= 0) {                    // the post-decision state is what is kept (SerialMC.jl:49-53)
+          W.samples[(kk * d + j) * Cp + c] = pj;
+          if (W.grads) W.grads[(kk * d + j) * Cp + c] = need_grad_state ? gj : CUDART_NAN;
+        }
         if (begin) {
-          if (W.inj_normals) {
-            z0 = W.inj_normals[(inext * d + 2 * k) * Cp + c];
-            if (2 * k + 1 < d) z1 = W.inj_normals[(inext * d + 2 * k + 1) * Cp + c];
+          const double z = t2 ? z1 : z0;
+          if (kind == MCMCGPU_RWM) {
+            q[j * Cp + c] = pj + z * (W.scale[j] * S.scale);            // RWM.jl:52,59
+          } else if (kind == MCMCGPU_MALA) {
+            const double mean = pj + (eps / 2.0) * gj;                   // MALA.jl:98
+            q[j * Cp + c] = mean + sq * z;                               // :100
           } else {
-            philox_normal_pair(R.seed, gchain, (uint32_t)inext, (uint32_t)k, z0, z1);
-          }
-        }
-        // both elements of the pair: every load first, then every store
-        double pjv[2] = {0.0, 0.0}, gjv[2] = {0.0, 0.0};
-#pragma unroll
-        for (int t2 = 0; t2 < 2; t2++) {
-          const int64_t j = 2 * k + t2;
-          if (j >= d) break;
-          if (pre) {
-            pjv[t2] = *slot(buf, u, t2);
-            if (need_grad_state) {
-              const double b = *slot(buf, u, 2 + t2);
-              gjv[t2] = acc ? fin_grad_of(F, M, pjv[t2], b) : b;
-            }
-          } else if (acc) {
-            pjv[t2] = q[j * Cp + c];
-            if (need_grad_state) gjv[t2] = fin_grad(F, M, q, part, ns, Cp, c, j);
-          } else {
-            pjv[t2] = W.cur_pars[j * Cp + c];
-            if (need_grad_state) gjv[t2] = W.cur_grad[j * Cp + c];
-          }
-        }
-#pragma unroll
-        for (int t2 = 0; t2 < 2; t2++) {
-          const int64_t j = 2 * k + t2;
-          if (j >= d) break;
-          const double pj = pjv[t2], gj = gjv[t2];
-          if (acc) {
-            W.cur_pars[j * Cp + c] = pj;
-            if (need_grad_state) W.cur_grad[j * Cp + c] = gj;
-          }
-          if (kk >= 0) {                    // the post-decision state is what is kept (SerialMC.jl:49-53)
-            W.samples[(kk * d + j) * Cp + c] = pj;
-            if (W.grads) W.grads[(kk * d + j) * Cp + c] = need_grad_state ? gj : CUDART_NAN;
-          }
-          if (begin) {
-            const double z = t2 ? z1 : z0;
-            if (kind == MCMCGPU_RWM) {
-              q[j * Cp + c] = pj + z * (W.scale[j] * S.scale);            // RWM.jl:52,59
-            } else if (kind == MCMCGPU_MALA) {
-              const double mean = pj + (eps / 2.0) * gj;                   // MALA.jl:98
-              q[j * Cp + c] = mean + sq * z;                               // :100
-            } else {
-              double m = z;                                                // HMC.jl:136
-              mm_part += m * m;
-              m += (0.5 * gj) * eps;                                       // HMC.jl:95
-              double p = pj;
-              p += eps * m;                                                // HMC.jl:96
-              W.mom[j * Cp + c] = m;
-              q[j * Cp + c] = p;
-            }
+            double m = z;                                                // HMC.jl:136
+            mm_part += m * m;
+            m += (0.5 * gj) * eps;                                       // HMC.jl:95
+            double p = pj;
+            p += eps * m;                                                // HMC.jl:96
+            W.mom[j * Cp + c] = m;
+            q[j * Cp + c] = p;
           }
         }
       }
@@ -861,15 +797,7 @@ cudaError_t launch_transition(const WaveArgs& W, cudaStream_t st) {
   const bool regression = (W.M.family == MCMCGPU_FAM_LINEAR || W.M.family == MCMCGPU_FAM_LOGISTIC || W.M.family == MCMCGPU_FAM_PROBIT);
   if (regression && W.S.kind != MCMCGPU_RAM && W.rb == nullptr) {
     int blocks = (int)((W.R.C + CO_CHAINS - 1) / CO_CHAINS);
-    static bool attr_done[64] = {false};      // the attribute is per device
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-      cudaError_t e = cudaFuncSetAttribute(transition_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CO_STAGE_BYTES);
-      if (e != cudaSuccess) return e;
-      if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
-    transition_coop_kernel<<<blocks, CO_CHAINS * CO_GROUPS, CO_STAGE_BYTES, st>>>(W);
+    transition_coop_kernel<<<blocks, CO_CHAINS * CO_GROUPS, 0, st>>>(W);
     return cudaGetLastError();
   }
   int blocks = (int)((W.R.C + TR_CHAINS - 1) / TR_CHAINS);
