@@ -74,7 +74,7 @@ summarize('transition_r02', dict(command=full % ("transition_coop", 7, 2), cmd="
 summarize('stats_r02', dict(command=full % ("stats_", 4, 4), cmd="python tools/stats_probe.py imse",
                            kernel="stats_mean_kernel, stats_var_kernel<IMSE>, stats_gather_kernel, stats_more_warp_kernel", workload="65536 chains x 3 parameters x 9000 kept draws"))
 lines = {}
-for tag, f in (("default_n1", "bench_r2_final_n1"), ("default_n2", "bench_r2_n2"), ("default_n8", "bench_r2_n8"), ("reference_n1", "bench_r2_ref")):
+for tag, f in (("default_n1", "bench_r2_final_n1"), ("default_n2", "bench_r2_n2"), ("default_n4", "bench_r2_n4"), ("default_n8", "bench_r2_n8"), ("reference_n1", "bench_r2_ref")):
     pth = f'{G}/{f}.json'
     if not os.path.exists(pth): continue
     txt = open(pth).read().strip().splitlines()
